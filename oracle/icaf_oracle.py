@@ -1,0 +1,356 @@
+"""CPU oracle for the ICAFusion hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A plain fp32 restatement (torch CPU functional ops on a flat ``state_dict``) of the
+reference's two-stream CSPDarknet + DMFF forward.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this file; nothing under ``icafusion_b200/`` does, and the product path raises
+when its CUDA library is missing rather than falling back to this.
+
+Pinning: the reference has no tests / golden vectors of its own, so
+this oracle is pinned against *outputs of the reference itself*, executed in the build
+container by ``oracle/gen_golden.py`` (which imports /root/reference through
+``oracle/ref_shim.py``) and committed as ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` replays them.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+The restatement is deliberately *functional* (no nn.Module, no parameters objects): the
+reference's algorithm is "call these torch ops in this order with these tensors".
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+BN_EPS_MODEL = 1e-3      # utils/torch_utils.py:151  (initialize_weights sets eps on every BN of a built Model)
+BN_EPS_STANDALONE = 1e-5  # nn.BatchNorm2d default, stand-alone TransformerFusionBlock
+LN_EPS = 1e-5            # nn.LayerNorm default, models/common.py:631-632,723-724
+
+
+# ----------------------------------------------------------------------------------------
+# Conv / Bottleneck / C3 / SPPF            models/common.py:36-60, 184-194, 216-227, 252-267
+# ----------------------------------------------------------------------------------------
+def autopad(k: int, p=None) -> int:
+    """models/common.py:36-40"""
+    return k // 2 if p is None else p
+
+
+def conv_bn_silu(x, sd: SD, pre: str, k: int, s: int, p=None, act=True, bn_eps=BN_EPS_MODEL):
+    """`Conv.forward` (common.py:56-57) when `pre.bn.*` exists, else `Conv.fuseforward`
+    (common.py:59-60) on the BN-folded conv produced by fuse_conv_and_bn (torch_utils.py:182-202)."""
+    w = sd[pre + ".conv.weight"]
+    pad = autopad(k, p)
+    if pre + ".bn.weight" in sd:
+        y = F.conv2d(x, w, None, stride=s, padding=pad)
+        y = F.batch_norm(y, sd[pre + ".bn.running_mean"], sd[pre + ".bn.running_var"],
+                         sd[pre + ".bn.weight"], sd[pre + ".bn.bias"], False, 0.0, bn_eps)
+    else:
+        y = F.conv2d(x, w, sd[pre + ".conv.bias"], stride=s, padding=pad)
+    return F.silu(y) if act else y
+
+
+def bottleneck(x, sd: SD, pre: str, shortcut: bool, bn_eps=BN_EPS_MODEL):
+    """common.py:184-194  (c1 == c2 always inside C3, e=1.0)"""
+    y = conv_bn_silu(conv_bn_silu(x, sd, pre + ".cv1", 1, 1, bn_eps=bn_eps), sd, pre + ".cv2", 3, 1, bn_eps=bn_eps)
+    return x + y if shortcut else y
+
+
+def c3(x, sd: SD, pre: str, n: int, shortcut: bool, bn_eps=BN_EPS_MODEL):
+    """common.py:216-227"""
+    a = conv_bn_silu(x, sd, pre + ".cv1", 1, 1, bn_eps=bn_eps)
+    for j in range(n):
+        a = bottleneck(a, sd, f"{pre}.m.{j}", shortcut, bn_eps)
+    b = conv_bn_silu(x, sd, pre + ".cv2", 1, 1, bn_eps=bn_eps)
+    return conv_bn_silu(torch.cat((a, b), 1), sd, pre + ".cv3", 1, 1, bn_eps=bn_eps)
+
+
+def sppf(x, sd: SD, pre: str, k: int = 5, bn_eps=BN_EPS_MODEL):
+    """common.py:252-267"""
+    x = conv_bn_silu(x, sd, pre + ".cv1", 1, 1, bn_eps=bn_eps)
+    y1 = F.max_pool2d(x, k, 1, k // 2)
+    y2 = F.max_pool2d(y1, k, 1, k // 2)
+    y3 = F.max_pool2d(y2, k, 1, k // 2)
+    return conv_bn_silu(torch.cat([x, y1, y2, y3], 1), sd, pre + ".cv2", 1, 1, bn_eps=bn_eps)
+
+
+# ----------------------------------------------------------------------------------------
+# DMFF block                                                      models/common.py:569-891
+# ----------------------------------------------------------------------------------------
+def adaptive_pool(x, out_h: int, out_w: int, kind: str):
+    """AdaptivePool2d.forward, common.py:868-891 -- NOT nn.AdaptiveAvgPool2d semantics."""
+    H, W = x.shape[-2:]
+    if H > out_h or W > out_w:
+        sh, sw = H // out_h, W // out_w
+        kh, kw = H - (out_h - 1) * sh, W - (out_w - 1) * sw
+        if kind == "avg":
+            return F.avg_pool2d(x, (kh, kw), (sh, sw), 0)
+        return F.max_pool2d(x, (kh, kw), (sh, sw), 0)
+    return x
+
+
+def dmff_tokens(fea, sd: SD, pre: str, which: str, va: int, ha: int):
+    """common.py:817-823: LearnableWeights(avg, max) (:579-587) -> (B,N,C) + pos_emb."""
+    w1, w2 = sd[f"{pre}.{which}_coefficient.w1"], sd[f"{pre}.{which}_coefficient.w2"]
+    t = adaptive_pool(fea, va, ha, "avg") * w1 + adaptive_pool(fea, va, ha, "max") * w2
+    B, C, nh, nw = t.shape
+    return t.reshape(B, C, nh * nw).permute(0, 2, 1) + sd[f"{pre}.pos_emb_{which}"], nh, nw
+
+
+def _ln(x, sd: SD, pre: str):
+    return F.layer_norm(x, (x.shape[-1],), sd[pre + ".weight"], sd[pre + ".bias"], LN_EPS)
+
+
+def _lin(x, sd: SD, pre: str):
+    return F.linear(x, sd[pre + ".weight"], sd[pre + ".bias"])
+
+
+def cross_attention(r, i, sd: SD, pre: str, h: int = 8):
+    """CrossAttention.forward, common.py:641-687 (eval: dropouts are identity).
+    NOTE the crossing: RGB output = softmax(q_ir k_vis^T) v_vis (:670,682)."""
+    B, N, C = r.shape
+    d = C // h
+
+    def heads(t):  # (B,N,C) -> (B,h,N,d)
+        return t.reshape(B, N, h, d).permute(0, 2, 1, 3)
+
+    rn = _ln(r, sd, pre + ".LN1")                                              # :660
+    q_v, k_v, v_v = (heads(_lin(rn, sd, f"{pre}.{n}_proj_vis")) for n in ("que", "key", "val"))
+    inn = _ln(i, sd, pre + ".LN2")                                             # :665
+    q_i, k_i, v_i = (heads(_lin(inn, sd, f"{pre}.{n}_proj_ir")) for n in ("que", "key", "val"))
+    scale = 1.0 / math.sqrt(d)                                                 # :670-671
+    att_vis = torch.softmax(q_i @ k_v.transpose(-1, -2) * scale, -1)
+    att_ir = torch.softmax(q_v @ k_i.transpose(-1, -2) * scale, -1)
+    o_vis = (att_vis @ v_v).permute(0, 2, 1, 3).reshape(B, N, C)               # :682
+    o_ir = (att_ir @ v_i).permute(0, 2, 1, 3).reshape(B, N, C)                 # :684
+    return _lin(o_vis, sd, pre + ".out_proj_vis"), _lin(o_ir, sd, pre + ".out_proj_ir")
+
+
+def _mlp(x, sd: SD, pre: str):
+    """nn.Sequential(Linear, GELU(erf), Linear, Dropout), common.py:704-715"""
+    return _lin(F.gelu(_lin(x, sd, pre + ".0")), sd, pre + ".2")
+
+
+def cross_transformer_block(r, i, sd: SD, pre: str, loops: int = 1, h: int = 8):
+    """CrossTransformerBlock.forward, common.py:737-759.  Block-level LN2 feeds BOTH MLPs;
+    ln_input / ln_output / mlp / LN1 are dead parameters."""
+    c = [sd[f"{pre}.coefficient{j}.bias"] for j in range(1, 9)]
+    for _ in range(loops):
+        o_r, o_i = cross_attention(r, i, sd, pre + ".crossatt", h)
+        ra = r * c[0] + o_r * c[1]
+        ia = i * c[2] + o_i * c[3]
+        r = ra * c[4] + _mlp(_ln(ra, sd, pre + ".LN2"), sd, pre + ".mlp_vis") * c[5]
+        i = ia * c[6] + _mlp(_ln(ia, sd, pre + ".LN2"), sd, pre + ".mlp_ir") * c[7]
+    return r, i
+
+
+def dmff_block(rgb, ir, sd: SD, pre: str, va: int, ha: int, loops: int = 1, h: int = 8,
+               training: bool = False, bn_eps=BN_EPS_MODEL):
+    """TransformerFusionBlock.forward, common.py:809-865 (eval: bilinear; train: nearest)."""
+    B, C, H, W = rgb.shape
+    r, nh, nw = dmff_tokens(rgb, sd, pre, "vis", va, ha)
+    i, _, _ = dmff_tokens(ir, sd, pre, "ir", va, ha)
+    r, i = cross_transformer_block(r, i, sd, pre + ".crosstransformer.0", loops, h)
+    mode = "nearest" if training else "bilinear"
+
+    def up(t):
+        t = t.reshape(B, nh, nw, C).permute(0, 3, 1, 2)
+        return F.interpolate(t, size=(H, W), mode=mode)
+
+    cat = torch.cat([up(r) + rgb, up(i) + ir], 1)
+    return conv_bn_silu(cat, sd, pre + ".conv1x1_out", 1, 1, 0, bn_eps=bn_eps)
+
+
+# ----------------------------------------------------------------------------------------
+# Detect head + model walk                                  models/yolo_test.py:26-70,136-163
+# ----------------------------------------------------------------------------------------
+def detect(xs: Sequence[torch.Tensor], sd: SD, pre: str, nc: int, anchors, stride, training=False):
+    """Detect.forward, yolo_test.py:43-65. eval returns (cat(z), cat(logits), [x_i])."""
+    na = len(anchors[0]) // 2
+    no = nc + 5
+    a = torch.tensor(anchors, dtype=torch.float32).view(len(anchors), -1, 2)
+    z, lg, outs = [], [], []
+    for li, x in enumerate(xs):
+        x = F.conv2d(x, sd[f"{pre}.m.{li}.weight"], sd[f"{pre}.m.{li}.bias"])
+        bs, _, ny, nx = x.shape
+        x = x.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
+        outs.append(x)
+        if not training:
+            yv, xv = torch.meshgrid(torch.arange(ny), torch.arange(nx), indexing="ij")
+            grid = torch.stack((xv, yv), 2).view(1, 1, ny, nx, 2).float()
+            y = x.sigmoid()
+            xy = (y[..., 0:2] * 2.0 - 0.5 + grid) * stride[li]
+            wh = (y[..., 2:4] * 2) ** 2 * a[li].view(1, na, 1, 1, 2)
+            y = torch.cat((xy, wh, y[..., 4:]), -1)
+            z.append(y.view(bs, -1, no))
+            lg.append(x[..., 5:].reshape(bs, -1, no - 5))
+    return outs if training else (torch.cat(z, 1), torch.cat(lg, 1), outs)
+
+
+def make_divisible(x, divisor):
+    """utils/general.py:234-236"""
+    return math.ceil(x / divisor) * divisor
+
+
+def parse_layers(cfg: dict) -> List[dict]:
+    """The subset of parse_model (yolo_test.py:216-302) the Transfusion YAMLs exercise:
+    Conv / C3 / SPPF / nn.Upsample / Concat / TransformerFusionBlock / Detect."""
+    gd, gw = cfg["depth_multiple"], cfg["width_multiple"]
+    nc, anchors = cfg["nc"], cfg["anchors"]
+    no = (len(anchors[0]) // 2) * (nc + 5)
+    ch: List[int] = []
+    layers = []
+    for i, (f, n, m, args) in enumerate(cfg["backbone"] + cfg["head"]):
+        args = list(args)
+        n = max(round(n * gd), 1) if n > 1 else n
+        c_in_prev = ch[-1] if ch else 3
+        if m in ("Conv", "C3", "SPPF"):
+            if m == "Conv" and args[0] == 64:          # yolo_test.py:242-246: both stems take the image
+                c1 = 3
+            else:
+                c1 = ch[f] if ch else 3
+            c2 = args[0]
+            if c2 != no:
+                c2 = make_divisible(c2 * gw, 8)
+            spec = dict(type=m, c1=c1, c2=c2, args=args[1:], n=n)
+        elif m == "nn.Upsample":
+            c2 = c_in_prev
+            spec = dict(type="Upsample", scale=args[1], mode=args[2])
+        elif m == "Concat":
+            c2 = sum(ch[x] for x in f)
+            spec = dict(type="Concat")
+        elif m == "TransformerFusionBlock":
+            c2 = ch[f[0]]
+            spec = dict(type="DMFF", c=c2, va=args[1], ha=args[2])
+        elif m == "Detect":
+            c2 = None
+            spec = dict(type="Detect", nc=nc, anchors=anchors, ch=[ch[x] for x in f])
+        else:
+            raise ValueError(f"oracle does not restate module {m}")
+        spec.update(i=i, f=f)
+        layers.append(spec)
+        ch.append(c2)
+    return layers
+
+
+def model_forward(sd: SD, cfg: dict, rgb, ir, training=False, dmff_loops: int = 1):
+    """Model.forward_once, yolo_test.py:136-163: sequential walk; `f == -4` feeds the IR image."""
+    layers = parse_layers(cfg)
+    save = set()
+    for L in layers:
+        fs = [L["f"]] if isinstance(L["f"], int) else L["f"]
+        save.update(x % L["i"] for x in fs if x != -1)
+    y: List = []
+    x = rgb
+    for L in layers:
+        f, i, t = L["f"], L["i"], L["type"]
+        pre = f"model.{i}"
+        if f == -4:
+            x = ir
+        elif f != -1:
+            x = y[f] if isinstance(f, int) else [x if j == -1 else y[j] for j in f]
+        if t == "Conv":
+            a = L["args"]
+            k = a[0] if len(a) > 0 else 1
+            s = a[1] if len(a) > 1 else 1
+            p = a[2] if len(a) > 2 else None
+            x = conv_bn_silu(x, sd, pre, k, s, p)
+        elif t == "C3":
+            shortcut = L["args"][0] if L["args"] else True
+            x = c3(x, sd, pre, L["n"], shortcut)
+        elif t == "SPPF":
+            x = sppf(x, sd, pre, L["args"][0] if L["args"] else 5)
+        elif t == "Upsample":
+            x = F.interpolate(x, scale_factor=float(L["scale"]), mode=L["mode"])
+        elif t == "Concat":
+            x = torch.cat(x, 1)
+        elif t == "DMFF":
+            x = dmff_block(x[0], x[1], sd, pre, L["va"], L["ha"], dmff_loops, training=training)
+        elif t == "Detect":
+            x = detect(list(x), sd, pre, L["nc"], L["anchors"], [8.0, 16.0, 32.0], training)
+        y.append(x if i in save else None)
+    return x
+
+
+def fold_bn(sd: SD, bn_eps=BN_EPS_MODEL) -> SD:
+    """fuse_conv_and_bn (utils/torch_utils.py:182-202) applied to every Conv in a state_dict,
+    i.e. what Model.fuse() (yolo_test.py:182-190) leaves behind."""
+    out = {}
+    for k, v in sd.items():
+        if ".bn." in k:
+            continue
+        if k.endswith(".conv.weight") and k[:-len("conv.weight")] + "bn.weight" in sd:
+            pre = k[:-len(".conv.weight")]
+            g, b = sd[pre + ".bn.weight"], sd[pre + ".bn.bias"]
+            mu, var = sd[pre + ".bn.running_mean"], sd[pre + ".bn.running_var"]
+            scale = g / torch.sqrt(var + bn_eps)
+            out[k] = v * scale.view(-1, 1, 1, 1)
+            out[pre + ".conv.bias"] = b - mu * scale
+        else:
+            out[k] = v
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# Work accounting -- used by bench.py to turn time into GFLOP/s
+# ----------------------------------------------------------------------------------------
+def dmff_flops(B, C, H, W, N, loops=1):
+    """F_dmff = B*[L*(48 N C^2 + 8 N^2 C) + 4 H W C^2]"""
+    return B * (loops * (48 * N * C * C + 8 * N * N * C) + 4 * H * W * C * C)
+
+
+def model_conv_flops(cfg: dict, H: int, W: int) -> float:
+    """Algorithmic FLOPs (2*MAC) of every conv/linear/attention matmul for one RGB+IR pair."""
+    layers = parse_layers(cfg)
+    shapes: List = []
+    total = 0.0
+
+    def conv(ci, co, k, ho, wo):
+        return 2.0 * ho * wo * co * ci * k * k
+
+    for L in layers:
+        f, t = L["f"], L["type"]
+        if f == -4 or not shapes:
+            cin, h, w = 3, H, W
+        elif isinstance(f, int):
+            cin, h, w = shapes[f] if f != -1 else shapes[-1]
+        else:
+            srcs = [shapes[-1] if j == -1 else shapes[j] for j in f]
+            cin, h, w = sum(s[0] for s in srcs), srcs[0][1], srcs[0][2]
+        if t == "Conv":
+            a = L["args"]
+            k = a[0] if a else 1
+            s = a[1] if len(a) > 1 else 1
+            p = a[2] if len(a) > 2 else k // 2
+            ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+            total += conv(L["c1"], L["c2"], k, ho, wo)
+            shapes.append((L["c2"], ho, wo))
+        elif t == "C3":
+            c1, c2, n = L["c1"], L["c2"], L["n"]
+            c_ = c2 // 2
+            total += 2 * conv(c1, c_, 1, h, w) + conv(2 * c_, c2, 1, h, w)
+            total += n * (conv(c_, c_, 1, h, w) + conv(c_, c_, 3, h, w))
+            shapes.append((c2, h, w))
+        elif t == "SPPF":
+            c1, c2 = L["c1"], L["c2"]
+            total += conv(c1, c1 // 2, 1, h, w) + conv(2 * c1, c2, 1, h, w)
+            shapes.append((c2, h, w))
+        elif t == "Upsample":
+            shapes.append((cin, h * L["scale"], w * L["scale"]))
+        elif t == "Concat":
+            shapes.append((cin, h, w))
+        elif t == "DMFF":
+            c = L["c"]
+            nh, nw = min(L["va"], h), min(L["ha"], w)
+            total += dmff_flops(1, c, h, w, nh * nw)
+            shapes.append((c, h, w))
+        elif t == "Detect":
+            na = len(L["anchors"][0]) // 2
+            for j in f:
+                cj, hj, wj = shapes[j]
+                total += conv(cj, na * (L["nc"] + 5), 1, hj, wj)
+            shapes.append(None)
+    return total

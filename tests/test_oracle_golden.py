@@ -1,0 +1,58 @@
+"""Pins oracle/icaf_oracle.py to outputs of the real reference (tests/golden/*.npz, produced by
+oracle/gen_golden.py in the build container).  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, normwise
+from icafusion_b200.cfg import load_cfg
+from oracle import icaf_oracle as O
+from oracle import synth
+
+DMFF = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "dmff_*.npz")))
+MODELS = ["yolov5s_320", "yolov5s_512x640"]   # yolov5l replay is in the gpu suite (CPU time)
+
+TOL_FP32 = 2e-5   # fp32 vs fp32, different op order only
+
+
+@pytest.mark.parametrize("name", DMFF)
+def test_dmff_oracle_matches_reference(name):
+    m, d = load_golden(name)
+    sd = synth.synth_state_dict(synth.dmff_param_shapes(m["C"], m["va"] * m["ha"], "blk"), m["seed"])
+    rgb, ir = synth.synth_features(m["B"], m["C"], m["H"], m["W"], m["seed"])
+    with torch.no_grad():
+        r, _, _ = O.dmff_tokens(rgb, sd, "blk", "vis", m["va"], m["ha"])
+        i, _, _ = O.dmff_tokens(ir, sd, "blk", "ir", m["va"], m["ha"])
+        tr, ti = O.cross_transformer_block(r, i, sd, "blk.crosstransformer.0", m["loops"])
+        out = O.dmff_block(rgb, ir, sd, "blk", m["va"], m["ha"], m["loops"], bn_eps=m["bn_eps"])
+    assert normwise(tr.numpy(), d["tok_vis"]) < TOL_FP32
+    assert normwise(ti.numpy(), d["tok_ir"]) < TOL_FP32
+    assert normwise(out.numpy(), d["out"]) < TOL_FP32
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_model_oracle_matches_reference(name):
+    m, d = load_golden(name)
+    cfg = load_cfg(f"yolov5{m['size']}_Transfusion_kaist")
+    sd = synth.synth_state_dict(synth.model_param_shapes(cfg), m["seed"])
+    rgb, ir = synth.synth_images(m["B"], m["H"], m["W"], m["seed"])
+    with torch.no_grad():
+        z, lg, xs = O.model_forward(sd, cfg, rgb, ir)
+        zf = O.model_forward(O.fold_bn(sd), cfg, rgb, ir)[0]
+    assert z.shape == d["z"].shape
+    assert normwise(z.numpy(), d["z"]) < TOL_FP32
+    assert normwise(lg.numpy(), d["logits"]) < TOL_FP32
+    assert normwise(zf.numpy(), d["z_fused"]) < TOL_FP32       # fold_bn == Model.fuse()
+    for j in range(3):
+        assert normwise(xs[j].numpy(), d[f"x{j}"].astype(np.float32)) < 2e-3   # stored as fp16
+
+
+def test_flop_accounting_matches_survey():
+    # hook-counted on the reference: 24.61 / 155.82 GFLOP per 512x640 pair
+    s = O.model_conv_flops(load_cfg("yolov5s_Transfusion_kaist"), 512, 640) / 1e9
+    l = O.model_conv_flops(load_cfg("yolov5l_Transfusion_kaist"), 512, 640) / 1e9
+    assert abs(s - 24.61) < 0.02 and abs(l - 155.82) < 0.05, (s, l)
+    assert abs(O.dmff_flops(1, 256, 64, 80, 400) / 1e9 - 2.928) < 0.01
