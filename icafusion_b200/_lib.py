@@ -1,0 +1,76 @@
+"""ctypes binding of libicaf_b200.so (the C ABI declared in include/icaf_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the
+product path raises.  Build it with ``python -m icafusion_b200.build`` (or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libicaf_b200.so")
+
+ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+EPI_BIAS_ROW, EPI_ADD_RES, EPI_SCALED_RES = 1, 2, 4
+
+
+class ConvGeom(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "Hi", "Wi", "Cin", "Ho", "Wo", "Cout", "kh", "kw", "stride", "pad",
+                                       "k_pad", "w_rows", "act", "epi")]
+
+
+class ConvIO(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_ld", C.c_int64), ("w", C.c_void_p), ("bias", C.c_void_p),
+                ("res", C.c_void_p), ("res_ld", C.c_int64), ("y", C.c_void_p), ("y_ld", C.c_int64),
+                ("alpha", C.c_void_p), ("beta", C.c_void_p)]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+# name -> argtypes; every symbol include/icaf_b200.h declares (tests check the .so exports them all)
+SIGNATURES = {
+    "icaf_version": [],
+    "icaf_last_error": [],
+    "icaf_sm_count": [],
+    "icaf_conv2d_fwd": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
+    "icaf_conv2d_fwd_simt": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
+    "icaf_pack_image": [_vp, _i, _f, _i, _i, _i, _vp, _vp],
+    "icaf_sppf_pool": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
+    "icaf_upsample2x": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp],
+    "icaf_copy_channels": [_vp, _i64, _vp, _i64, _i64, _i, _vp],
+    "icaf_dmff_pool_tokens": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "icaf_layernorm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp],
+    "icaf_cross_attention": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "icaf_cross_attention_simt": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "icaf_dmff_upsample_cat": [_vp, _vp, _i, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "icaf_detect_decode": [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.POINTER(C.c_float), _vp],
+}
+
+_lib = None
+
+
+class IcafError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IcafError(f"{LIB_PATH} not found -- build it with `python -m icafusion_b200.build`; "
+                            "icafusion_b200 has no non-CUDA fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(L, name)            # AttributeError here = header/.so drift
+            fn.argtypes = argtypes
+            fn.restype = C.c_char_p if name == "icaf_last_error" else C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().icaf_last_error()
+        raise IcafError(f"{what or 'icaf call'} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,469 @@
+"""Host-side mirror of the reference operator library (models/common.py) for the ICAFusion hot path.
+
+Same class names, constructor signatures, sub-module / parameter names and ``state_dict`` keys as the
+reference, so reference checkpoints load with ``strict=True`` and ``models/yolo_test.py``-style graph
+builders can ``eval()`` these names.  The ``forward`` bodies do not call PyTorch operators: they
+marshal tensors into libicaf_b200.so (hand-written sm_100a kernels, see include/icaf_b200.h).
+
+Data layout: modules accept logical (B,C,H,W) tensors like the reference; internally everything is
+fp16 NHWC, which is exactly torch's ``channels_last`` memory format, so consecutive modules exchange
+tensors without any layout conversion (outputs are returned as channels_last views).
+
+Scope of this round: inference semantics (``eval()``: BatchNorm running statistics, dropout = identity,
+bilinear DMFF up-sampling) with or without ``Model.fuse()``.  Training-mode forward (batch statistics,
+dropout, autograd) raises NotImplementedError -- there is no silent PyTorch fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ACT_GELU, ACT_NONE, ACT_SILU, PackedConv
+
+__all__ = ["autopad", "Conv", "Bottleneck", "C3", "SPPF", "Concat", "Upsample", "LearnableCoefficient",
+           "LearnableWeights", "CrossAttention", "CrossTransformerBlock", "TransformerFusionBlock",
+           "AdaptivePool2d", "to_nhwc", "to_nchw"]
+
+
+def autopad(k, p=None):
+    """reference: models/common.py:36-40"""
+    if p is None:
+        p = k // 2 if isinstance(k, int) else [x // 2 for x in k]
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# layout plumbing
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Logical (B,C,H,W) -> fp16 (B,H,W,C) contiguous view (zero-copy for channels_last fp16 input)."""
+    if not x.is_cuda:
+        raise RuntimeError("icafusion_b200 operators run on CUDA tensors only (no CPU fallback)")
+    v = x.permute(0, 2, 3, 1)
+    if v.dtype != torch.float16 or not v.is_contiguous():
+        v = v.to(torch.float16).contiguous()
+    return v
+
+
+def to_nchw(v: torch.Tensor) -> torch.Tensor:
+    """(B,H,W,C) -> logical (B,C,H,W) channels_last view."""
+    return v.permute(0, 3, 1, 2)
+
+
+def _require_eval(m: nn.Module):
+    if m.training:
+        raise NotImplementedError(f"{type(m).__name__}: training-mode forward is not built yet in icafusion_b200 "
+                                  "(call .eval()); there is no PyTorch fallback")
+
+
+def _versions(*ts) -> tuple:
+    return tuple((t.data_ptr(), t._version, t.device) if t is not None else None for t in ts)
+
+
+# ------------------------------------------------------------------------------------------------
+class Conv(nn.Module):
+    """Conv2d + BatchNorm2d + SiLU (reference: models/common.py:48-60).  After ``Model.fuse()`` the BN is
+    folded into ``self.conv`` (with bias) and ``forward`` is rebound to ``fuseforward`` exactly as the
+    reference does; before that, eval-mode BN is folded on the fly into the packed filter."""
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, autopad(k, p), groups=g, bias=False)
+        self.bn = nn.BatchNorm2d(c2)
+        self.act = nn.SiLU() if act is True else (act if isinstance(act, nn.Module) else nn.Identity())
+
+    # -- packed filter cache -------------------------------------------------------------------
+    def packed(self) -> PackedConv:
+        conv = self.conv
+        bn = getattr(self, "bn", None)
+        key = _versions(conv.weight, conv.bias, *( (bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else ()))
+        cache = self.__dict__.get("_icaf_pack")
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        if conv.groups != 1 or conv.dilation != (1, 1) or conv.kernel_size[0] != conv.kernel_size[1] or \
+                conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1]:
+            raise NotImplementedError("Conv: only groups=1, dilation=1, square kernel/stride/padding are supported")
+        if isinstance(self.act, nn.SiLU):
+            act = ACT_SILU
+        elif isinstance(self.act, nn.Identity):
+            act = ACT_NONE
+        else:
+            raise NotImplementedError(f"Conv: activation {type(self.act).__name__} not supported")
+        w = conv.weight.detach().float()
+        b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+        if bn is not None:   # fold eval-mode BN: utils/torch_utils.py:182-202
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            w = w * scale.view(-1, 1, 1, 1)
+            b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+        pk = ops.pack_conv_weight(w, b, conv.stride[0], conv.padding[0], act)
+        self.__dict__["_icaf_pack"] = (key, pk)
+        return pk
+
+    @staticmethod
+    def run(mods: Sequence["Conv"], xs: Sequence[torch.Tensor], outs=None, res=None) -> List[torch.Tensor]:
+        """NHWC-level entry: 1 or 2 Conv modules of identical geometry in one grouped launch."""
+        for m in mods:
+            if hasattr(m, "bn"):
+                _require_eval(m)
+        return ops.conv2d(list(xs), [m.packed() for m in mods], outs, res)
+
+    def forward(self, x):
+        if x.shape[1] == 3 and self.conv.in_channels == 3:     # image stem: planar -> packed NHWC4
+            v = ops.pack_image(x if x.dtype in (torch.float16, torch.float32, torch.uint8) else x.float())
+        else:
+            v = to_nhwc(x)
+        return to_nchw(Conv.run([self], [v])[0])
+
+    def fuseforward(self, x):
+        return Conv.forward(self, x)
+
+
+class Bottleneck(nn.Module):
+    """reference: models/common.py:184-194"""
+
+    def __init__(self, c1, c2, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_, c2, 3, 1, g=g)
+        self.add = shortcut and c1 == c2
+
+    @staticmethod
+    def run(mods, xs, outs=None):
+        h = Conv.run([m.cv1 for m in mods], xs)
+        return Conv.run([m.cv2 for m in mods], h, outs, list(xs) if mods[0].add else None)   # residual fused in the epilogue
+
+    def forward(self, x):
+        return to_nchw(Bottleneck.run([self], [to_nhwc(x)])[0])
+
+
+class C3(nn.Module):
+    """CSP bottleneck with 3 convolutions (reference: models/common.py:216-227).  The channel concat is
+    never materialised as a copy: the last bottleneck and cv2 write straight into the two halves of the
+    buffer cv3 reads."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*[Bottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)])
+
+    @staticmethod
+    def run(mods, xs):
+        c_ = mods[0].cv1.conv.out_channels
+        B, H, W, _ = xs[0].shape
+        cats = [torch.empty(B, H, W, 2 * c_, dtype=torch.float16, device=xs[0].device) for _ in mods]
+        left = [c[..., :c_] for c in cats]
+        right = [c[..., c_:] for c in cats]
+        n = len(mods[0].m)
+        a = Conv.run([m.cv1 for m in mods], xs, left if n == 0 else None)
+        for j in range(n):
+            a = Bottleneck.run([m.m[j] for m in mods], a, left if j == n - 1 else None)
+        Conv.run([m.cv2 for m in mods], xs, right)
+        return Conv.run([m.cv3 for m in mods], cats)
+
+    def forward(self, x):
+        return to_nchw(C3.run([self], [to_nhwc(x)])[0])
+
+
+class SPPF(nn.Module):
+    """reference: models/common.py:252-267 (three chained 5x5 max pools, concatenated with the input)."""
+
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1, 1)
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+
+    @staticmethod
+    def run(mods, xs):
+        c_ = mods[0].cv1.conv.out_channels
+        if mods[0].m.kernel_size != 5:
+            raise NotImplementedError("SPPF: only k=5 is supported")
+        B, H, W, _ = xs[0].shape
+        cats = [torch.empty(B, H, W, 4 * c_, dtype=torch.float16, device=xs[0].device) for _ in mods]
+        Conv.run([m.cv1 for m in mods], xs, [c[..., :c_] for c in cats])
+        for c in cats:
+            ops.sppf_pool(c[..., :c_], c[..., c_:2 * c_], c[..., 2 * c_:3 * c_], c[..., 3 * c_:])
+        return Conv.run([m.cv2 for m in mods], cats)
+
+    def forward(self, x):
+        return to_nchw(SPPF.run([self], [to_nhwc(x)])[0])
+
+
+class Concat(nn.Module):
+    """reference: models/common.py:313-321 (channel concat of NCHW maps)."""
+
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+    @staticmethod
+    def run(vs: Sequence[torch.Tensor]) -> torch.Tensor:
+        B, H, W, _ = vs[0].shape
+        out = torch.empty(B, H, W, sum(v.shape[3] for v in vs), dtype=torch.float16, device=vs[0].device)
+        o = 0
+        for v in vs:
+            ops.copy_channels(v, out[..., o:o + v.shape[3]])
+            o += v.shape[3]
+        return out
+
+    def forward(self, x):
+        if self.d != 1:
+            raise NotImplementedError("Concat: only the channel dimension is supported")
+        return to_nchw(Concat.run([to_nhwc(t) for t in x]))
+
+
+class Upsample(nn.Upsample):
+    """`nn.Upsample(None, 2, 'nearest')` rows of the model YAML (yolov5l_Transfusion_kaist.yaml:48,53)."""
+
+    def forward(self, x):
+        if self.mode != "nearest" or float(self.scale_factor) != 2.0:
+            raise NotImplementedError("Upsample: only nearest x2 is supported")
+        return to_nchw(ops.upsample2x(to_nhwc(x)))
+
+
+# ------------------------------------------------------------------------------------------------
+# DMFF
+class LearnableCoefficient(nn.Module):
+    """reference: models/common.py:569-576 (scalar gain; consumed fused inside CrossTransformerBlock)."""
+
+    def __init__(self):
+        super().__init__()
+        self.bias = nn.Parameter(torch.FloatTensor([1.0]), requires_grad=True)
+
+    def forward(self, x):
+        raise NotImplementedError("LearnableCoefficient is applied inside the fused CrossTransformerBlock epilogues")
+
+
+class LearnableWeights(nn.Module):
+    """reference: models/common.py:579-587 (two scalar mixing weights; fused into the token pooling kernel)."""
+
+    def __init__(self):
+        super().__init__()
+        self.w1 = nn.Parameter(torch.tensor([0.5]), requires_grad=True)
+        self.w2 = nn.Parameter(torch.tensor([0.5]), requires_grad=True)
+
+    def forward(self, x1, x2):
+        raise NotImplementedError("LearnableWeights is applied inside the fused DMFF token-pooling kernel")
+
+
+class AdaptivePool2d(nn.Module):
+    """reference: models/common.py:868-891.  Holds the geometry; the pooling itself runs fused with the
+    avg/max mix and the positional embedding in icaf_dmff_pool_tokens."""
+
+    def __init__(self, output_h, output_w, pool_type="avg"):
+        super().__init__()
+        self.output_h = output_h
+        self.output_w = output_w
+        self.pool_type = pool_type
+
+    def out_size(self, H: int, W: int):
+        if H > self.output_h or W > self.output_w:
+            if H < self.output_h or W < self.output_w:
+                raise ValueError(f"AdaptivePool2d: map {H}x{W} is smaller than the {self.output_h}x{self.output_w} grid in "
+                                 "one dimension (the reference divides by zero here, common.py:880)")
+            return self.output_h, self.output_w
+        return H, W
+
+    def forward(self, x):
+        raise NotImplementedError("AdaptivePool2d runs fused inside TransformerFusionBlock")
+
+
+class CrossAttention(nn.Module):
+    """reference: models/common.py:590-687.  Parameters only; the computation (LN -> fused QK / V^T
+    projections -> flash cross-attention -> out_proj) is driven by CrossTransformerBlock."""
+
+    def __init__(self, d_model, d_k, d_v, h, attn_pdrop=.1, resid_pdrop=.1):
+        super().__init__()
+        assert d_k % h == 0
+        self.d_model = d_model
+        self.d_k = d_model // h
+        self.d_v = d_model // h
+        self.h = h
+        self.que_proj_vis = nn.Linear(d_model, h * self.d_k)
+        self.key_proj_vis = nn.Linear(d_model, h * self.d_k)
+        self.val_proj_vis = nn.Linear(d_model, h * self.d_v)
+        self.que_proj_ir = nn.Linear(d_model, h * self.d_k)
+        self.key_proj_ir = nn.Linear(d_model, h * self.d_k)
+        self.val_proj_ir = nn.Linear(d_model, h * self.d_v)
+        self.out_proj_vis = nn.Linear(h * self.d_v, d_model)
+        self.out_proj_ir = nn.Linear(h * self.d_v, d_model)
+        self.attn_drop = nn.Dropout(attn_pdrop)
+        self.resid_drop = nn.Dropout(resid_pdrop)
+        self.LN1 = nn.LayerNorm(d_model)
+        self.LN2 = nn.LayerNorm(d_model)
+        for m in self.modules():          # reference init, common.py:626-639
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, std=0.001)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, x, attention_mask=None, attention_weights=None):
+        raise NotImplementedError("CrossAttention runs fused inside CrossTransformerBlock")
+
+
+def _mlp(d_model, block_exp, resid_pdrop):
+    return nn.Sequential(nn.Linear(d_model, block_exp * d_model), nn.GELU(),
+                         nn.Linear(block_exp * d_model, d_model), nn.Dropout(resid_pdrop))
+
+
+class CrossTransformerBlock(nn.Module):
+    """reference: models/common.py:690-759.  ``loops`` is mutable like in the reference.  Dead parameters
+    (ln_input, ln_output, mlp, LN1) are kept so state_dicts match."""
+
+    def __init__(self, d_model, d_k, d_v, h, block_exp, attn_pdrop, resid_pdrop, loops_num=1):
+        super().__init__()
+        self.loops = loops_num
+        self.ln_input = nn.LayerNorm(d_model)
+        self.ln_output = nn.LayerNorm(d_model)
+        self.crossatt = CrossAttention(d_model, d_k, d_v, h, attn_pdrop, resid_pdrop)
+        self.mlp_vis = _mlp(d_model, block_exp, resid_pdrop)
+        self.mlp_ir = _mlp(d_model, block_exp, resid_pdrop)
+        self.mlp = _mlp(d_model, block_exp, resid_pdrop)
+        self.LN1 = nn.LayerNorm(d_model)
+        self.LN2 = nn.LayerNorm(d_model)
+        for j in range(1, 9):
+            setattr(self, f"coefficient{j}", LearnableCoefficient())
+
+    # -- packed parameters ---------------------------------------------------------------------
+    def packed(self):
+        ca = self.crossatt
+        live = [ca.que_proj_vis, ca.key_proj_vis, ca.val_proj_vis, ca.que_proj_ir, ca.key_proj_ir, ca.val_proj_ir,
+                ca.out_proj_vis, ca.out_proj_ir, self.mlp_vis[0], self.mlp_vis[2], self.mlp_ir[0], self.mlp_ir[2],
+                ca.LN1, ca.LN2, self.LN2]
+        ts = [p for m in live for p in (m.weight, m.bias)] + [getattr(self, f"coefficient{j}").bias for j in range(1, 9)]
+        key = _versions(*ts)
+        cache = self.__dict__.get("_icaf_pack")
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        d = ca.d_model
+        if d % 64:
+            raise NotImplementedError("CrossTransformerBlock: d_model must be a multiple of 64")
+        f32 = lambda t: t.detach().float().contiguous()   # noqa: E731
+        P = {}
+        for mod, q, k, v, o in (("vis", ca.que_proj_vis, ca.key_proj_vis, ca.val_proj_vis, ca.out_proj_vis),
+                                ("ir", ca.que_proj_ir, ca.key_proj_ir, ca.val_proj_ir, ca.out_proj_ir)):
+            P[f"qk_{mod}"] = ops.pack_linear(torch.cat([q.weight, k.weight], 0), torch.cat([q.bias, k.bias], 0))
+            P[f"wv_{mod}"] = v.weight.detach().to(torch.float16).contiguous()     # A operand of the swap-AB V^T linear
+            P[f"bv_{mod}"] = f32(v.bias)
+            P[f"out_{mod}"] = ops.pack_linear(o.weight, o.bias)
+        for mod, mlp in (("vis", self.mlp_vis), ("ir", self.mlp_ir)):
+            P[f"fc1_{mod}"] = ops.pack_linear(mlp[0].weight, mlp[0].bias, ACT_GELU)
+            P[f"fc2_{mod}"] = ops.pack_linear(mlp[2].weight, mlp[2].bias)
+        for name, ln in (("ln_vis", ca.LN1), ("ln_ir", ca.LN2), ("ln2", self.LN2)):
+            P[name] = (f32(ln.weight), f32(ln.bias), ln.eps)
+        P["coef"] = torch.cat([getattr(self, f"coefficient{j}").bias.detach().float().reshape(1) for j in range(1, 9)])
+        self.__dict__["_icaf_pack"] = (key, P)
+        return P
+
+    def run(self, r: torch.Tensor, i: torch.Tensor, N: int):
+        """r, i: fp16 (B, Npad, C) token streams (pad rows finite).  Returns the updated streams."""
+        _require_eval(self)
+        P = self.packed()
+        B, n_pad, C = r.shape
+        rows = B * n_pad
+        h = self.crossatt.h
+        c = P["coef"]
+        co = lambda a, b: (c[a - 1:a], c[b - 1:b])   # noqa: E731  (alpha, beta) device scalars
+        r2, i2 = r.view(rows, C), i.view(rows, C)
+        for _ in range(self.loops):
+            # LN1(rgb), LN2(ir)                                        common.py:660,665
+            rn, inn = ops.layernorm(r2, P["ln_vis"][0], P["ln_vis"][1], i2, P["ln_ir"][0], P["ln_ir"][1], P["ln_vis"][2])
+            # fused [Q|K] projections, both modalities in one launch   common.py:661-662,666-667
+            qk_v, qk_i = ops.linear([rn, inn], [P["qk_vis"], P["qk_ir"]])
+            # V^T = Wv . LN(x)^T (swap-AB: the token matrix is the "filter")   common.py:663,668
+            tok_as_w = [PackedConv(t, None, C, rows, 1, 1, 1, 0, ACT_NONE) for t in (rn, inn)]
+            for t, b in zip(tok_as_w, (P["bv_vis"], P["bv_ir"])):
+                t.bias = b
+            vt_v, vt_i = ops.linear([P["wv_vis"], P["wv_ir"]], tok_as_w, bias_row=True)
+            # flash cross-attention, both directions                   common.py:670-684
+            a_v, a_i = ops.cross_attention(qk_v, qk_i, vt_v, vt_i, B, N, n_pad, C, h)
+            # out_proj + coefficient pair: ra = c1*r + c2*o_r          common.py:683,685,747-748
+            ra, ia = ops.linear([a_v.view(rows, C), a_i.view(rows, C)], [P["out_vis"], P["out_ir"]],
+                                res=[r2, i2], scaled=[co(1, 2), co(3, 4)])
+            # MLPs on LN2 (same LN2 for both)                          common.py:749-750
+            rl, il = ops.layernorm(ra, P["ln2"][0], P["ln2"][1], ia, P["ln2"][0], P["ln2"][1], P["ln2"][2])
+            hr, hi = ops.linear([rl, il], [P["fc1_vis"], P["fc1_ir"]])
+            r2, i2 = ops.linear([hr, hi], [P["fc2_vis"], P["fc2_ir"]], res=[ra, ia], scaled=[co(5, 6), co(7, 8)])
+        return r2.view(B, n_pad, C), i2.view(B, n_pad, C)
+
+    def forward(self, x):
+        """x = [rgb_tokens, ir_tokens], each (B, N, C) like the reference (common.py:737-759)."""
+        r, i = x
+        B, N, C = r.shape
+        n_pad = ops.round_up(N, 8)
+
+        def pad(t):
+            t = t.to(torch.float16)
+            if n_pad == N:
+                return t.contiguous()
+            out = t.new_zeros(B, n_pad, C)
+            out[:, :N] = t
+            return out
+        r, i = self.run(pad(r), pad(i), N)
+        return [r[:, :N], i[:, :N]]
+
+
+class TransformerFusionBlock(nn.Module):
+    """The DMFF block (reference: models/common.py:762-865)."""
+
+    def __init__(self, d_model, vert_anchors=16, horz_anchors=16, h=8, block_exp=4, n_layer=1, embd_pdrop=0.1,
+                 attn_pdrop=0.1, resid_pdrop=0.1):
+        super().__init__()
+        self.n_embd = d_model
+        self.vert_anchors = vert_anchors
+        self.horz_anchors = horz_anchors
+        d_k = d_v = d_model
+        self.pos_emb_vis = nn.Parameter(torch.zeros(1, vert_anchors * horz_anchors, self.n_embd))
+        self.pos_emb_ir = nn.Parameter(torch.zeros(1, vert_anchors * horz_anchors, self.n_embd))
+        self.avgpool = AdaptivePool2d(self.vert_anchors, self.horz_anchors, "avg")
+        self.maxpool = AdaptivePool2d(self.vert_anchors, self.horz_anchors, "max")
+        self.vis_coefficient = LearnableWeights()
+        self.ir_coefficient = LearnableWeights()
+        self.crosstransformer = nn.Sequential(*[CrossTransformerBlock(d_model, d_k, d_v, h, block_exp, attn_pdrop,
+                                                                      resid_pdrop) for _ in range(n_layer)])
+        for m in self.crosstransformer.modules():   # reference applies _init_weights before building these; keep
+            if isinstance(m, nn.Linear):             # transformer-style init for a usable default
+                nn.init.normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+        self.concat = Concat(dimension=1)
+        self.conv1x1_out = Conv(c1=d_model * 2, c2=d_model, k=1, s=1, p=0, g=1, act=True)
+
+    def _front(self):
+        ts = (self.pos_emb_vis, self.pos_emb_ir, self.vis_coefficient.w1, self.vis_coefficient.w2,
+              self.ir_coefficient.w1, self.ir_coefficient.w2)
+        key = _versions(*ts)
+        cache = self.__dict__.get("_icaf_pack")
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        pk = (self.pos_emb_vis.detach()[0].to(torch.float16).contiguous(),
+              self.pos_emb_ir.detach()[0].to(torch.float16).contiguous(),
+              torch.cat([t.detach().float().reshape(1) for t in ts[2:]]))
+        self.__dict__["_icaf_pack"] = (key, pk)
+        return pk
+
+    def run(self, rgb: torch.Tensor, ir: torch.Tensor) -> torch.Tensor:
+        """rgb, ir: fp16 NHWC feature maps -> fused NHWC map."""
+        _require_eval(self)
+        B, H, W, C = rgb.shape
+        nh, nw = self.avgpool.out_size(H, W)
+        N = nh * nw
+        if N != self.pos_emb_vis.shape[1]:
+            raise ValueError(f"TransformerFusionBlock: {nh}x{nw} tokens but pos_emb has {self.pos_emb_vis.shape[1]} rows")
+        pos_v, pos_i, mix = self._front()
+        r, i = ops.dmff_pool_tokens(rgb, ir, pos_v, pos_i, mix, nh, nw)            # common.py:817-823
+        for blk in self.crosstransformer:
+            r, i = blk.run(r, i, N)                                                # common.py:825
+        cat = ops.dmff_upsample_cat(r, i, rgb, ir, nh, nw, mode=0)                 # common.py:827-840 (eval: bilinear)
+        return Conv.run([self.conv1x1_out], [cat])[0]                              # common.py:841
+
+    def forward(self, x):
+        rgb, ir = x
+        assert rgb.shape[0] == ir.shape[0]
+        return to_nchw(self.run(to_nhwc(rgb), to_nhwc(ir)))

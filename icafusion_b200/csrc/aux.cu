@@ -1,0 +1,398 @@
+// HBM-bound helper kernels of the hot path (everything that is not a GEMM): image staging, SPPF pooling,
+// nearest up-sampling / concat copies, DMFF token pooling (+pos-emb), LayerNorm, DMFF bilinear tail, Detect decode.
+// All work on fp16 NHWC views; each thread moves 16-byte (8-channel) vectors so every warp access is a run of
+// full 128-byte lines along the channel axis.
+#include "icaf_internal.cuh"
+
+namespace icaf {
+
+__device__ __forceinline__ uint4 ldg16(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_half2(f[0], f[1]); v.y = pack_half2(f[2], f[3]);
+  v.z = pack_half2(f[4], f[5]); v.w = pack_half2(f[6], f[7]);
+  return v;
+}
+__device__ __forceinline__ uint4 hmax8(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __half2* x = reinterpret_cast<const __half2*>(&a);
+  const __half2* y = reinterpret_cast<const __half2*>(&b);
+  __half2* z = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (B,3,H,W) planar -> (B,H,W,4) fp16
+template <typename T>
+__global__ void pack_image_kernel(const T* __restrict__ src, float scale, long long npix, long long hw, __half* __restrict__ dst) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  long long b = i / hw, p = i - b * hw;
+  const T* s = src + b * 3 * hw + p;
+  float r = float(s[0]) * scale, g = float(s[hw]) * scale, bl = float(s[2 * hw]) * scale;
+  uint2 o;
+  o.x = pack_half2(r, g);
+  o.y = pack_half2(bl, 0.f);
+  reinterpret_cast<uint2*>(dst)[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPPF: three chained 5x5/s1/p2 max pools == 5x5, 9x9, 13x13 windows clipped to the map (-inf padding)
+__global__ void sppf_pool_kernel(const __half* __restrict__ x, long long x_ld, __half* y1, __half* y2, __half* y3,
+                                 long long y_ld, int B, int H, int W, int C8) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * W * C8;
+  if (i >= total) return;
+  int c = int(i % C8);
+  long long p = i / C8;
+  int px = int(p % W);
+  long long t = p / W;
+  int py = int(t % H);
+  int b = int(t / H);
+  const __half ninf = __ushort_as_half(0xFC00);
+  __half2 n2 = __halves2half2(ninf, ninf);
+  uint4 m5, m9, m13;
+  *reinterpret_cast<__half2*>(&m5.x) = n2; m5.y = m5.x; m5.z = m5.x; m5.w = m5.x;
+  m9 = m5; m13 = m5;
+  for (int dy = -6; dy <= 6; ++dy) {
+    int yy = py + dy;
+    if ((unsigned)yy >= (unsigned)H) continue;
+    for (int dx = -6; dx <= 6; ++dx) {
+      int xx = px + dx;
+      if ((unsigned)xx >= (unsigned)W) continue;
+      uint4 v = ldg16(x + ((long long)(b * H + yy) * W + xx) * x_ld + c * 8);
+      m13 = hmax8(m13, v);
+      if (dy >= -4 && dy <= 4 && dx >= -4 && dx <= 4) m9 = hmax8(m9, v);
+      if (dy >= -2 && dy <= 2 && dx >= -2 && dx <= 2) m5 = hmax8(m5, v);
+    }
+  }
+  long long o = p * y_ld + c * 8;
+  *reinterpret_cast<uint4*>(y1 + o) = m5;
+  *reinterpret_cast<uint4*>(y2 + o) = m9;
+  *reinterpret_cast<uint4*>(y3 + o) = m13;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const __half* __restrict__ x, long long x_ld, __half* __restrict__ y, long long y_ld,
+                                  int B, int H, int W, int C8) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)B * (2 * H) * (2 * W) * C8;
+  if (i >= total) return;
+  int c = int(i % C8);
+  long long p = i / C8;
+  int ox = int(p % (2 * W));
+  long long t = p / (2 * W);
+  int oy = int(t % (2 * H));
+  int b = int(t / (2 * H));
+  uint4 v = ldg16(x + ((long long)(b * H + (oy >> 1)) * W + (ox >> 1)) * x_ld + c * 8);
+  *reinterpret_cast<uint4*>(y + p * y_ld + c * 8) = v;
+}
+
+__global__ void copy_channels_kernel(const __half* __restrict__ x, long long x_ld, __half* __restrict__ y,
+                                     long long y_ld, long long pixels, int C8) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= pixels * C8) return;
+  int c = int(i % C8);
+  long long p = i / C8;
+  *reinterpret_cast<uint4*>(y + p * y_ld + c * 8) = ldg16(x + p * x_ld + c * 8);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMFF front: avg+max pool with (kh,kw)/(sh,sw) windows, learnable mix, + pos_emb -> tokens (B,Npad,C)
+struct PoolTokParams {
+  const __half* x[2]; const __half* pos[2]; __half* tok[2];
+  const float* mix;
+  long long x_ld;
+  int B, H, W, C8, nh, nw, n_pad, kh, kw, sh, sw;
+};
+__global__ void dmff_pool_tokens_kernel(const PoolTokParams P) {
+  const int mod = blockIdx.y;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)P.B * P.n_pad * P.C8;
+  if (i >= total) return;
+  int c = int(i % P.C8);
+  long long t = i / P.C8;
+  int n = int(t % P.n_pad);
+  int b = int(t / P.n_pad);
+  __half* out = (mod ? P.tok[1] : P.tok[0]) + t * (P.C8 * 8) + c * 8;
+  const int N = P.nh * P.nw;
+  if (n >= N) {
+    *reinterpret_cast<uint4*>(out) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const __half* x = mod ? P.x[1] : P.x[0];
+  const int ty = n / P.nw, tx = n % P.nw;
+  float sum[8], mx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sum[e] = 0.f; mx[e] = -INFINITY; }
+  for (int ky = 0; ky < P.kh; ++ky)
+    for (int kx = 0; kx < P.kw; ++kx) {
+      int yy = ty * P.sh + ky, xx = tx * P.sw + kx;
+      float f[8];
+      unpack8(ldg16(x + ((long long)(b * P.H + yy) * P.W + xx) * P.x_ld + c * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sum[e] += f[e]; mx[e] = fmaxf(mx[e], f[e]); }
+    }
+  const float w1 = P.mix[mod * 2], w2 = P.mix[mod * 2 + 1];
+  const float inv = 1.f / float(P.kh * P.kw);
+  float pe[8], o[8];
+  unpack8(ldg16((mod ? P.pos[1] : P.pos[0]) + (long long)n * (P.C8 * 8) + c * 8), pe);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = w1 * (sum[e] * inv) + w2 * mx[e] + pe[e];
+  *reinterpret_cast<uint4*>(out) = pack8(o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row cached in registers (C <= 2048)
+struct LnParams {
+  const __half* x[2]; __half* y[2]; const float* g[2]; const float* b[2];
+  long long rows; int C; float eps;
+};
+__global__ void layernorm_kernel(const LnParams P) {
+  const int prob = blockIdx.y;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= P.rows) return;
+  const int lane = threadIdx.x & 31;
+  const __half* x = (prob ? P.x[1] : P.x[0]) + row * P.C;
+  __half* y = (prob ? P.y[1] : P.y[0]) + row * P.C;
+  const float* g = prob ? P.g[1] : P.g[0];
+  const float* be = prob ? P.b[1] : P.b[0];
+  const int nch = P.C >> 3;                 // 16-byte chunks in the row
+  float v[8][8];                            // up to 8 chunks per lane -> C <= 2048
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ch = lane + 32 * j;
+    if (ch < nch) {
+      unpack8(ldg16(x + ch * 8), v[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[j][e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / float(P.C);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ch = lane + 32 * j;
+    if (ch < nch) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { float d = v[j][e] - mean; q += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / float(P.C) + P.eps);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ch = lane + 32 * j;
+    if (ch < nch) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * __ldg(g + ch * 8 + e) + __ldg(be + ch * 8 + e);
+      *reinterpret_cast<uint4*>(y + ch * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMFF tail: tokens -> (nh,nw) map -> interpolate to (H,W) + stream features -> concat buffer (B,H,W,2C)
+struct UpCatParams {
+  const __half* tok[2]; const __half* x[2]; __half* y;
+  long long x_ld, y_ld;
+  int B, H, W, C8, nh, nw, n_pad, mode;
+  float sy, sx;   // nh/H, nw/W
+};
+__global__ void dmff_upsample_cat_kernel(const UpCatParams P) {
+  const int mod = blockIdx.y;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)P.B * P.H * P.W * P.C8;
+  if (i >= total) return;
+  int c = int(i % P.C8);
+  long long p = i / P.C8;
+  int ox = int(p % P.W);
+  long long t = p / P.W;
+  int oy = int(t % P.H);
+  int b = int(t / P.H);
+  const int C = P.C8 * 8;
+  const __half* tok = (mod ? P.tok[1] : P.tok[0]) + (long long)b * P.n_pad * C + c * 8;
+  float r[8];
+  if (P.nh == P.H && P.nw == P.W) {                    // identity resample (un-pooled DMFF)
+    unpack8(ldg16(tok + (long long)(oy * P.nw + ox) * C), r);
+  } else if (P.mode == 1) {                            // nearest: src = min(floor(dst*scale), in-1)
+    int iy = min(int(floorf(oy * P.sy)), P.nh - 1), ix = min(int(floorf(ox * P.sx)), P.nw - 1);
+    unpack8(ldg16(tok + (long long)(iy * P.nw + ix) * C), r);
+  } else {                                             // bilinear, align_corners=False
+    float fy = fmaxf((oy + 0.5f) * P.sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * P.sx - 0.5f, 0.f);
+    int y0 = int(fy), x0 = int(fx);
+    int y1 = min(y0 + 1, P.nh - 1), x1 = min(x0 + 1, P.nw - 1);
+    float ly = fy - y0, lx = fx - x0;
+    float a[8], bq[8], cq[8], d[8];
+    unpack8(ldg16(tok + (long long)(y0 * P.nw + x0) * C), a);
+    unpack8(ldg16(tok + (long long)(y0 * P.nw + x1) * C), bq);
+    unpack8(ldg16(tok + (long long)(y1 * P.nw + x0) * C), cq);
+    unpack8(ldg16(tok + (long long)(y1 * P.nw + x1) * C), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      r[e] = (1.f - ly) * ((1.f - lx) * a[e] + lx * bq[e]) + ly * ((1.f - lx) * cq[e] + lx * d[e]);
+  }
+  float f[8];
+  unpack8(ldg16((mod ? P.x[1] : P.x[0]) + p * P.x_ld + c * 8), f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) r[e] += f[e];
+  *reinterpret_cast<uint4*>(P.y + p * P.y_ld + mod * C + c * 8) = pack8(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Detect decode for one level
+struct DetectParams {
+  const __half* p; long long p_ld;
+  __half* x_out; __half* z; __half* logits;
+  int B, ny, nx, na, no, total_rows, row_off;
+  float stride;
+  float anchors[16];
+};
+__global__ void detect_decode_kernel(const DetectParams P) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)P.B * P.na * P.ny * P.nx;
+  if (i >= total) return;
+  int gx = int(i % P.nx);
+  long long t = i / P.nx;
+  int gy = int(t % P.ny); t /= P.ny;
+  int a = int(t % P.na);
+  int b = int(t / P.na);
+  const __half* src = P.p + ((long long)(b * P.ny + gy) * P.nx + gx) * P.p_ld + a * P.no;
+  __half* xo = P.x_out + i * P.no;                                      // (B,na,ny,nx,no) contiguous
+  long long zr = (long long)b * P.total_rows + P.row_off + ((long long)a * P.ny + gy) * P.nx + gx;
+  __half* zo = P.z + zr * P.no;
+  __half* lo = P.logits + zr * (P.no - 5);
+  for (int o = 0; o < P.no; ++o) {
+    __half raw = src[o];
+    xo[o] = raw;
+    float v = __half2float(raw);
+    float s = 1.f / (1.f + __expf(-v));
+    float r;
+    if (o == 0) r = (s * 2.f - 0.5f + gx) * P.stride;
+    else if (o == 1) r = (s * 2.f - 0.5f + gy) * P.stride;
+    else if (o == 2) r = (s * 2.f) * (s * 2.f) * P.anchors[a * 2];
+    else if (o == 3) r = (s * 2.f) * (s * 2.f) * P.anchors[a * 2 + 1];
+    else r = s;
+    zo[o] = __float2half_rn(r);
+    if (o >= 5) lo[o - 5] = raw;
+  }
+}
+
+static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace icaf
+
+using namespace icaf;
+
+extern "C" int icaf_pack_image(const void* src, int src_dtype, float scale, int B, int H, int W, void* dst, void* stream) {
+  if (!src || !dst || B < 1 || H < 1 || W < 1) return set_error(ICAF_ERR_BAD_ARG, "pack_image: bad argument");
+  long long hw = (long long)H * W, npix = hw * B;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned g = blocks_for(npix, 256);
+  if (src_dtype == 0) pack_image_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, scale, npix, hw, (__half*)dst);
+  else if (src_dtype == 1) pack_image_kernel<float><<<g, 256, 0, st>>>((const float*)src, scale, npix, hw, (__half*)dst);
+  else if (src_dtype == 2) pack_image_kernel<uint8_t><<<g, 256, 0, st>>>((const uint8_t*)src, scale, npix, hw, (__half*)dst);
+  else return set_error(ICAF_ERR_BAD_ARG, "pack_image: src_dtype must be 0 (fp16), 1 (fp32) or 2 (uint8)");
+  return check_launch("pack_image");
+}
+
+extern "C" int icaf_sppf_pool(const void* x, int64_t x_ld, void* y1, void* y2, void* y3, int64_t y_ld, int B, int H,
+                              int W, int C, void* stream) {
+  if (!x || !y1 || !y2 || !y3 || C % 8 || x_ld % 8 || y_ld % 8) return set_error(ICAF_ERR_BAD_ARG, "sppf_pool: bad argument");
+  long long total = (long long)B * H * W * (C / 8);
+  sppf_pool_kernel<<<blocks_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __half*)x, x_ld, (__half*)y1, (__half*)y2,
+                                                                            (__half*)y3, y_ld, B, H, W, C / 8);
+  return check_launch("sppf_pool");
+}
+
+extern "C" int icaf_upsample2x(const void* x, int64_t x_ld, void* y, int64_t y_ld, int B, int H, int W, int C, void* stream) {
+  if (!x || !y || C % 8 || x_ld % 8 || y_ld % 8) return set_error(ICAF_ERR_BAD_ARG, "upsample2x: bad argument");
+  long long total = (long long)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, x_ld, (__half*)y, y_ld, B, H, W, C / 8);
+  return check_launch("upsample2x");
+}
+
+extern "C" int icaf_copy_channels(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t pixels, int C, void* stream) {
+  if (!x || !y || C % 8 || x_ld % 8 || y_ld % 8) return set_error(ICAF_ERR_BAD_ARG, "copy_channels: bad argument");
+  copy_channels_kernel<<<blocks_for(pixels * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, x_ld, (__half*)y, y_ld,
+                                                                                          pixels, C / 8);
+  return check_launch("copy_channels");
+}
+
+extern "C" int icaf_dmff_pool_tokens(const void* x_vis, const void* x_ir, int64_t x_ld, const void* pos_vis,
+                                     const void* pos_ir, const float* mix, void* tok_vis, void* tok_ir, int B, int H,
+                                     int W, int C, int nh, int nw, int n_pad, void* stream) {
+  if (!x_vis || !x_ir || !pos_vis || !pos_ir || !mix || !tok_vis || !tok_ir) return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens: null pointer");
+  if (C % 8 || x_ld % 8 || nh < 1 || nw < 1 || nh > H || nw > W || n_pad < nh * nw || n_pad % 8)
+    return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens: bad shape (token grid must not exceed the map)");
+  PoolTokParams P;
+  P.x[0] = (const __half*)x_vis; P.x[1] = (const __half*)x_ir;
+  P.pos[0] = (const __half*)pos_vis; P.pos[1] = (const __half*)pos_ir;
+  P.tok[0] = (__half*)tok_vis; P.tok[1] = (__half*)tok_ir;
+  P.mix = mix; P.x_ld = x_ld;
+  P.B = B; P.H = H; P.W = W; P.C8 = C / 8; P.nh = nh; P.nw = nw; P.n_pad = n_pad;
+  // AdaptivePool2d geometry, models/common.py:878-882 (identity when the map is not larger than the grid)
+  P.sh = H / nh; P.sw = W / nw;
+  P.kh = H - (nh - 1) * P.sh; P.kw = W - (nw - 1) * P.sw;
+  long long total = (long long)B * n_pad * P.C8;
+  dim3 grid(blocks_for(total, 128), 2);
+  dmff_pool_tokens_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("dmff_pool_tokens");
+}
+
+extern "C" int icaf_layernorm(const void* x0, const void* x1, const float* g0, const float* b0, const float* g1,
+                              const float* b1, void* y0, void* y1, int64_t rows, int C, float eps, void* stream) {
+  if (!x0 || !y0 || !g0 || !b0 || (x1 && (!y1 || !g1 || !b1))) return set_error(ICAF_ERR_BAD_ARG, "layernorm: null pointer");
+  if (C % 8 || C > 2048 || rows < 1) return set_error(ICAF_ERR_UNSUPPORTED, "layernorm: C must be a multiple of 8, <= 2048");
+  LnParams P;
+  P.x[0] = (const __half*)x0; P.x[1] = (const __half*)x1; P.y[0] = (__half*)y0; P.y[1] = (__half*)y1;
+  P.g[0] = g0; P.g[1] = g1; P.b[0] = b0; P.b[1] = b1; P.rows = rows; P.C = C; P.eps = eps;
+  dim3 grid(blocks_for(rows, 4), x1 ? 2 : 1);
+  layernorm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("layernorm");
+}
+
+extern "C" int icaf_dmff_upsample_cat(const void* tok_vis, const void* tok_ir, int n_pad, const void* x_vis,
+                                      const void* x_ir, int64_t x_ld, void* y, int64_t y_ld, int B, int H, int W, int C,
+                                      int nh, int nw, int mode, void* stream) {
+  if (!tok_vis || !tok_ir || !x_vis || !x_ir || !y) return set_error(ICAF_ERR_BAD_ARG, "dmff_upsample_cat: null pointer");
+  if (C % 8 || x_ld % 8 || y_ld % 8 || y_ld < 2 * C || n_pad < nh * nw) return set_error(ICAF_ERR_BAD_ARG, "dmff_upsample_cat: bad shape");
+  UpCatParams P;
+  P.tok[0] = (const __half*)tok_vis; P.tok[1] = (const __half*)tok_ir;
+  P.x[0] = (const __half*)x_vis; P.x[1] = (const __half*)x_ir; P.y = (__half*)y;
+  P.x_ld = x_ld; P.y_ld = y_ld; P.B = B; P.H = H; P.W = W; P.C8 = C / 8; P.nh = nh; P.nw = nw; P.n_pad = n_pad; P.mode = mode;
+  P.sy = float(nh) / float(H); P.sx = float(nw) / float(W);
+  long long total = (long long)B * H * W * P.C8;
+  dim3 grid(blocks_for(total, 256), 2);
+  dmff_upsample_cat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("dmff_upsample_cat");
+}
+
+extern "C" int icaf_detect_decode(const void* p, int64_t p_ld, void* x_out, void* z, void* logits, int B, int ny, int nx,
+                                  int na, int no, int total_rows, int row_off, float stride, const float* anchors_host,
+                                  void* stream) {
+  if (!p || !x_out || !z || !logits || !anchors_host || na < 1 || na > 8 || no < 6) return set_error(ICAF_ERR_BAD_ARG, "detect_decode: bad argument");
+  DetectParams P;
+  P.p = (const __half*)p; P.p_ld = p_ld; P.x_out = (__half*)x_out; P.z = (__half*)z; P.logits = (__half*)logits;
+  P.B = B; P.ny = ny; P.nx = nx; P.na = na; P.no = no; P.total_rows = total_rows; P.row_off = row_off; P.stride = stride;
+  for (int i = 0; i < na * 2; ++i) P.anchors[i] = anchors_host[i];
+  long long total = (long long)B * na * ny * nx;
+  detect_decode_kernel<<<blocks_for(total, 128), 128, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("detect_decode");
+}

@@ -1,0 +1,351 @@
+// Implicit-GEMM Conv(+folded BN)+bias+activation(+residual) / Linear on the 5th-gen tensor cores (tcgen05).
+//
+//   C[M=B*Ho*Wo, N=Cout] = A[M, K=kh*kw*Cin] * W[N, K]^T           fp16 operands, fp32 accumulate in TMEM
+//
+// A is never materialised (no im2col): producer warps gather 16-byte channel runs of the NHWC input straight
+// into the 128B-swizzled K-major shared-memory layout the UMMA descriptors expect (zero-fill = padding).
+// CTA = one 128 x BN output tile.  Warp roles (160 threads):
+//   warps 0-3 : gather producers (cp.async, 4 rows x 128 B per warp instruction -> fully coalesced),
+//               then the epilogue (thread t owns TMEM lane t = output row t)
+//   warp  4   : TMEM allocator + single-thread tcgen05.mma issuer
+// Pipelines: smem ring full[]/empty[] (producers <-> MMA), accum_full (MMA -> epilogue).
+#include "icaf_internal.cuh"
+
+namespace icaf {
+
+constexpr int BM = 128;
+constexpr int BK = 64;              // 64 halfs = one 128-byte swizzle atom row
+constexpr int kStages = 4;
+constexpr int kLag = 2;             // cp.async groups kept in flight per producer thread
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 160;
+
+struct ConvProblem {
+  const __half* x; const __half* w; const float* bias; const __half* res; __half* y;
+  const float* alpha; const float* beta;
+  long long x_ld, res_ld, y_ld;
+};
+struct ConvParams {
+  ConvProblem p[2];
+  int M, N, K, k_pad, w_rows;
+  int B, Hi, Wi, Cin, Ho, Wo, kh, kw, stride, pad;
+  int act, epi;
+};
+
+__device__ __forceinline__ ConvProblem pick_problem(const ConvParams& P, unsigned z) {
+  ConvProblem r;
+  r.x = z ? P.p[1].x : P.p[0].x;          r.w = z ? P.p[1].w : P.p[0].w;
+  r.bias = z ? P.p[1].bias : P.p[0].bias; r.res = z ? P.p[1].res : P.p[0].res;
+  r.y = z ? P.p[1].y : P.p[0].y;          r.alpha = z ? P.p[1].alpha : P.p[0].alpha;
+  r.beta = z ? P.p[1].beta : P.p[0].beta; r.x_ld = z ? P.p[1].x_ld : P.p[0].x_ld;
+  r.res_ld = z ? P.p[1].res_ld : P.p[0].res_ld; r.y_ld = z ? P.p[1].y_ld : P.p[0].y_ld;
+  return r;
+}
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOff + 128 + 1024;   // barriers + tmem slot, + 1024 alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(const ConvParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  using L = SmemLayout<BN>;
+  const uint32_t bar_base = smem_base + L::kBarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  const ConvProblem pr = pick_problem(P, blockIdx.z);   // by value: a dynamic param index would spill to local
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int nkb = P.k_pad / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), kProducerThreads);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(smem_gen + L::kBarOff + 8 * (2 * kStages + 1));
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int c = tid & 7;          // 16-byte chunk within the 128-byte K row
+    const int r0 = tid >> 3;        // rows r0 + 16*i
+    const uint32_t sw = uint32_t(c ^ (r0 & 7)) << 4;
+    // per-row pixel decomposition (constant across the K loop)
+    uint32_t base[8];
+    int iy0[8], ix0[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m = m0 + r0 + 16 * i;
+      bool mv = m < P.M;
+      int mm = mv ? m : 0;
+      int ox = mm % P.Wo;
+      int t = mm / P.Wo;
+      int oy = t % P.Ho;
+      int b = t / P.Ho;
+      base[i] = uint32_t(b) * uint32_t(P.Hi * P.Wi);
+      iy0[i] = mv ? oy * P.stride - P.pad : -100000;   // invalid rows fall out of bounds -> zero fill
+      ix0[i] = ox * P.stride - P.pad;
+    }
+    const __half* wrow = pr.w + size_t(n0 + r0) * P.k_pad + c * 8;
+
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(empty_bar(s), ph ^ 1);
+      const uint32_t sa = smem_base + s * L::kStageBytes;
+      const uint32_t sb = sa + L::kABytes;
+      // A: which filter tap / channel run does this thread's chunk cover?
+      const int k0 = kb * BK + c * 8;
+      const bool kvalid = k0 < P.K;
+      const int tap = k0 / P.Cin;
+      const int ch = k0 - tap * P.Cin;
+      const int ky = tap / P.kw;
+      const int kx = tap - ky * P.kw;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int iy = iy0[i] + ky, ix = ix0[i] + kx;
+        bool ok = kvalid && (unsigned)iy < (unsigned)P.Hi && (unsigned)ix < (unsigned)P.Wi;
+        size_t off = ok ? (size_t(base[i] + uint32_t(iy * P.Wi + ix)) * size_t(pr.x_ld) + ch) : 0;
+        cp_async16(sa + uint32_t(r0 + 16 * i) * 128u + sw, pr.x + off, ok);
+      }
+      // B: packed filter rows (always in-bounds in K; rows beyond w_rows zero-filled)
+#pragma unroll
+      for (int i = 0; i < BN / 16; ++i) {
+        bool ok = (n0 + r0 + 16 * i) < P.w_rows;
+        cp_async16(sb + uint32_t(r0 + 16 * i) * 128u + sw, ok ? wrow + size_t(16 * i) * P.k_pad + kb * BK : pr.w, ok);
+      }
+      cp_async_commit();
+      if (kb >= kLag) {
+        cp_async_wait<kLag>();
+        fence_proxy_async_smem();
+        mbar_arrive(full_bar((kb - kLag) % kStages));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int kb = (nkb > kLag ? nkb - kLag : 0); kb < nkb; ++kb) mbar_arrive(full_bar(kb % kStages));
+
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int row = tid;                   // TMEM lane == tile row
+    const int m = m0 + row;
+    const bool mvalid = m < P.M;
+    const uint32_t trow = tmem_d + (uint32_t(warp * 32) << 16);
+    float alpha = 0.f, beta = 1.f;
+    if (P.epi & ICAF_EPI_SCALED_RES) { alpha = *pr.alpha; beta = *pr.beta; }
+    const float rbias = ((P.epi & ICAF_EPI_BIAS_ROW) && pr.bias && mvalid) ? pr.bias[m] : 0.f;
+    __half* yrow = pr.y + size_t(mvalid ? m : 0) * pr.y_ld;
+    const __half* rrow = pr.res ? pr.res + size_t(mvalid ? m : 0) * pr.res_ld : nullptr;
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t acc[32];
+      __syncwarp();
+      tmem_ld32(trow + cb, acc);      // .sync.aligned: executed by the whole (converged) warp
+      tmem_ld_wait();
+      const int nb = n0 + cb;
+      if (mvalid && nb < P.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = __uint_as_float(acc[j]);
+          if (P.epi & ICAF_EPI_BIAS_ROW) t += rbias;
+          else if (pr.bias && nb + j < P.N) t += __ldg(pr.bias + nb + j);
+          if (P.act == ICAF_ACT_SILU) t = silu_f(t);
+          else if (P.act == ICAF_ACT_GELU) t = gelu_erf_f(t);
+          v[j] = t;
+        }
+        const bool full = (nb + 32 <= P.N);
+        const bool vec = full && ((reinterpret_cast<uintptr_t>(yrow + nb) & 15) == 0) &&
+                         (!rrow || (reinterpret_cast<uintptr_t>(rrow + nb) & 15) == 0);
+        if (vec) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (rrow) {
+              uint4 rr = *reinterpret_cast<const uint4*>(rrow + nb + q * 8);
+              const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 rf = __half22float2(rh[e]);
+                if (P.epi & ICAF_EPI_SCALED_RES) {
+                  v[q * 8 + 2 * e] = alpha * rf.x + beta * v[q * 8 + 2 * e];
+                  v[q * 8 + 2 * e + 1] = alpha * rf.y + beta * v[q * 8 + 2 * e + 1];
+                } else {
+                  v[q * 8 + 2 * e] += rf.x;
+                  v[q * 8 + 2 * e + 1] += rf.y;
+                }
+              }
+            }
+            uint4 o;
+            o.x = pack_half2(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = pack_half2(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = pack_half2(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = pack_half2(v[q * 8 + 6], v[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(yrow + nb + q * 8) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nb + j >= P.N) continue;
+            float t = v[j];
+            if (rrow) {
+              float rf = __half2float(rrow[nb + j]);
+              t = (P.epi & ICAF_EPI_SCALED_RES) ? alpha * rf + beta * t : t + rf;
+            }
+            yrow[nb + j] = __float2half_rn(t);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + s * L::kStageBytes;
+        const uint64_t ad = umma_desc_sw128(sa);
+        const uint64_t bd = umma_desc_sw128(sa + L::kABytes);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_f16_ss(tmem_d, ad + uint64_t(2 * k), bd + uint64_t(2 * k), idesc, (kb | k) != 0);
+        umma_commit(empty_bar(s));
+        if (kb == nkb - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_d);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CUDA-core reference with the identical contract (tests only).
+__global__ void conv_gemm_simt_kernel(const ConvParams P) {
+  const ConvProblem pr = pick_problem(P, blockIdx.z);
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)P.M * P.N) return;
+  int n = int(idx % P.N);
+  int m = int(idx / P.N);
+  int ox = m % P.Wo, t = m / P.Wo, oy = t % P.Ho, b = t / P.Ho;
+  float acc = 0.f;
+  for (int ky = 0; ky < P.kh; ++ky)
+    for (int kx = 0; kx < P.kw; ++kx) {
+      int iy = oy * P.stride - P.pad + ky, ix = ox * P.stride - P.pad + kx;
+      if ((unsigned)iy >= (unsigned)P.Hi || (unsigned)ix >= (unsigned)P.Wi) continue;
+      const __half* xp = pr.x + (size_t(b) * P.Hi * P.Wi + size_t(iy) * P.Wi + ix) * pr.x_ld;
+      const __half* wp = pr.w + size_t(n) * P.k_pad + (ky * P.kw + kx) * P.Cin;
+      for (int c = 0; c < P.Cin; ++c) acc += __half2float(xp[c]) * __half2float(wp[c]);
+    }
+  if (pr.bias) acc += (P.epi & ICAF_EPI_BIAS_ROW) ? pr.bias[m] : pr.bias[n];
+  if (P.act == ICAF_ACT_SILU) acc = silu_f(acc);
+  else if (P.act == ICAF_ACT_GELU) acc = gelu_erf_f(acc);
+  if (pr.res) {
+    float rf = __half2float(pr.res[size_t(m) * pr.res_ld + n]);
+    acc = (P.epi & ICAF_EPI_SCALED_RES) ? (*pr.alpha) * rf + (*pr.beta) * acc : acc + rf;
+  }
+  pr.y[size_t(m) * pr.y_ld + n] = __float2half_rn(acc);
+}
+
+static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, ConvParams& P) {
+  if (!g || !io || n_io < 1 || n_io > 2) return set_error(ICAF_ERR_BAD_ARG, "conv2d: need 1 or 2 problems");
+  if (!(g->Cin == 4 || g->Cin % 8 == 0)) return set_error(ICAF_ERR_UNSUPPORTED, "conv2d: Cin must be 4 or a multiple of 8");
+  if (g->Cin == 4 && (g->Wi % 2 || g->stride % 2 || g->pad % 2 || g->kw % 2))
+    return set_error(ICAF_ERR_UNSUPPORTED, "conv2d: packed-image (Cin=4) path needs even Wi, stride, pad, kw");
+  if (g->k_pad % 64 || g->k_pad < g->kh * g->kw * g->Cin) return set_error(ICAF_ERR_BAD_ARG, "conv2d: bad k_pad");
+  if (g->w_rows < g->Cout) return set_error(ICAF_ERR_BAD_ARG, "conv2d: w_rows < Cout");
+  long long M = (long long)g->B * g->Ho * g->Wo;
+  if (M <= 0 || M > 0x7fffffffLL || (long long)g->B * g->Hi * g->Wi > 0x7fffffffLL)
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d: size out of range");
+  if ((g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES)) == (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES))
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d: ADD_RES and SCALED_RES are exclusive");
+  P.M = int(M); P.N = g->Cout; P.K = g->kh * g->kw * g->Cin; P.k_pad = g->k_pad; P.w_rows = g->w_rows;
+  P.B = g->B; P.Hi = g->Hi; P.Wi = g->Wi; P.Cin = g->Cin; P.Ho = g->Ho; P.Wo = g->Wo;
+  P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad = g->pad; P.act = g->act; P.epi = g->epi;
+  for (int i = 0; i < 2; ++i) {
+    const icaf_conv_io& s = io[i < n_io ? i : 0];
+    bool need_res = g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES);
+    if (!s.x || !s.w || !s.y || (need_res && !s.res) || ((g->epi & ICAF_EPI_SCALED_RES) && (!s.alpha || !s.beta)))
+      return set_error(ICAF_ERR_BAD_ARG, "conv2d: null pointer");
+    if ((reinterpret_cast<uintptr_t>(s.x) & 15) || (reinterpret_cast<uintptr_t>(s.w) & 15) || (s.x_ld % 8 && g->Cin != 4) ||
+        (g->Cin == 4 && s.x_ld != 4))
+      return set_error(ICAF_ERR_BAD_ARG, "conv2d: x / w must be 16-byte aligned with x_ld a multiple of 8");
+    P.p[i] = ConvProblem{(const __half*)s.x, (const __half*)s.w, s.bias, need_res ? (const __half*)s.res : nullptr,
+                         (__half*)s.y, s.alpha, s.beta, s.x_ld, s.res_ld, s.y_ld};
+  }
+  return ICAF_OK;
+}
+
+template <int BN>
+static int launch_tc(const ConvParams& P, int n_io, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  static bool configured = false;   // idempotent attribute; benign race
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute");
+    configured = true;
+  }
+  dim3 grid((P.M + BM - 1) / BM, (P.N + BN - 1) / BN, n_io);
+  conv_gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(P);
+  return check_launch("conv2d_fwd");
+}
+
+}  // namespace icaf
+
+using namespace icaf;
+
+extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream) {
+  ConvParams P;
+  int rc = fill_params(g, io, n_io, P);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // Tile width: the widest BN that still yields at least ~one CTA per SM; small problems take BN=32
+  // so that more SMs share the K loop.
+  const long long mt = (P.M + BM - 1) / BM;
+  const int sms = sm_count_cached();
+  auto ctas = [&](int bn) { return mt * ((P.N + bn - 1) / bn) * n_io; };
+  int bn = 32;
+  if (P.N > 64 && ctas(128) >= sms) bn = 128;
+  else if (P.N > 32 && ctas(64) >= sms) bn = 64;
+  switch (bn) {
+    case 128: return launch_tc<128>(P, n_io, st);
+    case 64: return launch_tc<64>(P, n_io, st);
+    default: return launch_tc<32>(P, n_io, st);
+  }
+}
+
+extern "C" int icaf_conv2d_fwd_simt(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream) {
+  ConvParams P;
+  int rc = fill_params(g, io, n_io, P);
+  if (rc) return rc;
+  long long total = (long long)P.M * P.N;
+  dim3 grid((unsigned)((total + 255) / 256), 1, n_io);
+  conv_gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("conv2d_fwd_simt");
+}

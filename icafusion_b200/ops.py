@@ -1,0 +1,284 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, torch tensors out, kernels on the current stream.
+
+Activations are fp16 NHWC tensors (shape (B,H,W,C)); a channel slice ``t[..., a:b]`` of a
+contiguous tensor is a valid "view" (pixel pitch = t.stride(2)).  PyTorch only provides device
+memory and the stream here -- every computation is a kernel from libicaf_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, EPI_ADD_RES, EPI_BIAS_ROW, EPI_SCALED_RES  # noqa: F401
+
+
+_LAUNCHES = 0          # kernels of libicaf_b200 enqueued so far (each C-ABI compute call launches exactly one)
+_PROFILE = None        # when a list: every call appends (name, work dict, start event, end event)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+class profile:
+    """Context manager: bracket every libicaf_b200 launch with CUDA events on its stream.
+    `with ops.profile() as recs: ...; torch.cuda.synchronize(); recs.summary()`"""
+
+    def __enter__(self):
+        global _PROFILE
+        self.records = []
+        _PROFILE = self.records
+        return self
+
+    def __exit__(self, *a):
+        global _PROFILE
+        _PROFILE = None
+
+    def summary(self):
+        out = {}
+        for name, work, e0, e1 in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += work.get("flops", 0.0)
+            d["bytes"] += work.get("bytes", 0.0)
+        return out
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _call(name: str, fn, args, work=None):
+    """Invoke one C-ABI kernel launcher on the current stream (optionally event-bracketed)."""
+    global _LAUNCHES
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args, _stream())
+        e1.record()
+        _PROFILE.append((name, work or {}, e0, e1))
+    else:
+        rc = fn(*args, _stream())
+    _lib.check(rc, name)
+    _LAUNCHES += 1
+
+
+def _check_view(t: torch.Tensor, what: str) -> int:
+    """Validate an fp16 NHWC view and return its pixel pitch (elements)."""
+    if t.dtype != torch.float16 or not t.is_cuda or t.dim() != 4:
+        raise ValueError(f"{what}: expected a CUDA fp16 (B,H,W,C) tensor, got {t.dtype} {tuple(t.shape)} on {t.device}")
+    B, H, W, Cc = t.shape
+    ld = t.stride(2) if W > 1 else (t.stride(1) if H > 1 else (t.stride(0) if B > 1 else Cc))
+    ok = t.stride(3) == 1 and (W == 1 or t.stride(2) == ld) and (H == 1 or t.stride(1) == W * ld) and \
+        (B == 1 or t.stride(0) == H * W * ld)
+    if not ok:
+        raise ValueError(f"{what}: not a dense NHWC view (shape {tuple(t.shape)}, strides {t.stride()})")
+    return ld
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class PackedConv:
+    """Filter bank in the layout the implicit-GEMM kernel consumes: fp16 [w_rows][k_pad], K order (ky,kx,c)."""
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]      # fp32 [Cout]
+    cin: int                          # channels consumed per tap (4 for the packed image)
+    cout: int
+    kh: int
+    kw: int
+    stride: int
+    pad: int
+    act: int
+
+
+def pack_conv_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, pad: int, act: int,
+                     device=None) -> PackedConv:
+    """(Cout,Cin,kh,kw) fp32 filter (BN already folded) -> PackedConv.  A 3-channel filter is padded to 4
+    input channels to match the packed image layout (icaf_pack_image)."""
+    cout, cin, kh, kw = weight.shape
+    w = weight.detach().float()
+    if cin == 3:
+        w = torch.cat([w, w.new_zeros(cout, 1, kh, kw)], 1)
+        cin = 4
+    if not (cin == 4 or cin % 8 == 0):
+        raise ValueError(f"conv input channels must be 3/4 or a multiple of 8, got {cin}")
+    K = kh * kw * cin
+    k_pad, rows = round_up(K, 64), round_up(cout, 32)
+    m = w.permute(0, 2, 3, 1).reshape(cout, K)
+    out = torch.zeros(rows, k_pad, dtype=torch.float16, device=device or weight.device)
+    out[:cout, :K] = m.to(out.device, torch.float16)
+    b = None if bias is None else bias.detach().float().to(out.device).contiguous()
+    return PackedConv(out, b, cin, cout, kh, kw, stride, pad, act)
+
+
+def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE, device=None) -> PackedConv:
+    """nn.Linear weight (out,in) as a 1x1 filter bank."""
+    return pack_conv_weight(weight.detach()[:, :, None, None], bias, 1, 0, act, device)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Optional[Sequence[torch.Tensor]] = None,
+           res: Optional[Sequence[torch.Tensor]] = None, scaled: Optional[Sequence] = None,
+           bias_row: bool = False, simt: bool = False) -> List[torch.Tensor]:
+    """Grouped (1 or 2 problems of identical geometry) Conv+bias+act(+residual).
+    `scaled`: per problem (alpha, beta) device fp32 scalars -> y = alpha*res + beta*(acc+bias)."""
+    n = len(xs)
+    assert n in (1, 2) and len(packs) == n
+    p0 = packs[0]
+    B, Hi, Wi, Cx = xs[0].shape
+    if Cx != p0.cin:
+        raise ValueError(f"conv2d: input has {Cx} channels, filter expects {p0.cin}")
+    Ho = (Hi + 2 * p0.pad - p0.kh) // p0.stride + 1
+    Wo = (Wi + 2 * p0.pad - p0.kw) // p0.stride + 1
+    epi = (EPI_BIAS_ROW if bias_row else 0) | (EPI_SCALED_RES if scaled is not None else (EPI_ADD_RES if res is not None else 0))
+    g = _lib.ConvGeom(B, Hi, Wi, p0.cin, Ho, Wo, p0.cout, p0.kh, p0.kw, p0.stride, p0.pad, p0.w.shape[1],
+                      p0.w.shape[0], p0.act, epi)
+    if outs is None:
+        outs = [torch.empty(B, Ho, Wo, p0.cout, dtype=torch.float16, device=xs[0].device) for _ in range(n)]
+    ios = (_lib.ConvIO * n)()
+    for i in range(n):
+        pk = packs[i]
+        if (pk.cin, pk.cout, pk.kh, pk.kw, pk.stride, pk.pad, pk.act) != (p0.cin, p0.cout, p0.kh, p0.kw, p0.stride, p0.pad, p0.act) \
+                or tuple(xs[i].shape) != tuple(xs[0].shape):
+            raise ValueError("conv2d: grouped problems must share one geometry")
+        if tuple(outs[i].shape) != (B, Ho, Wo, p0.cout):
+            raise ValueError(f"conv2d: output shape {tuple(outs[i].shape)} != {(B, Ho, Wo, p0.cout)}")
+        ios[i].x, ios[i].x_ld = xs[i].data_ptr(), _check_view(xs[i], "conv2d input")
+        ios[i].w = pk.w.data_ptr()
+        ios[i].bias = pk.bias.data_ptr() if pk.bias is not None else None
+        ios[i].y, ios[i].y_ld = outs[i].data_ptr(), _check_view(outs[i], "conv2d output")
+        if res is not None:
+            if tuple(res[i].shape) != (B, Ho, Wo, p0.cout):
+                raise ValueError("conv2d: residual shape mismatch")
+            ios[i].res, ios[i].res_ld = res[i].data_ptr(), _check_view(res[i], "conv2d residual")
+        if scaled is not None:
+            ios[i].alpha, ios[i].beta = scaled[i][0].data_ptr(), scaled[i][1].data_ptr()
+    fn = _lib.lib().icaf_conv2d_fwd_simt if simt else _lib.lib().icaf_conv2d_fwd
+    M = B * Ho * Wo
+    kk = p0.kh * p0.kw * p0.cin
+    work = {"flops": 2.0 * M * p0.cout * kk * n,
+            "bytes": 2.0 * n * (B * Hi * Wi * p0.cin + M * p0.cout * (2 if res is not None else 1) + p0.cout * kk)}
+    _call("icaf_conv2d_fwd_simt" if simt else "icaf_conv2d_fwd", fn, (C.byref(g), ios, n), work)
+    return list(outs)
+
+
+def linear(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs=None, res=None, scaled=None,
+           bias_row: bool = False, simt: bool = False) -> List[torch.Tensor]:
+    """Rows-as-pixels view of conv2d: xs are (rows, K) fp16 matrices (row pitch = stride(0))."""
+    def as4(t):
+        return None if t is None else t.unflatten(0, (1, 1, t.shape[0])) if t.dim() == 2 else t
+    o = conv2d([as4(x) for x in xs], packs, None if outs is None else [as4(t) for t in outs],
+               None if res is None else [as4(t) for t in res], scaled, bias_row, simt)
+    return [t[0, 0] for t in o]
+
+
+def pack_image(img: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """(B,3,H,W) fp16 / fp32 / uint8 planar image -> (B,H,W,4) fp16."""
+    if img.dim() != 4 or img.shape[1] != 3 or not img.is_cuda:
+        raise ValueError(f"pack_image: expected a CUDA (B,3,H,W) tensor, got {tuple(img.shape)}")
+    code = {torch.float16: 0, torch.float32: 1, torch.uint8: 2}.get(img.dtype)
+    if code is None:
+        raise ValueError(f"pack_image: unsupported dtype {img.dtype}")
+    img = img.contiguous()
+    B, _, H, W = img.shape
+    out = torch.empty(B, H, W, 4, dtype=torch.float16, device=img.device)
+    _call("icaf_pack_image", _lib.lib().icaf_pack_image, (_ptr(img), code, float(scale), B, H, W, _ptr(out)),
+          {"bytes": float(img.numel() * img.element_size() + out.numel() * 2)})
+    return out
+
+
+def sppf_pool(x: torch.Tensor, y1: torch.Tensor, y2: torch.Tensor, y3: torch.Tensor) -> None:
+    B, H, W, Cc = x.shape
+    ld = _check_view(y1, "sppf y1")
+    assert _check_view(y2, "sppf y2") == ld and _check_view(y3, "sppf y3") == ld
+    _call("icaf_sppf_pool", _lib.lib().icaf_sppf_pool, (_ptr(x), _check_view(x, "sppf x"), _ptr(y1), _ptr(y2), _ptr(y3), ld, B, H, W, Cc),
+          {"bytes": 8.0 * x.numel()})
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, Cc, dtype=torch.float16, device=x.device)
+    _call("icaf_upsample2x", _lib.lib().icaf_upsample2x, (_ptr(x), _check_view(x, "upsample x"), _ptr(out), _check_view(out, "upsample out"),
+                                                        B, H, W, Cc), {"bytes": 10.0 * x.numel()})
+    return out
+
+
+def copy_channels(x: torch.Tensor, out: torch.Tensor) -> None:
+    B, H, W, Cc = x.shape
+    assert tuple(out.shape) == tuple(x.shape)
+    _call("icaf_copy_channels", _lib.lib().icaf_copy_channels, (_ptr(x), _check_view(x, "copy x"), _ptr(out), _check_view(out, "copy out"),
+                                                              B * H * W, Cc), {"bytes": 4.0 * x.numel()})
+
+
+def dmff_pool_tokens(x_vis, x_ir, pos_vis, pos_ir, mix, nh: int, nw: int):
+    """-> (tok_vis, tok_ir) fp16 (B, Npad, C)."""
+    B, H, W, Cc = x_vis.shape
+    n_pad = round_up(nh * nw, 8)
+    tv = torch.empty(B, n_pad, Cc, dtype=torch.float16, device=x_vis.device)
+    ti = torch.empty_like(tv)
+    ld = _check_view(x_vis, "dmff x_vis")
+    assert _check_view(x_ir, "dmff x_ir") == ld
+    _call("icaf_dmff_pool_tokens", _lib.lib().icaf_dmff_pool_tokens,
+          (_ptr(x_vis), _ptr(x_ir), ld, _ptr(pos_vis), _ptr(pos_ir), _ptr(mix), _ptr(tv), _ptr(ti), B, H, W, Cc, nh, nw, n_pad),
+          {"bytes": 4.0 * x_vis.numel() + 4.0 * tv.numel() + 4.0 * pos_vis.numel()})
+    return tv, ti
+
+
+def layernorm(x0, g0, b0, x1=None, g1=None, b1=None, eps: float = 1e-5):
+    """LayerNorm over the last dim of (.., C) fp16 contiguous tensors; one or two problems per launch."""
+    Cc = x0.shape[-1]
+    rows = x0.numel() // Cc
+    y0 = torch.empty_like(x0)
+    y1 = torch.empty_like(x1) if x1 is not None else None
+    assert x0.is_contiguous() and (x1 is None or (x1.is_contiguous() and x1.shape == x0.shape))
+    _call("icaf_layernorm", _lib.lib().icaf_layernorm,
+          (_ptr(x0), _ptr(x1), _ptr(g0), _ptr(b0), _ptr(g1), _ptr(b1), _ptr(y0), _ptr(y1), rows, Cc, float(eps)),
+          {"bytes": 4.0 * x0.numel() * (2 if x1 is not None else 1)})
+    return (y0, y1) if x1 is not None else y0
+
+
+def cross_attention(qk_vis, qk_ir, vt_vis, vt_ir, B: int, N: int, n_pad: int, Cc: int, heads: int, simt: bool = False):
+    out_v = torch.empty(B, n_pad, Cc, dtype=torch.float16, device=qk_vis.device)
+    out_i = torch.empty_like(out_v)
+    fn = _lib.lib().icaf_cross_attention_simt if simt else _lib.lib().icaf_cross_attention
+    for t in (qk_vis, qk_ir, vt_vis, vt_ir):
+        assert t.is_contiguous() and t.dtype == torch.float16
+    _call("icaf_cross_attention_simt" if simt else "icaf_cross_attention", fn,
+          (_ptr(qk_vis), _ptr(qk_ir), _ptr(vt_vis), _ptr(vt_ir), _ptr(out_v), _ptr(out_i), B, N, n_pad, Cc, heads),
+          {"flops": 8.0 * B * N * N * Cc, "bytes": 2.0 * 2 * (3 * B * n_pad * Cc + B * n_pad * Cc)})
+    return out_v, out_i
+
+
+def dmff_upsample_cat(tok_vis, tok_ir, x_vis, x_ir, nh: int, nw: int, mode: int = 0) -> torch.Tensor:
+    B, H, W, Cc = x_vis.shape
+    out = torch.empty(B, H, W, 2 * Cc, dtype=torch.float16, device=x_vis.device)
+    ld = _check_view(x_vis, "dmff x_vis")
+    assert _check_view(x_ir, "dmff x_ir") == ld and tok_vis.is_contiguous() and tok_ir.is_contiguous()
+    _call("icaf_dmff_upsample_cat", _lib.lib().icaf_dmff_upsample_cat,
+          (_ptr(tok_vis), _ptr(tok_ir), tok_vis.shape[1], _ptr(x_vis), _ptr(x_ir), ld, _ptr(out), 2 * Cc, B, H, W, Cc, nh, nw, mode),
+          {"bytes": 2.0 * (2 * x_vis.numel() + out.numel() + 2 * tok_vis.numel())})
+    return out
+
+
+def detect_decode(p: torch.Tensor, na: int, no: int, z: torch.Tensor, logits: torch.Tensor, row_off: int, stride: float,
+                  anchors_px: Sequence[float]) -> torch.Tensor:
+    """p: (B,ny,nx,>=na*no) conv output. Fills rows [row_off, row_off+na*ny*nx) of z/logits; returns x (B,na,ny,nx,no)."""
+    B, ny, nx, _ = p.shape
+    x_out = torch.empty(B, na, ny, nx, no, dtype=torch.float16, device=p.device)
+    anch = (C.c_float * (2 * na))(*[float(a) for a in anchors_px])
+    _call("icaf_detect_decode", _lib.lib().icaf_detect_decode,
+          (_ptr(p), _check_view(p, "detect p"), _ptr(x_out), _ptr(z), _ptr(logits), B, ny, nx, na, no, z.shape[1], row_off, float(stride), anch),
+          {"bytes": 2.0 * (p.numel() + 2.2 * x_out.numel())})
+    return x_out

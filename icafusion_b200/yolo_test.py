@@ -1,0 +1,273 @@
+"""Two-stream model builder: the ``Model`` / ``Detect`` / ``parse_model`` surface of the reference's
+models/yolo_test.py, built on the icafusion_b200 operator classes.
+
+``Model(cfg, ch=3, nc=None)`` accepts the reference's YAML row format (``[from, number, module, args]``) or a
+stock name; ``model(rgb, ir)`` returns what the reference returns (eval: ``(z, logits, [x0,x1,x2])``).
+The walk over the layer list follows Model.forward_once (yolo_test.py:136-163) -- ``f == -4`` routes the IR
+image -- but runs on NHWC tensors and issues the RGB and IR streams as *grouped* launches (one kernel, two
+filter banks), since both streams have identical geometry.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from copy import deepcopy
+from typing import List
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .cfg import load_cfg
+from .common import (C3, SPPF, Bottleneck, Concat, Conv, TransformerFusionBlock, Upsample, to_nchw, to_nhwc)
+from .ops import ACT_NONE
+
+logger = logging.getLogger(__name__)
+
+_MODULES = {"Conv": Conv, "C3": C3, "SPPF": SPPF, "Bottleneck": Bottleneck, "Concat": Concat,
+            "nn.Upsample": Upsample, "Upsample": Upsample, "TransformerFusionBlock": TransformerFusionBlock}
+
+
+def make_divisible(x, divisor):
+    """reference: utils/general.py:234-236"""
+    return math.ceil(x / divisor) * divisor
+
+
+class Detect(nn.Module):
+    """Detection head (reference: models/yolo_test.py:26-70): per level a 1x1 Conv2d to na*(nc+5) channels,
+    reshaped to (B,na,ny,nx,no); in eval additionally sigmoid + grid/anchor decode, concatenated over levels."""
+    stride = None
+    export = False
+
+    def __init__(self, nc=80, anchors=(), ch=()):
+        super().__init__()
+        self.nc = nc
+        self.no = nc + 5
+        self.nl = len(anchors)
+        self.na = len(anchors[0]) // 2
+        self.grid = [torch.zeros(1)] * self.nl
+        a = torch.tensor(anchors).float().view(self.nl, -1, 2)
+        self.register_buffer("anchors", a)
+        self.register_buffer("anchor_grid", a.clone().view(self.nl, 1, -1, 1, 1, 2))
+        self.m = nn.ModuleList(nn.Conv2d(x, self.no * self.na, 1) for x in ch)
+
+    def _packed(self, i):
+        conv = self.m[i]
+        key = (conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version)
+        cache = self.__dict__.setdefault("_icaf_pack", {})
+        if i not in cache or cache[i][0] != key:
+            cache[i] = (key, ops.pack_conv_weight(conv.weight, conv.bias, 1, 0, ACT_NONE))
+        return cache[i][1]
+
+    def run(self, vs: List[torch.Tensor]):
+        """vs: NHWC maps of the nl levels."""
+        B = vs[0].shape[0]
+        rows = [self.na * v.shape[1] * v.shape[2] for v in vs]
+        total = sum(rows)
+        if self.training:
+            raise NotImplementedError("Detect: training-mode forward is not built yet in icafusion_b200")
+        z = torch.empty(B, total, self.no, dtype=torch.float16, device=vs[0].device)
+        logits = torch.empty(B, total, self.no - 5, dtype=torch.float16, device=vs[0].device)
+        anchor_px = self.__dict__.get("_icaf_anchor_px")
+        if anchor_px is None:                      # host copy of anchor_grid (pixels); constant after build
+            anchor_px = self.anchor_grid.detach().float().cpu().view(self.nl, -1).tolist()
+            self.__dict__["_icaf_anchor_px"] = anchor_px
+        xs, off = [], 0
+        for i, v in enumerate(vs):
+            p = ops.conv2d([v], [self._packed(i)])[0]                                   # yolo_test.py:49
+            xs.append(ops.detect_decode(p, self.na, self.no, z, logits, off, float(self.stride[i]), anchor_px[i]))
+            off += rows[i]
+        return z, logits, xs
+
+    def forward(self, x):
+        z, logits, xs = self.run([to_nhwc(t) for t in x])
+        for i in range(self.nl):
+            x[i] = xs[i]                 # the reference overwrites its input list in place (yolo_test.py:49-51)
+        return z, logits, x
+
+
+def fuse_conv_and_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
+    """Fold an eval-mode BatchNorm into the preceding bias-free convolution
+    (same result as the reference's utils/torch_utils.py:182-202)."""
+    fused = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding,
+                      groups=conv.groups, bias=True).requires_grad_(False).to(conv.weight.device, conv.weight.dtype)
+    with torch.no_grad():
+        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).to(conv.weight.dtype)
+        fused.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
+        b = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+        fused.bias.copy_((b - bn.running_mean) * scale + bn.bias)
+    return fused
+
+
+def parse_model(d: dict, ch: List[int]):
+    """Build the layer list from YAML rows (reference: models/yolo_test.py:216-302; the subset of module
+    types the Transfusion configurations use)."""
+    anchors, nc, gd, gw = d["anchors"], d["nc"], d["depth_multiple"], d["width_multiple"]
+    na = (len(anchors[0]) // 2) if isinstance(anchors, list) else anchors
+    no = na * (nc + 5)
+    layers, save, c2 = [], [], ch[-1]
+    for i, (f, n, m, args) in enumerate(d["backbone"] + d["head"]):
+        name = m if isinstance(m, str) else m.__name__
+        if name == "Detect":
+            cls = Detect
+        elif name in _MODULES:
+            cls = _MODULES[name]
+        else:
+            raise NotImplementedError(f"parse_model: module '{name}' is outside the ICAFusion hot path built here")
+        args = [nc if a == "nc" else anchors if a == "anchors" else (None if a == "None" else a) for a in args]
+        n = max(round(n * gd), 1) if n > 1 else n
+        if cls in (Conv, C3, SPPF, Bottleneck):
+            c1 = 3 if (cls is Conv and args[0] == 64) else ch[f]      # yolo_test.py:242-246: both stems take an image
+            c2 = args[0]
+            if c2 != no:
+                c2 = make_divisible(c2 * gw, 8)
+            args = [c1, c2, *args[1:]]
+            if cls is C3:
+                args.insert(2, n)
+                n = 1
+        elif cls is Concat:
+            c2 = sum(ch[x] for x in f)
+        elif cls is Detect:
+            args.append([ch[x] for x in f])
+            if isinstance(args[1], int):
+                args[1] = [list(range(args[1] * 2))] * len(f)
+        elif cls is TransformerFusionBlock:
+            c2 = ch[f[0]]
+            args = [c2, *args[1:]]
+        else:   # Upsample
+            c2 = ch[f]
+        m_ = nn.Sequential(*[cls(*args) for _ in range(n)]) if n > 1 else cls(*args)
+        t = f"{cls.__module__}.{cls.__name__}"
+        np_ = sum(x.numel() for x in m_.parameters())
+        m_.i, m_.f, m_.type, m_.np = i, f, t, np_
+        logger.info("%3s%18s%3s%10.0f  %-40s%-30s" % (i, f, n, np_, t, args))
+        save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
+        layers.append(m_)
+        if i == 0:
+            ch = []
+        ch.append(c2)
+    return nn.Sequential(*layers), sorted(save)
+
+
+class Model(nn.Module):
+    """reference: models/yolo_test.py:73-213"""
+
+    def __init__(self, cfg="yolov5s_Transfusion_kaist", ch=3, nc=None, anchors=None):
+        super().__init__()
+        self.yaml = load_cfg(cfg)
+        ch = self.yaml["ch"] = self.yaml.get("ch", ch)
+        if nc and nc != self.yaml["nc"]:
+            logger.info(f"Overriding model.yaml nc={self.yaml['nc']} with nc={nc}")
+            self.yaml["nc"] = nc
+        if anchors:
+            self.yaml["anchors"] = round(anchors)
+        self.model, self.save = parse_model(deepcopy(self.yaml), ch=[ch])
+        self.names = [str(i) for i in range(self.yaml["nc"])]
+        m = self.model[-1]
+        if isinstance(m, Detect):
+            m.stride = torch.Tensor([8.0, 16.0, 32.0])              # yolo_test.py:104 (hard-coded in the reference)
+            m.anchors /= m.stride.view(-1, 1, 1)
+            self.stride = m.stride
+        for mod in self.modules():                                    # utils/torch_utils.py:144-154
+            if type(mod) is nn.BatchNorm2d:
+                mod.eps = 1e-3
+                mod.momentum = 0.03
+        self._plan_streams()
+
+    # -- two-stream pairing ----------------------------------------------------------------------
+    def _plan_streams(self):
+        """Find the IR stream (first layer with from == -4) and check it mirrors the RGB stream layer by layer."""
+        layers = list(self.model)
+        starts = [m.i for m in layers if m.f == -4]
+        self._ir_start = None
+        if len(starts) != 1:
+            return
+        s = starts[0]
+        if 2 * s > len(layers):
+            return
+        def sig(m):
+            return (type(m), [tuple(p.shape) for p in m.parameters()])
+        for k in range(s):
+            a, b = layers[k], layers[s + k]
+            if sig(a) != sig(b) or (k > 0 and (a.f != -1 or b.f != -1)):
+                return
+        self._ir_start = s
+
+    def forward(self, x, x2, augment=False, profile=False):
+        if augment:
+            raise NotImplementedError("augmented (multi-scale / flip) inference is outside the hot path built here")
+        return self.forward_once(x, x2, profile)
+
+    def forward_once(self, x, x2, profile=False):
+        z, logits, xs = self._forward_nhwc(x, x2)
+        return z, logits, xs
+
+    def _run_layer(self, m, v):
+        if isinstance(m, Conv):
+            return Conv.run([m], [v])[0]
+        if isinstance(m, C3):
+            return C3.run([m], [v])[0]
+        if isinstance(m, SPPF):
+            return SPPF.run([m], [v])[0]
+        if isinstance(m, Upsample):
+            return ops.upsample2x(v)
+        if isinstance(m, Concat):
+            return Concat.run(v)
+        if isinstance(m, TransformerFusionBlock):
+            return m.run(v[0], v[1])
+        if isinstance(m, Detect):
+            return m.run(list(v))
+        raise NotImplementedError(type(m).__name__)
+
+    @staticmethod
+    def _stage(img):
+        if img.dim() != 4 or img.shape[1] != 3:
+            raise ValueError(f"expected (B,3,H,W) images, got {tuple(img.shape)}")
+        if not img.is_cuda:
+            raise RuntimeError("icafusion_b200 runs on CUDA tensors only (no CPU fallback)")
+        if img.dtype not in (torch.float16, torch.float32, torch.uint8):
+            img = img.float()
+        return ops.pack_image(img, 1.0 / 255.0 if img.dtype == torch.uint8 else 1.0)
+
+    def _forward_nhwc(self, rgb, ir):
+        layers = list(self.model)
+        y: List = [None] * len(layers)
+        v_rgb, v_ir = self._stage(rgb), self._stage(ir)
+        start = 0
+        if self._ir_start is not None:
+            s = self._ir_start
+            a, b = v_rgb, v_ir
+            for k in range(s):                       # both streams, one grouped launch per operator
+                ma, mb = layers[k], layers[s + k]
+                run = Conv.run if isinstance(ma, Conv) else C3.run if isinstance(ma, C3) else SPPF.run
+                a, b = run([ma, mb], [a, b])
+                y[k], y[s + k] = a, b
+            start = 2 * s
+            x = b
+        else:
+            x = v_rgb
+        for m in layers[start:]:
+            if m.f == -4:
+                x = v_ir
+            elif m.f != -1:
+                x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+            x = self._run_layer(m, x)
+            y[m.i] = x
+        for k in range(len(y)):
+            if k not in self.save:
+                y[k] = None
+        return x
+
+    def fuse(self):
+        """Fold every Conv's BatchNorm (reference: models/yolo_test.py:182-190)."""
+        for m in self.model.modules():
+            if type(m) is Conv and hasattr(m, "bn"):
+                m.conv = fuse_conv_and_bn(m.conv, m.bn)
+                delattr(m, "bn")
+                m.forward = m.fuseforward
+                m.__dict__.pop("_icaf_pack", None)
+        return self
+
+    def info(self, verbose=False, img_size=640):
+        n_p = sum(x.numel() for x in self.parameters())
+        logger.info(f"Model Summary: {len(list(self.modules()))} layers, {n_p} parameters")

@@ -1,0 +1,145 @@
+/*
+ * icaf_b200 -- C ABI of the B200 (sm_100a) kernels for the ICAFusion hot path:
+ * the two-stream CSPDarknet Conv+BN+SiLU backbone and the DMFF cross-attention fusion block.
+ *
+ * The reference (chanchanchan97/ICAFusion) is pure Python/PyTorch and has no FFI of its own; these
+ * entry points are what a binding for its operator library (models/common.py) calls instead of the
+ * PyTorch ops cited at each function.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - Plain C types only.  Every pointer is a DEVICE pointer unless stated otherwise.
+ *   - Activations are fp16 NHWC "views": a base pointer plus a pixel pitch `ld` in elements, so a
+ *     kernel can read or write a channel slice of a wider (concatenated) buffer in place.
+ *     (A torch tensor of logical shape (B,C,H,W) in channels_last memory format is exactly this.)
+ *   - Token tensors are fp16 (B, Npad, C) with Npad = N rounded up to 8.
+ *   - The caller owns all memory (inputs, outputs, workspaces); the library never allocates device
+ *     memory, never synchronises, and enqueues all work on the `stream` argument (a cudaStream_t),
+ *     so it composes with the PyTorch caching allocator, autograd hooks and CUDA-graph capture.
+ *   - Return value: ICAF_OK or an error code; icaf_last_error() gives a thread-local message.
+ */
+#ifndef ICAF_B200_H
+#define ICAF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICAF_OK 0
+#define ICAF_ERR_BAD_ARG 1
+#define ICAF_ERR_UNSUPPORTED 2
+#define ICAF_ERR_CUDA 3
+
+#define ICAF_ACT_NONE 0
+#define ICAF_ACT_SILU 1 /* nn.SiLU, models/common.py:54 */
+#define ICAF_ACT_GELU 2 /* nn.GELU (erf), models/common.py:706 */
+
+#define ICAF_EPI_BIAS_ROW 1   /* bias indexed by output row (swap-AB linears) instead of channel   */
+#define ICAF_EPI_ADD_RES 2    /* y = act(acc+bias) + res          (Bottleneck shortcut, common.py:194) */
+#define ICAF_EPI_SCALED_RES 4 /* y = alpha*res + beta*(acc+bias)  (LearnableCoefficient pairs, common.py:747-750) */
+
+int icaf_version(void);
+const char* icaf_last_error(void);
+/* Number of SMs of the current device (grid sizing of callers' workspaces); <0 on error. */
+int icaf_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer on the tcgen05 tensor cores.
+ *   y[b,oy,ox,n] = epi( sum_{ky,kx,c} x[b, oy*s-p+ky, ox*s-p+kx, c] * w[n][(ky*kw+kx)*Cin + c] + bias[n] )
+ * Replaces: Conv.forward / Conv.fuseforward (models/common.py:56-60: nn.Conv2d -> BatchNorm2d -> SiLU,
+ * BN folded as utils/torch_utils.py:182-202), nn.Linear calls of CrossAttention / MLP
+ * (common.py:660-668,683-685,704-715; a linear is the 1x1 case with Hi=Wi=1 rows as pixels) and
+ * Detect's nn.Conv2d (models/yolo_test.py:49).
+ * `n_io` problems of identical geometry (e.g. the RGB and the IR stream) run in one launch.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, Hi, Wi, Cin; /* input  NHWC; Cin multiple of 8, or exactly 4 (packed 3-channel image, even Wi) */
+  int Ho, Wo, Cout;   /* output NHWC */
+  int kh, kw, stride, pad;
+  int k_pad;  /* row pitch of the packed filter matrix: multiple of 64, >= kh*kw*Cin (zero padded) */
+  int w_rows; /* rows present in the packed filter matrix (>= Cout, zero padded) */
+  int act;    /* ICAF_ACT_* */
+  int epi;    /* ICAF_EPI_* flags */
+} icaf_conv_geom;
+
+typedef struct {
+  const void* x;     int64_t x_ld;   /* fp16 input view                                   */
+  const void* w;                     /* fp16 [w_rows][k_pad], K order (ky,kx,c)           */
+  const float* bias;                 /* fp32 [Cout] (or [rows] with BIAS_ROW); may be NULL */
+  const void* res;   int64_t res_ld; /* fp16 residual view (ADD_RES / SCALED_RES) or NULL  */
+  void* y;           int64_t y_ld;   /* fp16 output view                                   */
+  const float* alpha;                /* device scalars for SCALED_RES                      */
+  const float* beta;
+} icaf_conv_io;
+
+int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream);
+
+/* Test-only CUDA-core reference of the same contract (slow, obviously-correct); used by tests to
+ * localise tensor-core bugs on the device.  Not called by the product path. */
+int icaf_conv2d_fwd_simt(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input staging: (B,3,H,W) planar image -> fp16 NHWC with C padded to 4 (r,g,b,0).
+ * Replaces the `.half()` / `/255` staging of detect_twostream.py:70-80 / train.py:295-297.
+ * src_dtype: 0 = fp16, 1 = fp32, 2 = uint8 (scaled by `scale`, e.g. 1/255).
+ * ------------------------------------------------------------------------------------------- */
+int icaf_pack_image(const void* src, int src_dtype, float scale, int B, int H, int W, void* dst, void* stream);
+
+/* SPPF's three chained MaxPool2d(5,1,2) (models/common.py:259-266): y1,y2,y3 written as channel
+ * slices; x is (B,H,W,C) view. */
+int icaf_sppf_pool(const void* x, int64_t x_ld, void* y1, void* y2, void* y3, int64_t y_ld, int B, int H, int W,
+                   int C, void* stream);
+
+/* nn.Upsample(None, 2, 'nearest') (yolov5l_Transfusion_kaist.yaml:48,53) into a channel slice. */
+int icaf_upsample2x(const void* x, int64_t x_ld, void* y, int64_t y_ld, int B, int H, int W, int C, void* stream);
+
+/* Copy a channel slice (Concat, models/common.py:313-321, when producer-side slice writes are not possible). */
+int icaf_copy_channels(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t pixels, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DMFF block pieces (models/common.py:762-891).
+ * ------------------------------------------------------------------------------------------- */
+/* AdaptivePool2d avg+max (common.py:868-891) + LearnableWeights (:579-587) + flatten/permute + pos_emb (:817-823):
+ *   tok[b, n, c] = w[0]*avgpool + w[1]*maxpool + pos[n, c];  rows n in [N, Npad) are zeroed.
+ * Two modalities per launch (x0/x1 ...). `mix` = 4 device floats {w1_vis, w2_vis, w1_ir, w2_ir}. */
+int icaf_dmff_pool_tokens(const void* x_vis, const void* x_ir, int64_t x_ld, const void* pos_vis, const void* pos_ir,
+                          const float* mix, void* tok_vis, void* tok_ir, int B, int H, int W, int C, int nh, int nw,
+                          int n_pad, void* stream);
+
+/* nn.LayerNorm over the last dim (eps 1e-5) of `rows` x C fp16 tokens; two independent problems per launch
+ * (x1 may be NULL).  gamma/beta are fp32 [C].  Replaces common.py:660,665,749-750. */
+int icaf_layernorm(const void* x0, const void* x1, const float* g0, const float* b0, const float* g1,
+                   const float* b1, void* y0, void* y1, int64_t rows, int C, float eps, void* stream);
+
+/* Bidirectional cross-attention core (common.py:670-684), flash style: no N x N score matrix in HBM.
+ *   out_vis = softmax(q_ir k_vis^T / sqrt(d)) v_vis ;  out_ir = softmax(q_vis k_ir^T / sqrt(d)) v_ir
+ * qk_*: fp16 (B, Npad, 2C) rows [q | k] as the fused projection emits them;
+ * vt_*: fp16 (C, B*Npad) value projection stored transposed (swap-AB linear);
+ * out_*: fp16 (B, Npad, C) heads merged (the layout out_proj consumes). */
+int icaf_cross_attention(const void* qk_vis, const void* qk_ir, const void* vt_vis, const void* vt_ir, void* out_vis,
+                         void* out_ir, int B, int N, int n_pad, int C, int heads, void* stream);
+
+/* Test-only CUDA-core reference of icaf_cross_attention (same contract). */
+int icaf_cross_attention_simt(const void* qk_vis, const void* qk_ir, const void* vt_vis, const void* vt_ir,
+                              void* out_vis, void* out_ir, int B, int N, int n_pad, int C, int heads, void* stream);
+
+/* Token map -> feature map tail (common.py:827-840): reshape (B,nh,nw,C), F.interpolate to (H,W)
+ * (mode 0 = bilinear align_corners=False [eval], 1 = nearest [train]), add the stream's own features,
+ * write both modalities into one (B,H,W,2C) buffer = the Concat that feeds conv1x1_out. */
+int icaf_dmff_upsample_cat(const void* tok_vis, const void* tok_ir, int n_pad, const void* x_vis, const void* x_ir,
+                           int64_t x_ld, void* y, int64_t y_ld, int B, int H, int W, int C, int nh, int nw, int mode,
+                           void* stream);
+
+/* Detect head decode (models/yolo_test.py:49-65) for one level.  `p` is the 1x1-conv output
+ * (B,ny,nx,p_ld) fp16 with na*no valid channels.  Writes
+ *   x_out  (B,na,ny,nx,no) fp16  raw,   z (B, total_rows, no) rows [row_off, row_off+na*ny*nx) decoded,
+ *   logits (B, total_rows, no-5) same rows.  anchors: host array na*2 floats (pixels). */
+int icaf_detect_decode(const void* p, int64_t p_ld, void* x_out, void* z, void* logits, int B, int ny, int nx, int na,
+                       int no, int total_rows, int row_off, float stride, const float* anchors_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICAF_B200_H */

@@ -1,0 +1,109 @@
+"""tcgen05 implicit-GEMM conv / linear kernel vs the CPU oracle (torch fp32 conv on the same fp16-rounded
+operands) and vs the on-device CUDA-core reference.  All calls go through the C ABI."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import err, nchw, nhwc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.5e-3   # fp16 output rounding (2^-11) + fp32 accumulation-order noise, norm-wise
+
+
+def _mk(B, Cin, H, W, Cout, k, s, p, seed=0, bias=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, H, W, generator=g).half()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).half()
+    b = torch.randn(Cout, generator=g) * 0.5 if bias else None
+    return x, w, b
+
+
+def _ref(x, w, b, s, p, act):
+    y = F.conv2d(x.float(), w.float(), b, stride=s, padding=p)
+    if act == 1:
+        y = F.silu(y)
+    elif act == 2:
+        y = F.gelu(y)
+    return y
+
+
+CASES = [
+    # B, Cin, H,  W,  Cout, k, s, p, act
+    (1, 64, 16, 20, 64, 1, 1, 0, 1),      # 1x1, partial last M tile
+    (1, 64, 16, 20, 128, 3, 1, 1, 1),     # 3x3 same
+    (1, 32, 32, 40, 64, 3, 2, 1, 1),      # stride 2, Cin < 64: one K block spans two taps
+    (2, 3, 64, 80, 32, 6, 2, 2, 1),       # image stem (packed NHWC4 input)
+    (1, 128, 16, 20, 18, 1, 1, 0, 0),     # Detect head: N=18, no activation
+    (1, 128, 64, 80, 128, 3, 1, 1, 1),    # M=5120
+    (2, 64, 128, 160, 256, 1, 1, 0, 1),   # many tiles -> BN=128 path
+    (1, 256, 16, 20, 256, 3, 1, 1, 1),    # deep K (36 K blocks), few tiles -> BN=32 path
+    (1, 8, 9, 11, 40, 3, 1, 1, 2),        # odd sizes, Cin=8, GELU
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_matches_oracle(cuda_device, case):
+    from icafusion_b200 import ops
+    B, Cin, H, W, Cout, k, s, p, act = case
+    x, w, b = _mk(B, Cin, H, W, Cout, k, s, p)
+    pk = ops.pack_conv_weight(w.float(), b, s, p, act, device=cuda_device)
+    xv = ops.pack_image(x.to(cuda_device)) if Cin == 3 else nhwc(x).to(cuda_device)
+    y = ops.conv2d([xv], [pk])[0]
+    y_simt = ops.conv2d([xv], [pk], simt=True)[0]
+    torch.cuda.synchronize()
+    ref = _ref(x, w, b, s, p, act)
+    assert err(nchw(y_simt), ref) < TOL, "CUDA-core reference kernel disagrees with the oracle"
+    assert err(nchw(y), ref) < TOL
+    assert err(y, y_simt) < TOL
+
+
+def test_grouped_residual_and_slices(cuda_device):
+    """Two problems per launch, fused residual add, input read from / output written into channel slices."""
+    from icafusion_b200 import ops
+    B, C, H, W = 2, 64, 16, 20
+    xs, ws, bs, refs, packs, outs, ress, xin = [], [], [], [], [], [], [], []
+    for i in range(2):
+        x, w, b = _mk(B, C, H, W, C, 3, 1, 1, seed=10 + i)
+        wide = torch.randn(B, H, W, 2 * C).half().to(cuda_device)          # input lives in a slice of a wider buffer
+        wide[..., C:] = nhwc(x).to(cuda_device)
+        res = torch.randn(B, C, H, W).half()
+        out_wide = torch.zeros(B, H, W, 3 * C, dtype=torch.float16, device=cuda_device)
+        xin.append(wide[..., C:]); ress.append(nhwc(res).to(cuda_device)); outs.append(out_wide[..., C:2 * C])
+        packs.append(ops.pack_conv_weight(w.float(), b, 1, 1, 1, device=cuda_device))
+        refs.append(_ref(x, w, b, 1, 1, 1) + res.float())
+        xs.append(out_wide)
+    ops.conv2d(xin, packs, outs, ress)
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert err(nchw(outs[i]), refs[i]) < TOL
+        assert float(xs[i][..., :C].abs().max()) == 0 and float(xs[i][..., 2 * C:].abs().max()) == 0   # neighbours untouched
+
+
+def test_linear_epilogues(cuda_device):
+    """GELU linear; scaled residual (alpha*res + beta*(xW^T+b)); swap-AB with per-row bias."""
+    from icafusion_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    rows, K, N = 208, 128, 512
+    x = torch.randn(rows, K, generator=g).half()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).half()
+    b = torch.randn(N, generator=g)
+    xd = x.to(cuda_device)
+    y = ops.linear([xd], [ops.pack_linear(w.float(), b, ops.ACT_GELU, device=cuda_device)])[0]
+    assert err(y, F.gelu(F.linear(x.float(), w.float(), b))) < TOL
+    # scaled residual
+    w2 = (torch.randn(K, N, generator=g) / N ** 0.5).half()
+    b2 = torch.randn(K, generator=g)
+    res = torch.randn(rows, K, generator=g).half()
+    coef = torch.tensor([0.8, 1.3], device=cuda_device)
+    h = torch.randn(rows, N, generator=g).half()
+    y2 = ops.linear([h.to(cuda_device)], [ops.pack_linear(w2.float(), b2, device=cuda_device)], res=[res.to(cuda_device)],
+                    scaled=[(coef[0:1], coef[1:2])])[0]
+    assert err(y2, 0.8 * res.float() + 1.3 * F.linear(h.float(), w2.float(), b2)) < TOL
+    # swap-AB: out[C, rows] = Wv . x^T + bv[:, None]
+    wv = (torch.randn(K, K, generator=g) / K ** 0.5).half()
+    bv = torch.randn(K, generator=g)
+    tok = ops.PackedConv(xd, bv.to(cuda_device), K, rows, 1, 1, 1, 0, ops.ACT_NONE)
+    vt = ops.linear([wv.to(cuda_device)], [tok], bias_row=True)[0]
+    torch.cuda.synchronize()
+    assert err(vt, (F.linear(x.float(), wv.float(), bv)).t()) < TOL
