@@ -55,10 +55,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -66,10 +66,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
@@ -89,29 +89,56 @@ def _build_oracle_inputs(wl, seed=0):
     return cfg, sd
 
 
+def _usable_cpus() -> int:
+    """Cores this process may really use: affinity mask, capped by the cgroup CPU quota if there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
 def cpu_reference_throughput(wl, budget_s=20.0, max_pairs=64):
-    """The reference's CPU path (oracle port: same torch CPU ops, fp32, fused BN) on all host cores; bounded sample."""
+    """The reference's CPU path (oracle port: same torch CPU ops, fp32, fused BN) on the host cores; bounded sample.
+    PyTorch's intra-op pool does not scale to 100+ threads on these small convolutions (47 s/pair at 128 threads on the
+    GPU box vs 0.3 s at 8), so the thread count is picked by a short sweep and reported as `cores`."""
     import torch
     from oracle import icaf_oracle as O
     from oracle import synth
-    torch.set_num_threads(os.cpu_count() or 1)
     cfg, sd = _build_oracle_inputs(wl)
     B = 1                                   # the CPU sample runs batch 1 (latency-optimal on CPU)
     rgb, ir = synth.synth_images(B, wl["H"], wl["W"], 0)
+    usable = _usable_cpus()
+    t_start = time.perf_counter()
+    best = None
     with torch.no_grad():
-        O.model_forward(sd, cfg, rgb, ir)   # warm-up
-        t0, n = time.perf_counter(), 0
-        times = []
-        while n < max_pairs and (time.perf_counter() - t0) < budget_s:
+        for nt in [t for t in (8, 16, 32, 64, 128, 256) if t <= usable] or [usable]:
+            torch.set_num_threads(nt)
+            O.model_forward(sd, cfg, rgb, ir)                     # warm-up at this thread count
+            t = time.perf_counter()
+            O.model_forward(sd, cfg, rgb, ir)
+            dt = time.perf_counter() - t
+            if best is None or dt < best[1]:
+                best = (nt, dt)
+            if dt > 1.15 * best[1] or time.perf_counter() - t_start > 0.4 * budget_s:
+                break            # past the scaling knee: more threads only add contention
+        torch.set_num_threads(best[0])
+        t0, n, times = time.perf_counter(), 0, []
+        while n < max_pairs and (time.perf_counter() - t0) < 0.6 * budget_s:
             t = time.perf_counter()
             O.model_forward(sd, cfg, rgb, ir)
             times.append(time.perf_counter() - t)
             n += B
     per = sorted(times)[len(times) // 2]
-    return {"value": round(B / per, 3), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": round(B / per, 3), "unit": "pairs/s", "cores": best[0], "kind": "port",
             "sample": f"{n} pairs of {wl['desc'].split(',')[0]} at batch 1, fp32, median of {len(times)} forwards "
-                      f"({sum(times):.1f} s of CPU work); oracle/icaf_oracle.py (PyTorch-CPU restatement of the reference forward)",
-            "cpu_model": _cpu_model()}
+                      f"({sum(times):.1f} s of CPU work) at the fastest intra-op thread count of a sweep up to {usable} usable cores; "
+                      "oracle/icaf_oracle.py (PyTorch-CPU restatement of the reference forward)",
+            "cpu_model": _cpu_model(), "host_cpus": os.cpu_count()}
 
 
 def _cpu_model():

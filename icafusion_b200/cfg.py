@@ -35,7 +35,7 @@ def transfusion_kaist_cfg(size: str = "s", nc: int = 1) -> Dict:
     taps = ((4, 14, 256), (6, 16, 512), (9, 19, 1024))   # P3, P4, P5 outputs of each stream
     fusion = [[[a, b], 1, "TransformerFusionBlock", [c, va, ha]]
               for (a, b, c), (va, ha) in zip(taps, DMFF_GRIDS)]          # layers 20-22
-    up = [None, 2, "nearest"]
+    up = ["None", 2, "nearest"]          # the YAML literal `None` is a string (eval-ed by parse_model)
     head = [
         [-1, 1, "Conv", [512, 1, 1]],              # 23
         [-1, 1, "nn.Upsample", list(up)],          # 24

@@ -15,7 +15,6 @@ namespace icaf {
 
 constexpr int BM = 128;
 constexpr int BK = 64;              // 64 halfs = one 128-byte swizzle atom row
-constexpr int kStages = 4;
 constexpr int kLag = 2;             // cp.async groups kept in flight per producer thread
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 160;
@@ -42,20 +41,77 @@ __device__ __forceinline__ ConvProblem pick_problem(const ConvParams& P, unsigne
   return r;
 }
 
+// One 32-column chunk of one output row: + bias, activation, residual, fp16 store.
+// ACT: 0 none, 1 SiLU, 2 GELU(erf).  RES: 0 none, 1 y = act(v) + res, 2 y = alpha*res + beta*v.
+template <int ACT, int RES>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float* __restrict__ sb, float rbias,
+                                          float alpha, float beta, const __half* __restrict__ rp,
+                                          __half* __restrict__ yp, bool vec, int ncols) {
+  auto f = [&](int j) {
+    float t = __uint_as_float(acc[j]) + sb[j] + rbias;
+    if (ACT == ICAF_ACT_SILU) t = silu_f(t);
+    if (ACT == ICAF_ACT_GELU) t = gelu_erf_f(t);
+    return t;
+  };
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = f(q * 8 + e);
+      if (RES != 0) {
+        uint4 rr = *reinterpret_cast<const uint4*>(rp + q * 8);
+        const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 rf = __half22float2(rh[e]);
+          if (RES == 2) {
+            v[2 * e] = alpha * rf.x + beta * v[2 * e];
+            v[2 * e + 1] = alpha * rf.y + beta * v[2 * e + 1];
+          } else {
+            v[2 * e] += rf.x;
+            v[2 * e + 1] += rf.y;
+          }
+        }
+      }
+      uint4 o;
+      o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
+      o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(yp + q * 8) = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) {
+        float t = f(j);
+        if (RES != 0) {
+          float rf = __half2float(rp[j]);
+          t = RES == 2 ? alpha * rf + beta * t : t + rf;
+        }
+        yp[j] = __float2half_rn(t);
+      }
+    }
+  }
+}
+
 template <int BN>
 struct SmemLayout {
+  // ring depth chosen so that two CTAs fit one SM (<= ~100 KB each): one CTA's epilogue overlaps the other's mainloop
+  static constexpr int kStages = BN >= 128 ? 3 : 4;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOff + 128 + 1024;   // barriers + tmem slot, + 1024 alignment slack
+  static constexpr int kBiasOff = kBarOff + 128;        // fp32 bias tile [BN]
+  static constexpr int kTotal = kBiasOff + BN * 4 + 1024;   // + 1024 alignment slack
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(const ConvParams P) {
+__global__ void __launch_bounds__(kThreads, 2) conv_gemm_tc_kernel(const ConvParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   using L = SmemLayout<BN>;
+  constexpr int kStages = L::kStages;
   const uint32_t bar_base = smem_base + L::kBarOff;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -79,6 +135,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(const ConvPar
     fence_mbar_init();
   }
   if (warp == 4) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  float* sbias = reinterpret_cast<float*>(smem_gen + L::kBiasOff);
+  if (tid < BN) sbias[tid] = (pr.bias && !(P.epi & ICAF_EPI_BIAS_ROW) && n0 + tid < P.N) ? pr.bias[n0 + tid] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -156,6 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(const ConvPar
     const float rbias = ((P.epi & ICAF_EPI_BIAS_ROW) && pr.bias && mvalid) ? pr.bias[m] : 0.f;
     __half* yrow = pr.y + size_t(mvalid ? m : 0) * pr.y_ld;
     const __half* rrow = pr.res ? pr.res + size_t(mvalid ? m : 0) * pr.res_ld : nullptr;
+    const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : (rrow ? 1 : 0);
 #pragma unroll 1
     for (int cb = 0; cb < BN; cb += 32) {
       uint32_t acc[32];
@@ -164,55 +223,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(const ConvPar
       tmem_ld_wait();
       const int nb = n0 + cb;
       if (mvalid && nb < P.N) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(acc[j]);
-          if (P.epi & ICAF_EPI_BIAS_ROW) t += rbias;
-          else if (pr.bias && nb + j < P.N) t += __ldg(pr.bias + nb + j);
-          if (P.act == ICAF_ACT_SILU) t = silu_f(t);
-          else if (P.act == ICAF_ACT_GELU) t = gelu_erf_f(t);
-          v[j] = t;
-        }
-        const bool full = (nb + 32 <= P.N);
-        const bool vec = full && ((reinterpret_cast<uintptr_t>(yrow + nb) & 15) == 0) &&
+        const int ncols = min(32, P.N - nb);
+        const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(yrow + nb) & 15) == 0) &&
                          (!rrow || (reinterpret_cast<uintptr_t>(rrow + nb) & 15) == 0);
-        if (vec) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (rrow) {
-              uint4 rr = *reinterpret_cast<const uint4*>(rrow + nb + q * 8);
-              const __half2* rh = reinterpret_cast<const __half2*>(&rr);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 rf = __half22float2(rh[e]);
-                if (P.epi & ICAF_EPI_SCALED_RES) {
-                  v[q * 8 + 2 * e] = alpha * rf.x + beta * v[q * 8 + 2 * e];
-                  v[q * 8 + 2 * e + 1] = alpha * rf.y + beta * v[q * 8 + 2 * e + 1];
-                } else {
-                  v[q * 8 + 2 * e] += rf.x;
-                  v[q * 8 + 2 * e + 1] += rf.y;
-                }
-              }
-            }
-            uint4 o;
-            o.x = pack_half2(v[q * 8 + 0], v[q * 8 + 1]);
-            o.y = pack_half2(v[q * 8 + 2], v[q * 8 + 3]);
-            o.z = pack_half2(v[q * 8 + 4], v[q * 8 + 5]);
-            o.w = pack_half2(v[q * 8 + 6], v[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(yrow + nb + q * 8) = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (nb + j >= P.N) continue;
-            float t = v[j];
-            if (rrow) {
-              float rf = __half2float(rrow[nb + j]);
-              t = (P.epi & ICAF_EPI_SCALED_RES) ? alpha * rf + beta * t : t + rf;
-            }
-            yrow[nb + j] = __float2half_rn(t);
-          }
+        const float* sb = sbias + cb;
+        const __half* rp = rrow ? rrow + nb : nullptr;
+        __half* yp = yrow + nb;
+        // act / residual mode are warp-uniform: dispatch once per chunk to straight-line specialisations
+        switch (P.act * 3 + mode) {
+          case 0: epi_chunk<0, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          case 1: epi_chunk<0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          case 2: epi_chunk<0, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          case 3: epi_chunk<1, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          case 4: epi_chunk<1, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          case 5: epi_chunk<1, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          case 6: epi_chunk<2, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          case 7: epi_chunk<2, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          default: epi_chunk<2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
         }
       }
     }

@@ -14,12 +14,13 @@ from oracle import synth
 
 pytestmark = pytest.mark.gpu
 
-# north_star: "within 1e-3 fp16 relative tolerance" (norm-wise).  The reference's OWN fp16 path
-# deviates 0.8e-3 .. 1.5e-3 from its fp32 path on these cases (meta['ref_fp16_self_dev']); we hold the CUDA path
-# to the tighter of 2e-3 and 1.5x that self-deviation, and print the achieved number.
-def _tol(meta):
-    dev = meta.get("ref_fp16_self_dev") or 1.2e-3
-    return min(2e-3, max(1e-3, 1.5 * dev))
+# north_star: the DMFF forward matches the reference "within 1e-3 fp16 relative tolerance" (norm-wise max|a-b|/max|b|,
+# SURVEY.md 7.2) -- that is TOL_OUT, applied to the block output against the reference's fp32 result.  (The reference's
+# OWN fp16 path deviates 0.8e-3 .. 1.5e-3 from its fp32 path on these cases, meta['ref_fp16_self_dev'].)
+# The token streams after the cross transformer are an internal intermediate (fp16 residual stream, rounded twice per
+# loop); they are checked against a looser bound so that a semantic bug is still caught early.
+TOL_OUT = 1e-3
+TOL_TOKENS = 2e-3
 
 
 NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "dmff_*.npz")))
@@ -53,7 +54,7 @@ def test_dmff_matches_reference_golden(cuda_device, name):
     e_out = err(out, d["out"])
     print(f"\n[{name}] tokens {e_tok:.2e}  out {e_out:.2e}  (reference's own fp16 path: {m.get('ref_fp16_self_dev')})")
     assert tuple(out.shape) == d["out"].shape
-    assert e_tok < _tol(m) and e_out < _tol(m)
+    assert e_out < TOL_OUT and e_tok < TOL_TOKENS
 
 
 @pytest.mark.parametrize("B,C,H,W,va,ha,loops", [
@@ -76,7 +77,7 @@ def test_dmff_matches_oracle(cuda_device, B, C, H, W, va, ha, loops):
         ref = O.dmff_block(rgb.half().float(), ir.half().float(), sd, "blk", va, ha, loops, bn_eps=1e-5)
     e = err(out, ref)
     print(f"\n[C={C} {H}x{W}->{va}x{ha} L={loops}] {e:.2e}")
-    assert e < 2e-3
+    assert e < TOL_OUT
 
 
 def test_cross_transformer_block_token_api(cuda_device):
