@@ -153,19 +153,36 @@ class C3(nn.Module):
         self.cv3 = Conv(2 * c_, c2, 1)
         self.m = nn.Sequential(*[Bottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)])
 
+    def packed_cv12(self) -> PackedConv:
+        """cv1 and cv2 read the same input: one GEMM with the two filter banks stacked ([cv1 | cv2] output channels)."""
+        p1, p2 = self.cv1.packed(), self.cv2.packed()
+        cache = self.__dict__.get("_icaf_pack12")
+        if cache is not None and cache[0] is p1 and cache[1] is p2:
+            return cache[2]
+        c_ = p1.cout
+        w = torch.cat([p1.w[:c_], p2.w[:c_]], 0)
+        rows = ops.round_up(2 * c_, 32)
+        if rows != 2 * c_:
+            w = torch.cat([w, w.new_zeros(rows - 2 * c_, w.shape[1])], 0)
+        pk = PackedConv(w.contiguous(), torch.cat([p1.bias, p2.bias]).contiguous(), p1.cin, 2 * c_, 1, 1, 1, 0, p1.act)
+        self.__dict__["_icaf_pack12"] = (p1, p2, pk)
+        return pk
+
     @staticmethod
-    def run(mods, xs):
+    def run(mods, xs, outs=None):
         c_ = mods[0].cv1.conv.out_channels
         B, H, W, _ = xs[0].shape
+        for m in mods:
+            _require_eval(m)
         cats = [torch.empty(B, H, W, 2 * c_, dtype=torch.float16, device=xs[0].device) for _ in mods]
         left = [c[..., :c_] for c in cats]
-        right = [c[..., c_:] for c in cats]
+        ops.conv2d(list(xs), [m.packed_cv12() for m in mods], cats)          # [cv1(x) | cv2(x)] in one launch
+        a = left
         n = len(mods[0].m)
-        a = Conv.run([m.cv1 for m in mods], xs, left if n == 0 else None)
         for j in range(n):
+            # the last bottleneck writes back into the left half (its own residual read is element-wise, same thread)
             a = Bottleneck.run([m.m[j] for m in mods], a, left if j == n - 1 else None)
-        Conv.run([m.cv2 for m in mods], xs, right)
-        return Conv.run([m.cv3 for m in mods], cats)
+        return Conv.run([m.cv3 for m in mods], cats, outs)
 
     def forward(self, x):
         return to_nchw(C3.run([self], [to_nhwc(x)])[0])
@@ -182,7 +199,7 @@ class SPPF(nn.Module):
         self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
 
     @staticmethod
-    def run(mods, xs):
+    def run(mods, xs, outs=None):
         c_ = mods[0].cv1.conv.out_channels
         if mods[0].m.kernel_size != 5:
             raise NotImplementedError("SPPF: only k=5 is supported")
@@ -191,7 +208,7 @@ class SPPF(nn.Module):
         Conv.run([m.cv1 for m in mods], xs, [c[..., :c_] for c in cats])
         for c in cats:
             ops.sppf_pool(c[..., :c_], c[..., c_:2 * c_], c[..., 2 * c_:3 * c_], c[..., 3 * c_:])
-        return Conv.run([m.cv2 for m in mods], cats)
+        return Conv.run([m.cv2 for m in mods], cats, outs)
 
     def forward(self, x):
         return to_nchw(SPPF.run([self], [to_nhwc(x)])[0])
@@ -448,8 +465,8 @@ class TransformerFusionBlock(nn.Module):
         self.__dict__["_icaf_pack"] = (key, pk)
         return pk
 
-    def run(self, rgb: torch.Tensor, ir: torch.Tensor) -> torch.Tensor:
-        """rgb, ir: fp16 NHWC feature maps -> fused NHWC map."""
+    def run(self, rgb: torch.Tensor, ir: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """rgb, ir: fp16 NHWC feature maps -> fused NHWC map (optionally written into the view `out`)."""
         _require_eval(self)
         B, H, W, C = rgb.shape
         nh, nw = self.avgpool.out_size(H, W)
@@ -461,7 +478,7 @@ class TransformerFusionBlock(nn.Module):
         for blk in self.crosstransformer:
             r, i = blk.run(r, i, N)                                                # common.py:825
         cat = ops.dmff_upsample_cat(r, i, rgb, ir, nh, nw, mode=0)                 # common.py:827-840 (eval: bilinear)
-        return Conv.run([self.conv1x1_out], [cat])[0]                              # common.py:841
+        return Conv.run([self.conv1x1_out], [cat], None if out is None else [out])[0]   # common.py:841
 
     def forward(self, x):
         rgb, ir = x

@@ -2,42 +2,58 @@
 //
 //   C[M=B*Ho*Wo, N=Cout] = A[M, K=kh*kw*Cin] * W[N, K]^T           fp16 operands, fp32 accumulate in TMEM
 //
-// A is never materialised (no im2col): producer warps gather 16-byte channel runs of the NHWC input straight
-// into the 128B-swizzled K-major shared-memory layout the UMMA descriptors expect (zero-fill = padding).
-// CTA = one 128 x BN output tile.  Warp roles (160 threads):
-//   warps 0-3 : gather producers (cp.async, 4 rows x 128 B per warp instruction -> fully coalesced),
-//               then the epilogue (thread t owns TMEM lane t = output row t)
+// A is never materialised (no im2col).  Three ways to stage the A tile (128 rows x 64 K) into the 128B-swizzled
+// K-major shared-memory layout the UMMA descriptors expect, picked per layer on the host:
+//   A_TMA2D  : 1x1 conv / linear -- A is a plain [M][Cin] matrix: one 2-D TMA box per stage.
+//   A_TMA4D  : kxk conv whose 128-row tile is a TH x TW patch of one image and Cin % 64 == 0: one 4-D TMA box
+//              (64 ch, TW*s, TH*s, 1) of the NHWC input per stage at coordinates shifted by the filter tap;
+//              out-of-bounds (= padding) is zero-filled by the TMA unit, the stride is the box traversal stride.
+//   A_GATHER : anything else (image stem with Cin=4, Cin<64, 20-wide P5 maps): producer warps gather 16-byte channel
+//              runs with cp.async (zero-fill), 4 rows x 128 B per warp instruction.
+// The filter tile (BN rows x 64 K) always arrives by 2-D TMA.
+// CTA = one 128 x BN output tile, 192 threads:
+//   warps 0-3 : A_GATHER producers, then the epilogue (thread t owns TMEM lane t = output row t)
 //   warp  4   : TMEM allocator + single-thread tcgen05.mma issuer
-// Pipelines: smem ring full[]/empty[] (producers <-> MMA), accum_full (MMA -> epilogue).
+//   warp  5   : TMA producer (one elected thread)
+// Pipelines: smem ring full[]/empty[] (producers <-> MMA), accum_full (MMA -> epilogue).  Two CTAs share an SM
+// (BN <= 128) so one CTA's epilogue overlaps the other's main loop.
+#include <cstring>
+
 #include "icaf_internal.cuh"
 
 namespace icaf {
 
 constexpr int BM = 128;
 constexpr int BK = 64;              // 64 halfs = one 128-byte swizzle atom row
-constexpr int kLag = 2;             // cp.async groups kept in flight per producer thread
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;
+constexpr int kLag = 2;             // cp.async groups kept in flight per gather thread
+constexpr int kThreads = 192;
+
+enum AMode { A_GATHER = 0, A_TMA2D = 1, A_TMA4D = 2 };
 
 struct ConvProblem {
-  const __half* x; const __half* w; const float* bias; const __half* res; __half* y;
+  const __half* x; const float* bias; const __half* res; __half* y;
   const float* alpha; const float* beta;
   long long x_ld, res_ld, y_ld;
 };
 struct ConvParams {
   ConvProblem p[2];
-  int M, N, K, k_pad, w_rows;
+  int M, N, K, k_pad;
   int B, Hi, Wi, Cin, Ho, Wo, kh, kw, stride, pad;
   int act, epi;
+  int a_mode, tw, th, tiles_x, tiles_y;   // A_TMA4D: tile = th x tw output pixels, tiles_x*tiles_y tiles per image
+};
+struct ConvMaps {          // TMA descriptors, passed by value as a __grid_constant__ kernel parameter
+  CUtensorMap w[2];
+  CUtensorMap a[2];
 };
 
 __device__ __forceinline__ ConvProblem pick_problem(const ConvParams& P, unsigned z) {
   ConvProblem r;
-  r.x = z ? P.p[1].x : P.p[0].x;          r.w = z ? P.p[1].w : P.p[0].w;
-  r.bias = z ? P.p[1].bias : P.p[0].bias; r.res = z ? P.p[1].res : P.p[0].res;
-  r.y = z ? P.p[1].y : P.p[0].y;          r.alpha = z ? P.p[1].alpha : P.p[0].alpha;
-  r.beta = z ? P.p[1].beta : P.p[0].beta; r.x_ld = z ? P.p[1].x_ld : P.p[0].x_ld;
-  r.res_ld = z ? P.p[1].res_ld : P.p[0].res_ld; r.y_ld = z ? P.p[1].y_ld : P.p[0].y_ld;
+  r.x = z ? P.p[1].x : P.p[0].x;          r.bias = z ? P.p[1].bias : P.p[0].bias;
+  r.res = z ? P.p[1].res : P.p[0].res;    r.y = z ? P.p[1].y : P.p[0].y;
+  r.alpha = z ? P.p[1].alpha : P.p[0].alpha; r.beta = z ? P.p[1].beta : P.p[0].beta;
+  r.x_ld = z ? P.p[1].x_ld : P.p[0].x_ld; r.res_ld = z ? P.p[1].res_ld : P.p[0].res_ld;
+  r.y_ld = z ? P.p[1].y_ld : P.p[0].y_ld;
   return r;
 }
 
@@ -96,7 +112,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float
 
 template <int BN>
 struct SmemLayout {
-  // ring depth chosen so that two CTAs fit one SM (<= ~100 KB each): one CTA's epilogue overlaps the other's mainloop
+  // ring depth chosen so that two CTAs fit one SM for BN <= 128 (<= ~100 KB each)
   static constexpr int kStages = BN >= 128 ? 3 : 4;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
@@ -104,10 +120,12 @@ struct SmemLayout {
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kBiasOff = kBarOff + 128;        // fp32 bias tile [BN]
   static constexpr int kTotal = kBiasOff + BN * 4 + 1024;   // + 1024 alignment slack
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 2) conv_gemm_tc_kernel(const ConvParams P) {
+__global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
+conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   using L = SmemLayout<BN>;
@@ -122,92 +140,106 @@ __global__ void __launch_bounds__(kThreads, 2) conv_gemm_tc_kernel(const ConvPar
   const int warp = threadIdx.x >> 5;
   const int tid = threadIdx.x;
   const ConvProblem pr = pick_problem(P, blockIdx.z);   // by value: a dynamic param index would spill to local
-  const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int nkb = P.k_pad / BK;
+  const int a_mode = P.a_mode;
+  // tile origin: linear rows (gather / 2-D) or a th x tw patch of image tb (4-D)
+  int m0 = blockIdx.x * BM, tb = 0, oy0 = 0, ox0 = 0;
+  if (a_mode == A_TMA4D) {
+    const int per_img = P.tiles_x * P.tiles_y;
+    tb = blockIdx.x / per_img;
+    const int t = blockIdx.x - tb * per_img;
+    oy0 = (t / P.tiles_x) * P.th;
+    ox0 = (t % P.tiles_x) * P.tw;
+  }
 
   if (tid == 0) {
+    const uint32_t nfull = a_mode == A_GATHER ? 129u : 1u;    // 128 gather threads + the TMA thread
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), kProducerThreads);
+      mbar_init(full_bar(s), nfull);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  if (warp == 4) tmem_alloc<L::kTmemCols>(tmem_slot);
+  if (warp == 5 && lane_id() == 0) {
+    tma_prefetch_desc(blockIdx.z ? &maps.w[1] : &maps.w[0]);
+    if (a_mode != A_GATHER) tma_prefetch_desc(blockIdx.z ? &maps.a[1] : &maps.a[0]);
+  }
   float* sbias = reinterpret_cast<float*>(smem_gen + L::kBiasOff);
-  if (tid < BN) sbias[tid] = (pr.bias && !(P.epi & ICAF_EPI_BIAS_ROW) && n0 + tid < P.N) ? pr.bias[n0 + tid] : 0.f;
+  for (int i = tid; i < BN; i += kThreads)
+    sbias[i] = (pr.bias && !(P.epi & ICAF_EPI_BIAS_ROW) && n0 + i < P.N) ? pr.bias[n0 + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(smem_gen + L::kBarOff + 8 * (2 * kStages + 1));
 
   if (warp < 4) {
-    // ------------------------------------------------------------------ producers
-    const int c = tid & 7;          // 16-byte chunk within the 128-byte K row
-    const int r0 = tid >> 3;        // rows r0 + 16*i
-    const uint32_t sw = uint32_t(c ^ (r0 & 7)) << 4;
-    // per-row pixel decomposition (constant across the K loop)
-    uint32_t base[8];
-    int iy0[8], ix0[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int m = m0 + r0 + 16 * i;
-      bool mv = m < P.M;
-      int mm = mv ? m : 0;
-      int ox = mm % P.Wo;
-      int t = mm / P.Wo;
-      int oy = t % P.Ho;
-      int b = t / P.Ho;
-      base[i] = uint32_t(b) * uint32_t(P.Hi * P.Wi);
-      iy0[i] = mv ? oy * P.stride - P.pad : -100000;   // invalid rows fall out of bounds -> zero fill
-      ix0[i] = ox * P.stride - P.pad;
-    }
-    const __half* wrow = pr.w + size_t(n0 + r0) * P.k_pad + c * 8;
-
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kStages;
-      const uint32_t ph = (kb / kStages) & 1;
-      mbar_wait(empty_bar(s), ph ^ 1);
-      const uint32_t sa = smem_base + s * L::kStageBytes;
-      const uint32_t sb = sa + L::kABytes;
-      // A: which filter tap / channel run does this thread's chunk cover?
-      const int k0 = kb * BK + c * 8;
-      const bool kvalid = k0 < P.K;
-      const int tap = k0 / P.Cin;
-      const int ch = k0 - tap * P.Cin;
-      const int ky = tap / P.kw;
-      const int kx = tap - ky * P.kw;
+    if (a_mode == A_GATHER) {
+      // ---------------------------------------------------------------- cp.async gather producers
+      const int c = tid & 7;          // 16-byte chunk within the 128-byte K row
+      const int r0 = tid >> 3;        // rows r0 + 16*i
+      const uint32_t sw = uint32_t(c ^ (r0 & 7)) << 4;
+      uint32_t base[8];
+      int iy0[8], ix0[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        int iy = iy0[i] + ky, ix = ix0[i] + kx;
-        bool ok = kvalid && (unsigned)iy < (unsigned)P.Hi && (unsigned)ix < (unsigned)P.Wi;
-        size_t off = ok ? (size_t(base[i] + uint32_t(iy * P.Wi + ix)) * size_t(pr.x_ld) + ch) : 0;
-        cp_async16(sa + uint32_t(r0 + 16 * i) * 128u + sw, pr.x + off, ok);
+        int m = m0 + r0 + 16 * i;
+        bool mv = m < P.M;
+        int mm = mv ? m : 0;
+        int ox = mm % P.Wo;
+        int t = mm / P.Wo;
+        int oy = t % P.Ho;
+        int b = t / P.Ho;
+        base[i] = uint32_t(b) * uint32_t(P.Hi * P.Wi);
+        iy0[i] = mv ? oy * P.stride - P.pad : -100000;   // invalid rows fall out of bounds -> zero fill
+        ix0[i] = ox * P.stride - P.pad;
       }
-      // B: packed filter rows (always in-bounds in K; rows beyond w_rows zero-filled)
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t sa = smem_base + s * L::kStageBytes;
+        const int k0 = kb * BK + c * 8;
+        const bool kvalid = k0 < P.K;
+        const int tap = k0 / P.Cin;
+        const int ch = k0 - tap * P.Cin;
+        const int ky = tap / P.kw;
+        const int kx = tap - ky * P.kw;
 #pragma unroll
-      for (int i = 0; i < BN / 16; ++i) {
-        bool ok = (n0 + r0 + 16 * i) < P.w_rows;
-        cp_async16(sb + uint32_t(r0 + 16 * i) * 128u + sw, ok ? wrow + size_t(16 * i) * P.k_pad + kb * BK : pr.w, ok);
+        for (int i = 0; i < 8; ++i) {
+          int iy = iy0[i] + ky, ix = ix0[i] + kx;
+          bool ok = kvalid && (unsigned)iy < (unsigned)P.Hi && (unsigned)ix < (unsigned)P.Wi;
+          size_t off = ok ? (size_t(base[i] + uint32_t(iy * P.Wi + ix)) * size_t(pr.x_ld) + ch) : 0;
+          cp_async16(sa + uint32_t(r0 + 16 * i) * 128u + sw, pr.x + off, ok);
+        }
+        cp_async_commit();
+        if (kb >= kLag) {
+          cp_async_wait<kLag>();
+          fence_proxy_async_smem();
+          mbar_arrive(full_bar((kb - kLag) % kStages));
+        }
       }
-      cp_async_commit();
-      if (kb >= kLag) {
-        cp_async_wait<kLag>();
-        fence_proxy_async_smem();
-        mbar_arrive(full_bar((kb - kLag) % kStages));
-      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (int kb = (nkb > kLag ? nkb - kLag : 0); kb < nkb; ++kb) mbar_arrive(full_bar(kb % kStages));
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int kb = (nkb > kLag ? nkb - kLag : 0); kb < nkb; ++kb) mbar_arrive(full_bar(kb % kStages));
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int row = tid;                   // TMEM lane == tile row
-    const int m = m0 + row;
-    const bool mvalid = m < P.M;
+    int m;
+    bool mvalid;
+    if (a_mode == A_TMA4D) {
+      const int ry = row / P.tw, rx = row - ry * P.tw;
+      m = (tb * P.Ho + oy0 + ry) * P.Wo + ox0 + rx;
+      mvalid = true;                       // tiles divide the map exactly (host-checked)
+    } else {
+      m = m0 + row;
+      mvalid = m < P.M;
+    }
     const uint32_t trow = tmem_d + (uint32_t(warp * 32) << 16);
     float alpha = 0.f, beta = 1.f;
     if (P.epi & ICAF_EPI_SCALED_RES) { alpha = *pr.alpha; beta = *pr.beta; }
@@ -243,8 +275,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_gemm_tc_kernel(const ConvPar
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ MMA issuer (warp 4)
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
@@ -263,19 +295,47 @@ __global__ void __launch_bounds__(kThreads, 2) conv_gemm_tc_kernel(const ConvPar
       }
       __syncwarp();
     }
+  } else {
+    // ------------------------------------------------------------------ TMA producer (warp 5, one thread)
+    if (elect_one()) {
+      const CUtensorMap* mw = blockIdx.z ? &maps.w[1] : &maps.w[0];
+      const CUtensorMap* ma = blockIdx.z ? &maps.a[1] : &maps.a[0];
+      const uint32_t bytes = L::kBBytes + (a_mode != A_GATHER ? L::kABytes : 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t sa = smem_base + s * L::kStageBytes;
+        mbar_arrive_expect_tx(full_bar(s), bytes);
+        tma_load_2d(sa + L::kABytes, mw, full_bar(s), kb * BK, n0);
+        if (a_mode == A_TMA2D) {
+          tma_load_2d(sa, ma, full_bar(s), kb * BK, m0);
+        } else if (a_mode == A_TMA4D) {
+          const int k0 = kb * BK;
+          const int tap = k0 / P.Cin;
+          const int ch = k0 - tap * P.Cin;
+          const int ky = tap / P.kw, kx = tap - ky * P.kw;
+          tma_load_4d(sa, ma, full_bar(s), ch, ox0 * P.stride - P.pad + kx, oy0 * P.stride - P.pad + ky, tb);
+        }
+      }
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_d);
+    tmem_dealloc<L::kTmemCols>(tmem_d);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // CUDA-core reference with the identical contract (tests only).
-__global__ void conv_gemm_simt_kernel(const ConvParams P) {
+struct SimtParams { ConvParams P; const __half* w[2]; };
+__global__ void conv_gemm_simt_kernel(const SimtParams S) {
+  const ConvParams& P = S.P;
   const ConvProblem pr = pick_problem(P, blockIdx.z);
+  const __half* w = blockIdx.z ? S.w[1] : S.w[0];
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)P.M * P.N) return;
   int n = int(idx % P.N);
@@ -287,11 +347,11 @@ __global__ void conv_gemm_simt_kernel(const ConvParams P) {
       int iy = oy * P.stride - P.pad + ky, ix = ox * P.stride - P.pad + kx;
       if ((unsigned)iy >= (unsigned)P.Hi || (unsigned)ix >= (unsigned)P.Wi) continue;
       const __half* xp = pr.x + (size_t(b) * P.Hi * P.Wi + size_t(iy) * P.Wi + ix) * pr.x_ld;
-      const __half* wp = pr.w + size_t(n) * P.k_pad + (ky * P.kw + kx) * P.Cin;
+      const __half* wp = w + size_t(n) * P.k_pad + (ky * P.kw + kx) * P.Cin;
       for (int c = 0; c < P.Cin; ++c) acc += __half2float(xp[c]) * __half2float(wp[c]);
     }
   if (pr.bias) acc += (P.epi & ICAF_EPI_BIAS_ROW) ? pr.bias[m] : pr.bias[n];
-  if (P.act == ICAF_ACT_SILU) acc = silu_f(acc);
+  if (P.act == ICAF_ACT_SILU) acc = acc / (1.0f + expf(-acc));
   else if (P.act == ICAF_ACT_GELU) acc = gelu_erf_f(acc);
   if (pr.res) {
     float rf = __half2float(pr.res[size_t(m) * pr.res_ld + n]);
@@ -300,7 +360,7 @@ __global__ void conv_gemm_simt_kernel(const ConvParams P) {
   pr.y[size_t(m) * pr.y_ld + n] = __float2half_rn(acc);
 }
 
-static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, ConvParams& P) {
+static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, ConvParams& P, const __half* (&w)[2]) {
   if (!g || !io || n_io < 1 || n_io > 2) return set_error(ICAF_ERR_BAD_ARG, "conv2d: need 1 or 2 problems");
   if (!(g->Cin == 4 || g->Cin % 8 == 0)) return set_error(ICAF_ERR_UNSUPPORTED, "conv2d: Cin must be 4 or a multiple of 8");
   if (g->Cin == 4 && (g->Wi % 2 || g->stride % 2 || g->pad % 2 || g->kw % 2))
@@ -312,9 +372,10 @@ static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io
     return set_error(ICAF_ERR_BAD_ARG, "conv2d: size out of range");
   if ((g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES)) == (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES))
     return set_error(ICAF_ERR_BAD_ARG, "conv2d: ADD_RES and SCALED_RES are exclusive");
-  P.M = int(M); P.N = g->Cout; P.K = g->kh * g->kw * g->Cin; P.k_pad = g->k_pad; P.w_rows = g->w_rows;
+  P.M = int(M); P.N = g->Cout; P.K = g->kh * g->kw * g->Cin; P.k_pad = g->k_pad;
   P.B = g->B; P.Hi = g->Hi; P.Wi = g->Wi; P.Cin = g->Cin; P.Ho = g->Ho; P.Wo = g->Wo;
   P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad = g->pad; P.act = g->act; P.epi = g->epi;
+  P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0;
   for (int i = 0; i < 2; ++i) {
     const icaf_conv_io& s = io[i < n_io ? i : 0];
     bool need_res = g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES);
@@ -323,14 +384,32 @@ static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io
     if ((reinterpret_cast<uintptr_t>(s.x) & 15) || (reinterpret_cast<uintptr_t>(s.w) & 15) || (s.x_ld % 8 && g->Cin != 4) ||
         (g->Cin == 4 && s.x_ld != 4))
       return set_error(ICAF_ERR_BAD_ARG, "conv2d: x / w must be 16-byte aligned with x_ld a multiple of 8");
-    P.p[i] = ConvProblem{(const __half*)s.x, (const __half*)s.w, s.bias, need_res ? (const __half*)s.res : nullptr,
-                         (__half*)s.y, s.alpha, s.beta, s.x_ld, s.res_ld, s.y_ld};
+    P.p[i] = ConvProblem{(const __half*)s.x, s.bias, need_res ? (const __half*)s.res : nullptr, (__half*)s.y, s.alpha, s.beta,
+                         s.x_ld, s.res_ld, s.y_ld};
+    w[i] = (const __half*)s.w;
   }
   return ICAF_OK;
 }
 
+// Pick how the A tile is staged (see the header comment) and, for A_TMA4D, the tile shape.
+static void plan_a_mode(const icaf_conv_geom* g, ConvParams& P) {
+  if (g->kh == 1 && g->kw == 1 && g->stride == 1 && g->pad == 0 && g->Cin % 8 == 0) {
+    P.a_mode = A_TMA2D;
+    return;
+  }
+  if (g->Cin % 64 == 0 && g->stride <= 2) {
+    for (int tw = 128; tw >= 4; tw >>= 1) {          // widest power-of-two tile row that divides the map
+      int th = 128 / tw;
+      if (g->Wo % tw == 0 && g->Ho % th == 0 && tw * g->stride <= 256 && th * g->stride <= 256) {
+        P.a_mode = A_TMA4D; P.tw = tw; P.th = th; P.tiles_x = g->Wo / tw; P.tiles_y = g->Ho / th;
+        return;
+      }
+    }
+  }
+}
+
 template <int BN>
-static int launch_tc(const ConvParams& P, int n_io, cudaStream_t st) {
+static int launch_tc(const ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
   using L = SmemLayout<BN>;
   static bool configured = false;   // idempotent attribute; benign race
   if (!configured) {
@@ -338,8 +417,22 @@ static int launch_tc(const ConvParams& P, int n_io, cudaStream_t st) {
     if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute");
     configured = true;
   }
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < n_io; ++i) {
+    int rc = encode_tmap_2d(&maps.w[i], w[i], (uint64_t)P.k_pad, (uint64_t)g->w_rows, (uint64_t)P.k_pad * 2, BK, BN);
+    if (rc) return rc;
+    const ConvProblem& pr = P.p[i];
+    if (P.a_mode == A_TMA2D)
+      rc = encode_tmap_2d(&maps.a[i], pr.x, (uint64_t)P.Cin, (uint64_t)P.M, (uint64_t)pr.x_ld * 2, BK, BM);
+    else if (P.a_mode == A_TMA4D)
+      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, P.tw * P.stride, P.th * P.stride, P.stride,
+                            P.stride);
+    if (rc) return rc;
+  }
+  if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
   dim3 grid((P.M + BM - 1) / BM, (P.N + BN - 1) / BN, n_io);
-  conv_gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(P);
+  conv_gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(P, maps);
   return check_launch("conv2d_fwd");
 }
 
@@ -349,30 +442,34 @@ using namespace icaf;
 
 extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream) {
   ConvParams P;
-  int rc = fill_params(g, io, n_io, P);
+  const __half* w[2];
+  int rc = fill_params(g, io, n_io, P, w);
   if (rc) return rc;
+  plan_a_mode(g, P);
   cudaStream_t st = (cudaStream_t)stream;
-  // Tile width: the widest BN that still yields at least ~one CTA per SM; small problems take BN=32
-  // so that more SMs share the K loop.
+  // Tile width: the widest BN that still yields at least ~one CTA per SM (two waves for the 1-CTA/SM BN=256); small
+  // problems take BN=32 so that more SMs share the K loop.
   const long long mt = (P.M + BM - 1) / BM;
   const int sms = sm_count_cached();
   auto ctas = [&](int bn) { return mt * ((P.N + bn - 1) / bn) * n_io; };
   int bn = 32;
-  if (P.N > 64 && ctas(128) >= sms) bn = 128;
+  if (P.N >= 256 && ctas(256) >= 2 * sms) bn = 256;
+  else if (P.N > 64 && ctas(128) >= sms) bn = 128;
   else if (P.N > 32 && ctas(64) >= sms) bn = 64;
   switch (bn) {
-    case 128: return launch_tc<128>(P, n_io, st);
-    case 64: return launch_tc<64>(P, n_io, st);
-    default: return launch_tc<32>(P, n_io, st);
+    case 256: return launch_tc<256>(P, w, g, n_io, st);
+    case 128: return launch_tc<128>(P, w, g, n_io, st);
+    case 64: return launch_tc<64>(P, w, g, n_io, st);
+    default: return launch_tc<32>(P, w, g, n_io, st);
   }
 }
 
 extern "C" int icaf_conv2d_fwd_simt(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream) {
-  ConvParams P;
-  int rc = fill_params(g, io, n_io, P);
+  SimtParams S;
+  int rc = fill_params(g, io, n_io, S.P, S.w);
   if (rc) return rc;
-  long long total = (long long)P.M * P.N;
+  long long total = (long long)S.P.M * S.P.N;
   dim3 grid((unsigned)((total + 255) / 256), 1, n_io);
-  conv_gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  conv_gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(S);
   return check_launch("conv2d_fwd_simt");
 }

@@ -1,6 +1,7 @@
 // Shared internals of libicaf_b200: error reporting, launch checks, device info.
 #pragma once
 #include <cstdio>
+#include <cuda.h>          // CUtensorMap + enums only; the driver entry point is resolved at run time (no -lcuda)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -13,5 +14,14 @@ int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
 int check_launch(const char* where);   // cudaGetLastError after a launch; never synchronises
 int sm_count_cached();
+
+// TMA descriptors (host side). fp16 tensors, 128-byte swizzle, zero fill out of bounds.
+// 2D: [rows][inner] with a row pitch in bytes; box = box_rows x box_inner (box_inner*2 <= 128 B).
+int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
+                   uint32_t box_inner, uint32_t box_rows);
+// 4D NHWC activation view (C, W, H, B) with pixel pitch `ld` elements; box = (box_c, box_w, box_h, 1) *input* elements,
+// traversal strides (1, sw, sh, 1): loads ceil(box_w/sw) x ceil(box_h/sh) pixels per box.
+int encode_tmap_nhwc(CUtensorMap* out, const void* base, int C, int W, int H, int B, int64_t ld, uint32_t box_c,
+                     uint32_t box_w, uint32_t box_h, uint32_t sw, uint32_t sh);
 
 }  // namespace icaf

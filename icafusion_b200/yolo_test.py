@@ -173,6 +173,7 @@ class Model(nn.Module):
                 mod.eps = 1e-3
                 mod.momentum = 0.03
         self._plan_streams()
+        self._plan_concats()
 
     # -- two-stream pairing ----------------------------------------------------------------------
     def _plan_streams(self):
@@ -193,6 +194,42 @@ class Model(nn.Module):
                 return
         self._ir_start = s
 
+    def _plan_concats(self):
+        """Concat elimination: every tensor that feeds a Concat layer is produced directly inside that layer's output
+        buffer (all kernels take channel-slice views), so Concat itself launches nothing.  Maps producer layer index ->
+        (concat layer index, channel offset); a producer feeding two concats keeps the first and is copied for the rest."""
+        self._concat_dst, self._concat_width = {}, {}
+        ch = self._layer_ch = {}
+        paired = 2 * self._ir_start if self._ir_start is not None else 0     # stream layers run in the grouped loop
+        for m in self.model:
+            if isinstance(m, Concat) and m.d == 1 and isinstance(m.f, (list, tuple)):
+                srcs = [m.i - 1 if j == -1 else j for j in m.f]
+                ok = all(j in ch and ch[j] and j >= paired and j not in self._concat_dst and
+                         not isinstance(self.model[j], (Concat, Detect)) for j in srcs)
+                if ok:
+                    off = 0
+                    for j in srcs:
+                        self._concat_dst[j] = (m.i, off)
+                        off += ch[j]
+                    self._concat_width[m.i] = off
+            ch[m.i] = self._out_channels(m, ch)
+
+    @staticmethod
+    def _out_channels(m, ch):
+        if isinstance(m, Conv):
+            return m.conv.out_channels
+        if isinstance(m, (C3,)):
+            return m.cv3.conv.out_channels
+        if isinstance(m, SPPF):
+            return m.cv2.conv.out_channels
+        if isinstance(m, TransformerFusionBlock):
+            return m.n_embd
+        if isinstance(m, Upsample):
+            return ch[m.i - 1] if m.f == -1 else ch[m.f]
+        if isinstance(m, Concat):
+            return sum(ch[m.i - 1 if j == -1 else j] for j in m.f)
+        return None
+
     def forward(self, x, x2, augment=False, profile=False):
         if augment:
             raise NotImplementedError("augmented (multi-scale / flip) inference is outside the hot path built here")
@@ -202,19 +239,20 @@ class Model(nn.Module):
         z, logits, xs = self._forward_nhwc(x, x2)
         return z, logits, xs
 
-    def _run_layer(self, m, v):
+    def _run_layer(self, m, v, out=None):
+        o = None if out is None else [out]
         if isinstance(m, Conv):
-            return Conv.run([m], [v])[0]
+            return Conv.run([m], [v], o)[0]
         if isinstance(m, C3):
-            return C3.run([m], [v])[0]
+            return C3.run([m], [v], o)[0]
         if isinstance(m, SPPF):
-            return SPPF.run([m], [v])[0]
+            return SPPF.run([m], [v], o)[0]
         if isinstance(m, Upsample):
-            return ops.upsample2x(v)
+            return ops.upsample2x(v, out)
         if isinstance(m, Concat):
             return Concat.run(v)
         if isinstance(m, TransformerFusionBlock):
-            return m.run(v[0], v[1])
+            return m.run(v[0], v[1], out)
         if isinstance(m, Detect):
             return m.run(list(v))
         raise NotImplementedError(type(m).__name__)
@@ -246,16 +284,39 @@ class Model(nn.Module):
             x = b
         else:
             x = v_rgb
+        cats = {}                                 # concat layer index -> its (lazily allocated) output buffer
+
+        def dest(m, shape_hw):
+            """Slice of the consumer Concat's buffer this layer should write into (or None)."""
+            d = self._concat_dst.get(m.i)
+            if d is None:
+                return None
+            ci, off = d
+            if ci not in cats:
+                B, H, W = shape_hw
+                cats[ci] = torch.empty(B, H, W, self._concat_width[ci], dtype=torch.float16, device=v_rgb.device)
+            return cats[ci][..., off:off + self._layer_ch[m.i]]
+
         for m in layers[start:]:
             if m.f == -4:
                 x = v_ir
             elif m.f != -1:
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
-            x = self._run_layer(m, x)
+            if isinstance(m, Concat) and m.i in cats:
+                x = cats[m.i]                      # every source already wrote its slice
+            else:
+                out = None
+                if m.i in self._concat_dst and not isinstance(m, (Concat, Detect)):
+                    ref = x[0] if isinstance(x, (list, tuple)) else x
+                    B, H, W = ref.shape[0], ref.shape[1], ref.shape[2]
+                    if isinstance(m, Upsample):
+                        H, W = 2 * H, 2 * W
+                    elif isinstance(m, Conv):
+                        k, s_, p = m.conv.kernel_size[0], m.conv.stride[0], m.conv.padding[0]
+                        H, W = (H + 2 * p - k) // s_ + 1, (W + 2 * p - k) // s_ + 1
+                    out = dest(m, (B, H, W))
+                x = self._run_layer(m, x, out)
             y[m.i] = x
-        for k in range(len(y)):
-            if k not in self.save:
-                y[k] = None
         return x
 
     def fuse(self):

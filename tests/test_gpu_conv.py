@@ -38,7 +38,12 @@ CASES = [
     (1, 128, 64, 80, 128, 3, 1, 1, 1),    # M=5120
     (2, 64, 128, 160, 256, 1, 1, 0, 1),   # many tiles -> BN=128 path
     (1, 256, 16, 20, 256, 3, 1, 1, 1),    # deep K (36 K blocks), few tiles -> BN=32 path
-    (1, 8, 9, 11, 40, 3, 1, 1, 2),        # odd sizes, Cin=8, GELU
+    (1, 8, 9, 11, 40, 3, 1, 1, 2),        # odd sizes, Cin=8, GELU (gather path)
+    (1, 32, 16, 20, 96, 1, 1, 0, 1),      # 1x1 via 2-D TMA with Cin < 64 and N not a multiple of the tile (TMA zero fill)
+    (2, 64, 32, 40, 128, 3, 2, 1, 1),     # 3x3 stride 2 via 4-D TMA (traversal stride 2, negative start coordinate)
+    (2, 128, 32, 40, 64, 3, 1, 1, 1),     # 3x3 stride 1 via 4-D TMA, tile 16 rows x 8 cols, two K blocks per tap
+    (16, 64, 32, 40, 512, 1, 1, 0, 1),    # BN=256 tiles (1 CTA/SM, 256 TMEM columns)
+    (1, 64, 16, 20, 64, 3, 1, 1, 1),      # 20-wide map: no 128-pixel rectangle -> gather path with TMA filters
 ]
 
 

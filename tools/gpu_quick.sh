@@ -1,0 +1,6 @@
+#!/bin/bash
+# Quick GPU session: parity tests + both workloads of the bench (no profiler).
+mkdir -p gpurun_out
+python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 15 gpurun_out/pytest_gpu.log
+python bench.py --steps 200 --warmup 20 > gpurun_out/bench_s_b1.json 2> gpurun_out/bench_s_b1.err; cat gpurun_out/bench_s_b1.json; tail -n 3 gpurun_out/bench_s_b1.err
+python bench.py --workload yolov5l_b16 --steps 20 --warmup 5 > gpurun_out/bench_l_b16.json 2> gpurun_out/bench_l_b16.err; cat gpurun_out/bench_l_b16.json; tail -n 3 gpurun_out/bench_l_b16.err
