@@ -247,6 +247,13 @@ def run_ours(args, wl):
                     model(eng.rgb, eng.ir)
             torch.cuda.synchronize()
         summ = prof.summary()
+        if args.layer_profile:           # per-launch table of the last profiled step (geometry, us, TFLOP/s, GB/s)
+            pl = prof.per_launch()
+            pl = pl[-(len(pl) // reps):]
+            with open(args.layer_profile, "w") as f:
+                f.write("kernel,geometry,us,tflops,gbs\n")
+                for name, tag, ms, fl, by in pl:
+                    f.write(f"{name},{tag},{ms * 1e3:.2f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.2f},{by / (ms * 1e-3) / 1e9 if ms > 0 else 0:.1f}\n")
         conv = summ.get("icaf_conv2d_fwd", {"ms": 1.0, "flops": 0.0, "launches": 1})
         tf_peak, hbm_peak, peak_src = _peaks()
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
@@ -287,6 +294,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="yolov5s_b1", choices=sorted(WORKLOADS))
+    ap.add_argument("--layer-profile", default=None, help="write a per-launch CSV (event-timed eager pass) to this path")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -1,4 +1,5 @@
 // Library-wide state of libicaf_b200: version, thread-local error string, device properties.
+#include <cstdlib>
 #include <cstring>
 
 #include "icaf_internal.cuh"
@@ -19,6 +20,14 @@ int check_launch(const char* where) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, where);
   return ICAF_OK;
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ICAF_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 int sm_count_cached() {
   static int sms = 0;

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(160, 1) cross_attn_tc_kernel(const AttnParams 
   auto kv_empty = [&](int i) { return bar + 48u + 8u * i; };
   const uint32_t tmem_slot = bar + 64;
 
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5;
   const int dir = blockIdx.z;                 // 0: out_vis (q_ir, k_vis, v_vis)   1: out_ir (q_vis, k_ir, v_ir)
   const int b = blockIdx.y / P.heads, head = blockIdx.y % P.heads;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(160, 1) cross_attn_tc_kernel(const AttnParams 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();           // everything above overlapped the previous kernel's tail; q/k/v are its outputs
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + L::kBarOff + 64);
   const uint32_t tmem_S = tmem, tmem_O = tmem + kKV;
 
@@ -255,6 +257,8 @@ __global__ void __launch_bounds__(160, 1) cross_attn_tc_kernel(const AttnParams 
 // ---------------------------------------------------------------------------------------------------
 // CUDA-core reference, one thread per (query, head, batch, direction). Tests only.
 __global__ void cross_attn_simt_kernel(const AttnParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int d = P.C / P.heads;
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = 2LL * P.B * P.heads * P.n_pad;
@@ -319,7 +323,7 @@ static int launch_attn(const AttnParams& P, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((P.n_pad + kQT - 1) / kQT, P.B * P.heads, 2);
-  cross_attn_tc_kernel<D><<<grid, 160, L::kTotal, st>>>(P);
+  launch_k(cross_attn_tc_kernel<D>, dim3(grid), dim3(160), L::kTotal, st, P);
   return check_launch("cross_attention");
 }
 
@@ -348,6 +352,6 @@ extern "C" int icaf_cross_attention_simt(const void* qk_vis, const void* qk_ir, 
   int rc = fill_attn(qk_vis, qk_ir, vt_vis, vt_ir, out_vis, out_ir, B, N, n_pad, C, heads, P);
   if (rc) return rc;
   long long total = 2LL * B * heads * n_pad;
-  cross_attn_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P);
+  launch_k(cross_attn_simt_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, P);
   return check_launch("cross_attention_simt");
 }

@@ -36,6 +36,8 @@ __device__ __forceinline__ uint4 hmax8(const uint4& a, const uint4& b) {
 // (B,3,H,W) planar -> (B,H,W,4) fp16
 template <typename T>
 __global__ void pack_image_kernel(const T* __restrict__ src, float scale, long long npix, long long hw, __half* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= npix) return;
   long long b = i / hw, p = i - b * hw;
@@ -51,6 +53,8 @@ __global__ void pack_image_kernel(const T* __restrict__ src, float scale, long l
 // SPPF: three chained 5x5/s1/p2 max pools == 5x5, 9x9, 13x13 windows clipped to the map (-inf padding)
 __global__ void sppf_pool_kernel(const __half* __restrict__ x, long long x_ld, __half* y1, __half* y2, __half* y3,
                                  long long y_ld, int B, int H, int W, int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)B * H * W * C8;
   if (i >= total) return;
@@ -86,6 +90,8 @@ __global__ void sppf_pool_kernel(const __half* __restrict__ x, long long x_ld, _
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const __half* __restrict__ x, long long x_ld, __half* __restrict__ y, long long y_ld,
                                   int B, int H, int W, int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)B * (2 * H) * (2 * W) * C8;
   if (i >= total) return;
@@ -101,6 +107,8 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, long long x_ld, 
 
 __global__ void copy_channels_kernel(const __half* __restrict__ x, long long x_ld, __half* __restrict__ y,
                                      long long y_ld, long long pixels, int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= pixels * C8) return;
   int c = int(i % C8);
@@ -117,6 +125,8 @@ struct PoolTokParams {
   int B, H, W, C8, nh, nw, n_pad, kh, kw, sh, sw;
 };
 __global__ void dmff_pool_tokens_kernel(const PoolTokParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int mod = blockIdx.y;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)P.B * P.n_pad * P.C8;
@@ -160,6 +170,8 @@ struct LnParams {
   long long rows; int C; float eps;
 };
 __global__ void layernorm_kernel(const LnParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int prob = blockIdx.y;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= P.rows) return;
@@ -216,6 +228,8 @@ struct UpCatParams {
   float sy, sx;   // nh/H, nw/W
 };
 __global__ void dmff_upsample_cat_kernel(const UpCatParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int mod = blockIdx.y;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)P.B * P.H * P.W * P.C8;
@@ -265,6 +279,8 @@ struct DetectParams {
   float anchors[16];
 };
 __global__ void detect_decode_kernel(const DetectParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)P.B * P.na * P.ny * P.nx;
   if (i >= total) return;
@@ -305,9 +321,9 @@ extern "C" int icaf_pack_image(const void* src, int src_dtype, float scale, int 
   long long hw = (long long)H * W, npix = hw * B;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned g = blocks_for(npix, 256);
-  if (src_dtype == 0) pack_image_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, scale, npix, hw, (__half*)dst);
-  else if (src_dtype == 1) pack_image_kernel<float><<<g, 256, 0, st>>>((const float*)src, scale, npix, hw, (__half*)dst);
-  else if (src_dtype == 2) pack_image_kernel<uint8_t><<<g, 256, 0, st>>>((const uint8_t*)src, scale, npix, hw, (__half*)dst);
+  if (src_dtype == 0) launch_k(pack_image_kernel<__half>, dim3(g), dim3(256), 0, st, (const __half*)src, scale, npix, hw, (__half*)dst);
+  else if (src_dtype == 1) launch_k(pack_image_kernel<float>, dim3(g), dim3(256), 0, st, (const float*)src, scale, npix, hw, (__half*)dst);
+  else if (src_dtype == 2) launch_k(pack_image_kernel<uint8_t>, dim3(g), dim3(256), 0, st, (const uint8_t*)src, scale, npix, hw, (__half*)dst);
   else return set_error(ICAF_ERR_BAD_ARG, "pack_image: src_dtype must be 0 (fp16), 1 (fp32) or 2 (uint8)");
   return check_launch("pack_image");
 }
@@ -316,7 +332,7 @@ extern "C" int icaf_sppf_pool(const void* x, int64_t x_ld, void* y1, void* y2, v
                               int W, int C, void* stream) {
   if (!x || !y1 || !y2 || !y3 || C % 8 || x_ld % 8 || y_ld % 8) return set_error(ICAF_ERR_BAD_ARG, "sppf_pool: bad argument");
   long long total = (long long)B * H * W * (C / 8);
-  sppf_pool_kernel<<<blocks_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __half*)x, x_ld, (__half*)y1, (__half*)y2,
+  launch_k(sppf_pool_kernel, dim3(blocks_for(total, 128)), dim3(128), 0, (cudaStream_t)stream, (const __half*)x, x_ld, (__half*)y1, (__half*)y2,
                                                                             (__half*)y3, y_ld, B, H, W, C / 8);
   return check_launch("sppf_pool");
 }
@@ -324,13 +340,13 @@ extern "C" int icaf_sppf_pool(const void* x, int64_t x_ld, void* y1, void* y2, v
 extern "C" int icaf_upsample2x(const void* x, int64_t x_ld, void* y, int64_t y_ld, int B, int H, int W, int C, void* stream) {
   if (!x || !y || C % 8 || x_ld % 8 || y_ld % 8) return set_error(ICAF_ERR_BAD_ARG, "upsample2x: bad argument");
   long long total = (long long)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, x_ld, (__half*)y, y_ld, B, H, W, C / 8);
+  launch_k(upsample2x_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, x_ld, (__half*)y, y_ld, B, H, W, C / 8);
   return check_launch("upsample2x");
 }
 
 extern "C" int icaf_copy_channels(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t pixels, int C, void* stream) {
   if (!x || !y || C % 8 || x_ld % 8 || y_ld % 8) return set_error(ICAF_ERR_BAD_ARG, "copy_channels: bad argument");
-  copy_channels_kernel<<<blocks_for(pixels * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, x_ld, (__half*)y, y_ld,
+  launch_k(copy_channels_kernel, dim3(blocks_for(pixels * (C / 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, x_ld, (__half*)y, y_ld,
                                                                                           pixels, C / 8);
   return check_launch("copy_channels");
 }
@@ -352,7 +368,7 @@ extern "C" int icaf_dmff_pool_tokens(const void* x_vis, const void* x_ir, int64_
   P.kh = H - (nh - 1) * P.sh; P.kw = W - (nw - 1) * P.sw;
   long long total = (long long)B * n_pad * P.C8;
   dim3 grid(blocks_for(total, 128), 2);
-  dmff_pool_tokens_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P);
+  launch_k(dmff_pool_tokens_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, P);
   return check_launch("dmff_pool_tokens");
 }
 
@@ -364,7 +380,7 @@ extern "C" int icaf_layernorm(const void* x0, const void* x1, const float* g0, c
   P.x[0] = (const __half*)x0; P.x[1] = (const __half*)x1; P.y[0] = (__half*)y0; P.y[1] = (__half*)y1;
   P.g[0] = g0; P.g[1] = g1; P.b[0] = b0; P.b[1] = b1; P.rows = rows; P.C = C; P.eps = eps;
   dim3 grid(blocks_for(rows, 4), x1 ? 2 : 1);
-  layernorm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P);
+  launch_k(layernorm_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, P);
   return check_launch("layernorm");
 }
 
@@ -380,7 +396,7 @@ extern "C" int icaf_dmff_upsample_cat(const void* tok_vis, const void* tok_ir, i
   P.sy = float(nh) / float(H); P.sx = float(nw) / float(W);
   long long total = (long long)B * H * W * P.C8;
   dim3 grid(blocks_for(total, 256), 2);
-  dmff_upsample_cat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  launch_k(dmff_upsample_cat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, P);
   return check_launch("dmff_upsample_cat");
 }
 
@@ -393,6 +409,6 @@ extern "C" int icaf_detect_decode(const void* p, int64_t p_ld, void* x_out, void
   P.B = B; P.ny = ny; P.nx = nx; P.na = na; P.no = no; P.total_rows = total_rows; P.row_off = row_off; P.stride = stride;
   for (int i = 0; i < na * 2; ++i) P.anchors[i] = anchors_host[i];
   long long total = (long long)B * na * ny * nx;
-  detect_decode_kernel<<<blocks_for(total, 128), 128, 0, (cudaStream_t)stream>>>(P);
+  launch_k(detect_decode_kernel, dim3(blocks_for(total, 128)), dim3(128), 0, (cudaStream_t)stream, P);
   return check_launch("detect_decode");
 }

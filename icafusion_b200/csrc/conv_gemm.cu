@@ -40,7 +40,8 @@ struct ConvParams {
   int M, N, K, k_pad;
   int B, Hi, Wi, Cin, Ho, Wo, kh, kw, stride, pad;
   int act, epi;
-  int a_mode, tw, th, tiles_x, tiles_y;   // A_TMA4D: tile = th x tw output pixels, tiles_x*tiles_y tiles per image
+  int a_mode, tw, th, tiles_x, tiles_y;   // A_TMA4D: tile = th x tw output pixels (tw*th <= 128), tiles per image
+  int stages;                             // smem ring depth (runtime: deep rings for small grids, 2 CTAs/SM otherwise)
 };
 struct ConvMaps {          // TMA descriptors, passed by value as a __grid_constant__ kernel parameter
   CUtensorMap w[2];
@@ -110,17 +111,16 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float
   }
 }
 
+constexpr int kMaxStages = 10;
 template <int BN>
 struct SmemLayout {
-  // ring depth chosen so that two CTAs fit one SM for BN <= 128 (<= ~100 KB each)
-  static constexpr int kStages = BN >= 128 ? 3 : 4;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOff = kStages * kStageBytes;
-  static constexpr int kBiasOff = kBarOff + 128;        // fp32 bias tile [BN]
-  static constexpr int kTotal = kBiasOff + BN * 4 + 1024;   // + 1024 alignment slack
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // [ring: stages x (A|B)] [barriers 256 B] [bias BN fp32] ; + 1024 B alignment slack
+  static constexpr int kTailBytes = 256 + BN * 4 + 1024;
+  static int total(int stages) { return stages * kStageBytes + kTailBytes; }
 };
 
 template <int BN>
@@ -129,14 +129,16 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   using L = SmemLayout<BN>;
-  constexpr int kStages = L::kStages;
-  const uint32_t bar_base = smem_base + L::kBarOff;
+  const int kStages = P.stages;
+  const uint32_t bar_off = uint32_t(kStages) * L::kStageBytes;
+  const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * kStages);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * kMaxStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int tid = threadIdx.x;
   const ConvProblem pr = pick_problem(P, blockIdx.z);   // by value: a dynamic param index would spill to local
@@ -147,6 +149,7 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
   int m0 = blockIdx.x * BM, tb = 0, oy0 = 0, ox0 = 0;
   if (a_mode == A_TMA4D) {
     const int per_img = P.tiles_x * P.tiles_y;
+    m0 = 0;
     tb = blockIdx.x / per_img;
     const int t = blockIdx.x - tb * per_img;
     oy0 = (t / P.tiles_x) * P.th;
@@ -167,13 +170,14 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
     tma_prefetch_desc(blockIdx.z ? &maps.w[1] : &maps.w[0]);
     if (a_mode != A_GATHER) tma_prefetch_desc(blockIdx.z ? &maps.a[1] : &maps.a[0]);
   }
-  float* sbias = reinterpret_cast<float*>(smem_gen + L::kBiasOff);
+  float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256);
   for (int i = tid; i < BN; i += kThreads)
     sbias[i] = (pr.bias && !(P.epi & ICAF_EPI_BIAS_ROW) && n0 + i < P.N) ? pr.bias[n0 + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(smem_gen + L::kBarOff + 8 * (2 * kStages + 1));
+  pdl_wait();   // prologue (barriers, TMEM, descriptor prefetch, bias = parameters only) overlapped the previous kernel
+  const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * kMaxStages + 1));
 
   if (warp < 4) {
     if (a_mode == A_GATHER) {
@@ -196,9 +200,9 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
         iy0[i] = mv ? oy * P.stride - P.pad : -100000;   // invalid rows fall out of bounds -> zero fill
         ix0[i] = ox * P.stride - P.pad;
       }
+      int s = 0, s_done = 0;          // stage being filled / next stage to hand to the MMA warp
+      uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t sa = smem_base + s * L::kStageBytes;
         const int k0 = kb * BK + c * 8;
@@ -215,15 +219,20 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
           cp_async16(sa + uint32_t(r0 + 16 * i) * 128u + sw, pr.x + off, ok);
         }
         cp_async_commit();
+        if (++s == kStages) { s = 0; ph ^= 1; }
         if (kb >= kLag) {
           cp_async_wait<kLag>();
           fence_proxy_async_smem();
-          mbar_arrive(full_bar((kb - kLag) % kStages));
+          mbar_arrive(full_bar(s_done));
+          if (++s_done == kStages) s_done = 0;
         }
       }
       cp_async_wait<0>();
       fence_proxy_async_smem();
-      for (int kb = (nkb > kLag ? nkb - kLag : 0); kb < nkb; ++kb) mbar_arrive(full_bar(kb % kStages));
+      for (int kb = (nkb > kLag ? nkb - kLag : 0); kb < nkb; ++kb) {
+        mbar_arrive(full_bar(s_done));
+        if (++s_done == kStages) s_done = 0;
+      }
     }
 
     // ------------------------------------------------------------------ epilogue
@@ -235,7 +244,7 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
     if (a_mode == A_TMA4D) {
       const int ry = row / P.tw, rx = row - ry * P.tw;
       m = (tb * P.Ho + oy0 + ry) * P.Wo + ox0 + rx;
-      mvalid = true;                       // tiles divide the map exactly (host-checked)
+      mvalid = ry < P.th && oy0 + ry < P.Ho;      // tw divides Wo; the last tile row of an image may hang over
     } else {
       m = m0 + row;
       mvalid = m < P.M;
@@ -278,9 +287,9 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    int s = 0;
+    uint32_t ph = 0;
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kStages;
-      const uint32_t ph = (kb / kStages) & 1;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       if (elect_one()) {
@@ -294,16 +303,18 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
         if (kb == nkb - 1) umma_commit(accum_bar);
       }
       __syncwarp();
+      if (++s == kStages) { s = 0; ph ^= 1; }
     }
   } else {
     // ------------------------------------------------------------------ TMA producer (warp 5, one thread)
     if (elect_one()) {
       const CUtensorMap* mw = blockIdx.z ? &maps.w[1] : &maps.w[0];
       const CUtensorMap* ma = blockIdx.z ? &maps.a[1] : &maps.a[0];
-      const uint32_t bytes = L::kBBytes + (a_mode != A_GATHER ? L::kABytes : 0);
+      const uint32_t a_bytes = a_mode == A_TMA2D ? L::kABytes : (a_mode == A_TMA4D ? uint32_t(P.tw * P.th) * 128u : 0u);
+      const uint32_t bytes = L::kBBytes + a_bytes;
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t sa = smem_base + s * L::kStageBytes;
         mbar_arrive_expect_tx(full_bar(s), bytes);
@@ -317,6 +328,7 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
           const int ky = tap / P.kw, kx = tap - ky * P.kw;
           tma_load_4d(sa, ma, full_bar(s), ch, ox0 * P.stride - P.pad + kx, oy0 * P.stride - P.pad + ky, tb);
         }
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
@@ -333,6 +345,8 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
 // CUDA-core reference with the identical contract (tests only).
 struct SimtParams { ConvParams P; const __half* w[2]; };
 __global__ void conv_gemm_simt_kernel(const SimtParams S) {
+  pdl_launch_dependents();
+  pdl_wait();
   const ConvParams& P = S.P;
   const ConvProblem pr = pick_problem(P, blockIdx.z);
   const __half* w = blockIdx.z ? S.w[1] : S.w[0];
@@ -398,25 +412,46 @@ static void plan_a_mode(const icaf_conv_geom* g, ConvParams& P) {
     return;
   }
   if (g->Cin % 64 == 0 && g->stride <= 2) {
-    for (int tw = 128; tw >= 4; tw >>= 1) {          // widest power-of-two tile row that divides the map
+    // tile = th x tw output pixels of one image, tw | Wo, tw*th <= 128: maximise the fraction of useful MMA rows
+    int best_tw = 0, best_th = 0;
+    double best_u = 0.0;
+    for (int tw = 1; tw <= 128 && tw <= g->Wo; ++tw) {
+      if (g->Wo % tw || tw * g->stride > 256) continue;
       int th = 128 / tw;
-      if (g->Wo % tw == 0 && g->Ho % th == 0 && tw * g->stride <= 256 && th * g->stride <= 256) {
-        P.a_mode = A_TMA4D; P.tw = tw; P.th = th; P.tiles_x = g->Wo / tw; P.tiles_y = g->Ho / th;
-        return;
-      }
+      if (th > g->Ho) th = g->Ho;
+      if (th * g->stride > 256) th = 256 / g->stride;
+      int ty = (g->Ho + th - 1) / th;
+      double u = double(g->Wo) * g->Ho / (double(g->Wo / tw) * ty * 128.0);
+      if (u > best_u + 1e-9 || (u > best_u - 1e-9 && tw > best_tw)) { best_u = u; best_tw = tw; best_th = th; }
+    }
+    if (best_u >= 0.6) {
+      P.a_mode = A_TMA4D; P.tw = best_tw; P.th = best_th; P.tiles_x = g->Wo / best_tw; P.tiles_y = (g->Ho + best_th - 1) / best_th;
     }
   }
 }
 
 template <int BN>
-static int launch_tc(const ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+static int launch_tc(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
   using L = SmemLayout<BN>;
+  constexpr int kSmemCap = 227 * 1024;
   static bool configured = false;   // idempotent attribute; benign race
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
     if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute");
     configured = true;
   }
+  const int mt = P.a_mode == A_TMA4D ? P.B * P.tiles_x * P.tiles_y : (P.M + BM - 1) / BM;
+  dim3 grid(mt, (P.N + BN - 1) / BN, n_io);
+  // Ring depth: a grid that fits in one wave gets the whole SM (deep ring: the K loop is latency-bound at small M);
+  // otherwise two CTAs share an SM so that one CTA's epilogue overlaps the other's main loop.
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  const int budget = (ctas <= sm_count_cached() || BN > 128) ? kSmemCap : (kSmemCap / 2 - 1024);
+  int stages = (budget - L::kTailBytes) / L::kStageBytes;
+  const int nkb = P.k_pad / BK;
+  if (stages > nkb) stages = nkb;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  P.stages = stages;
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < n_io; ++i) {
@@ -431,8 +466,7 @@ static int launch_tc(const ConvParams& P, const __half* const (&w)[2], const ica
     if (rc) return rc;
   }
   if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
-  dim3 grid((P.M + BM - 1) / BM, (P.N + BN - 1) / BN, n_io);
-  conv_gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(P, maps);
+  launch_k(conv_gemm_tc_kernel<BN>, grid, dim3(kThreads), (size_t)L::total(stages), st, P, maps);
   return check_launch("conv2d_fwd");
 }
 
@@ -449,7 +483,7 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   cudaStream_t st = (cudaStream_t)stream;
   // Tile width: the widest BN that still yields at least ~one CTA per SM (two waves for the 1-CTA/SM BN=256); small
   // problems take BN=32 so that more SMs share the K loop.
-  const long long mt = (P.M + BM - 1) / BM;
+  const long long mt = P.a_mode == A_TMA4D ? (long long)P.B * P.tiles_x * P.tiles_y : (P.M + BM - 1) / BM;
   const int sms = sm_count_cached();
   auto ctas = [&](int bn) { return mt * ((P.N + bn - 1) / bn) * n_io; };
   int bn = 32;
@@ -470,6 +504,6 @@ extern "C" int icaf_conv2d_fwd_simt(const icaf_conv_geom* g, const icaf_conv_io*
   if (rc) return rc;
   long long total = (long long)S.P.M * S.P.N;
   dim3 grid((unsigned)((total + 255) / 256), 1, n_io);
-  conv_gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(S);
+  launch_k(conv_gemm_simt_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, S);
   return check_launch("conv2d_fwd_simt");
 }

@@ -14,6 +14,21 @@ int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
 int check_launch(const char* where);   // cudaGetLastError after a launch; never synchronises
 int sm_count_cached();
+bool pdl_enabled();        // programmatic dependent launch on every kernel (env ICAF_PDL, default on)
+
+// Launch with the programmatic-stream-serialization attribute when PDL is enabled (every kernel of this library
+// executes griddepcontrol.wait before it touches memory another kernel may have produced).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // TMA descriptors (host side). fp16 tensors, 128-byte swizzle, zero fill out of bounds.
 // 2D: [rows][inner] with a row pitch in bytes; box = box_rows x box_inner (box_inner*2 <= 128 B).

@@ -63,6 +63,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream may start its prologue now; wait: block until every kernel this
+// launch programmatically depends on has completed and flushed its writes.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ proxy fences
 // generic-proxy smem writes (st.shared / completed cp.async) -> visible to the async proxy (UMMA, TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -38,6 +38,10 @@ class profile:
         global _PROFILE
         _PROFILE = None
 
+    def per_launch(self):
+        """[(name, tag, ms, flops, bytes)] in launch order (call after a device synchronize)."""
+        return [(n, w.get("tag", ""), e0.elapsed_time(e1), w.get("flops", 0.0), w.get("bytes", 0.0)) for n, w, e0, e1 in self.records]
+
     def summary(self):
         out = {}
         for name, work, e0, e1 in self.records:
@@ -167,7 +171,8 @@ def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Option
     fn = _lib.lib().icaf_conv2d_fwd_simt if simt else _lib.lib().icaf_conv2d_fwd
     M = B * Ho * Wo
     kk = p0.kh * p0.kw * p0.cin
-    work = {"flops": 2.0 * M * p0.cout * kk * n,
+    work = {"tag": f"M{M} N{p0.cout} K{kk} k{p0.kh}s{p0.stride} x{n}" + (" +res" if res is not None else ""),
+            "flops": 2.0 * M * p0.cout * kk * n,
             "bytes": 2.0 * n * (B * Hi * Wi * p0.cin + M * p0.cout * (2 if res is not None else 1) + p0.cout * kk)}
     _call("icaf_conv2d_fwd_simt" if simt else "icaf_conv2d_fwd", fn, (C.byref(g), ios, n), work)
     return list(outs)
