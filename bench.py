@@ -168,7 +168,9 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
-def run_ours(args, wl):
+def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
+    """Build the detector for workload `wl` on `dev`, time K graph-replayed steps (device-resident inputs) and, for the
+    primary workload, K end-to-end steps from pinned host frames; profile the kernels of one step.  Returns a dict on rank 0."""
     import torch
     import torch.distributed as dist
     from helpers import load_synth
@@ -177,15 +179,7 @@ def run_ours(args, wl):
     from oracle import icaf_oracle as O
     from oracle import synth
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    dev = torch.device(f"cuda:{local}")
-    torch.cuda.set_device(dev)
     B, H, W = wl["batch"], wl["H"], wl["W"]
-
     model = Model(f"yolov5{wl['size']}_Transfusion_kaist").eval()
     load_synth(model, 0)
     model = model.fuse().half().to(dev)
@@ -195,7 +189,6 @@ def run_ours(args, wl):
     eng.rgb.copy_(rgb_u8)
     eng.ir.copy_(ir_u8)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    K, Wm = args.steps, max(3, args.warmup)
 
     def barrier():
         if world > 1:
@@ -219,68 +212,107 @@ def run_ours(args, wl):
     t_wall = time.perf_counter() - t_wall
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     # ---------------- end-to-end timing through the public call with host frames -----------------------------
-    for _ in range(Wm):
-        eng.infer_to_host(rgb_pin, ir_pin)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        eng.infer_to_host(rgb_pin, ir_pin)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = 0.0
+    if primary:
+        for _ in range(Wm):
+            eng.infer_to_host(rgb_pin, ir_pin)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            eng.infer_to_host(rgb_pin, ir_pin)
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
 
+    # ---------------- roofline of the dominant kernel: event-bracketed eager pass --------------------------------
+    # The launches of the profiled step are queued behind a ~3 ms spin kernel so that they execute back to back (an
+    # event pair then sees kernel time + inter-kernel gap, not the Python launch latency).
+    with torch.no_grad():
+        model(eng.rgb, eng.ir)
+        torch.cuda.synchronize()
+        reps = 3
+        with ops.profile() as prof:
+            for _ in range(reps):
+                flush.zero_()
+                torch.cuda._sleep(int(6e6))
+                model(eng.rgb, eng.ir)
+                torch.cuda.synchronize()
+    summ = prof.summary()
+    if primary and args.layer_profile:           # per-launch table of the last profiled step (geometry, us, TFLOP/s, GB/s)
+        pl = prof.per_launch()
+        pl = pl[-(len(pl) // reps):]
+        with open(args.layer_profile, "w") as f:
+            f.write("kernel,geometry,us,tflops,gbs\n")
+            for name, tag, ms, fl, by in pl:
+                f.write(f"{name},{tag},{ms * 1e3:.2f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.2f},{by / (ms * 1e-3) / 1e9 if ms > 0 else 0:.1f}\n")
+    conv = summ.get("icaf_conv2d_fwd", {"ms": 1.0, "flops": 0.0, "launches": 1})
+    tf_peak, hbm_peak, peak_src = _peaks()
+    ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+    total_ms = sum(v["ms"] for v in summ.values())
+    roofline = {"kernel": "conv_gemm_tc_kernel (icaf_conv2d_fwd: every Conv/Linear/Detect GEMM of a step)", "bound": "tensor",
+                "achieved": round(ach, 3), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 5), "traffic": None,
+                "peak_source": peak_src, "launches_per_step": conv["launches"] // reps,
+                "avg_launch_us": round(1e3 * conv["ms"] / max(1, conv["launches"]), 2),
+                "share_of_step_kernel_time": round(conv["ms"] / total_ms, 3),
+                "per_kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(summ.items())}}
+    flops_pair = O.model_conv_flops(model.yaml, H, W)
+    pairs = world * B * K
+    out = {"value": round(pairs / (dev_ms * 1e-3), 2), "ms_per_step": round(dev_ms / K, 4), "steps": K, "warmup": Wm,
+           "config": {"workload": wl["desc"], "pairs_per_gpu_per_step": B, "gflop_per_pair": round(flops_pair / 1e9, 2),
+                      "weights": "seeded synthetic (oracle/synth.py), BN folded (Model.fuse())",
+                      "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                      "execution": "CUDA graph replay of libicaf_b200 kernels (programmatic dependent launch)",
+                      "parallelism": f"dp{world} (batch-sharded replicas, no collective)"},
+           "gpu_launches": eng.launches_per_step * K,
+           "model_tflops": round(flops_pair * pairs / (dev_ms * 1e-3) / 1e12, 3),
+           "wall_s_timed_region": round(t_wall, 4), "clocks": clocks, "roofline": roofline}
+    if primary:
+        out["e2e"] = {"value": round(pairs / (e2e_ms * 1e-3), 2), "unit": "pairs/s",
+                      "h2d_bytes_per_step": int(rgb_pin.numel() + ir_pin.numel()), "d2h_bytes_per_step": int(eng.z.numel() * 2),
+                      "ms_per_step": round(e2e_ms / K, 4), "api": "GraphedDetector.infer_to_host(rgb_u8_pinned, ir_u8_pinned)"}
+    del eng, model, flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    K, Wm = args.steps, max(3, args.warmup)
+    m = _measure(args, wl, K, Wm, dev, world, rank, local, primary=True)
+    sec_name = args.secondary
+    if sec_name == "auto":
+        sec_name = "yolov5l_b16" if (args.workload == "yolov5s_b1" and world == 1) else "none"
+    sec = None
+    if sec_name != "none" and world == 1:
+        sec = _measure(args, WORKLOADS[sec_name], max(5, min(K, 20)), 3, dev, world, rank, local, primary=False)
     if rank == 0:
-        # ---------------- roofline of the dominant kernel: event-bracketed eager pass -------------------------
-        with torch.no_grad():
-            model(eng.rgb, eng.ir)
-            torch.cuda.synchronize()
-            reps = 3
-            with ops.profile() as prof:
-                for _ in range(reps):
-                    flush.zero_()
-                    model(eng.rgb, eng.ir)
-            torch.cuda.synchronize()
-        summ = prof.summary()
-        if args.layer_profile:           # per-launch table of the last profiled step (geometry, us, TFLOP/s, GB/s)
-            pl = prof.per_launch()
-            pl = pl[-(len(pl) // reps):]
-            with open(args.layer_profile, "w") as f:
-                f.write("kernel,geometry,us,tflops,gbs\n")
-                for name, tag, ms, fl, by in pl:
-                    f.write(f"{name},{tag},{ms * 1e3:.2f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.2f},{by / (ms * 1e-3) / 1e9 if ms > 0 else 0:.1f}\n")
-        conv = summ.get("icaf_conv2d_fwd", {"ms": 1.0, "flops": 0.0, "launches": 1})
-        tf_peak, hbm_peak, peak_src = _peaks()
-        ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
-        total_ms = sum(v["ms"] for v in summ.values())
-        roofline = {"kernel": "conv_gemm_tc_kernel (icaf_conv2d_fwd: every Conv/Linear/Detect GEMM of a step)", "bound": "tensor",
-                    "achieved": round(ach, 3), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 5), "traffic": None,
-                    "peak_source": peak_src, "launches_per_step": conv["launches"] // reps,
-                    "avg_launch_us": round(1e3 * conv["ms"] / max(1, conv["launches"]), 2),
-                    "share_of_step_kernel_time": round(conv["ms"] / total_ms, 3),
-                    "per_kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(summ.items())}}
-        flops_pair = O.model_conv_flops(model.yaml, H, W)
         cb = cpu_reference_throughput(wl, budget_s=20.0)
-        pairs = world * B * K
-        line = {"metric": METRIC, "value": round(pairs / (dev_ms * 1e-3), 2), "unit": "pairs/s", "n_gpus": world, "steps": K,
-                "warmup": Wm, "ms_per_step": round(dev_ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16", "data": "synthetic",
-                "config": {"workload": wl["desc"], "pairs_per_gpu_per_step": B, "gflop_per_pair": round(flops_pair / 1e9, 2),
-                           "weights": "seeded synthetic (oracle/synth.py), BN folded (Model.fuse())",
-                           "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                           "execution": "CUDA graph replay of libicaf_b200 kernels", "parallelism": f"dp{world} (batch-sharded replicas, no collective)"},
-                "e2e": {"value": round(pairs / (e2e_ms * 1e-3), 2), "unit": "pairs/s",
-                        "h2d_bytes_per_step": int(rgb_pin.numel() + ir_pin.numel()), "d2h_bytes_per_step": int(eng.z.numel() * 2),
-                        "ms_per_step": round(e2e_ms / K, 4), "api": "GraphedDetector.infer_to_host(rgb_u8_pinned, ir_u8_pinned)"},
-                "gpu_launches": eng.launches_per_step * K,
-                "model_tflops": round(flops_pair * world * B * K / (dev_ms * 1e-3) / 1e12, 3),
-                "wall_s_timed_region": round(t_wall, 4),
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
+        line = {"metric": METRIC, "value": m["value"], "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16", "data": "synthetic", "config": m["config"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"],
+                "model_tflops": m["model_tflops"], "wall_s_timed_region": m["wall_s_timed_region"], "clocks": m["clocks"],
+                "roofline": m["roofline"], "cpu_baseline": cb}
+        if sec is not None:
+            line["secondary"] = {"note": "same detector path at BASELINE configs[2] (compute-bound regime of the same kernels)",
+                                 "metric": METRIC, "unit": "pairs/s", **{k: sec[k] for k in
+                                 ("value", "ms_per_step", "steps", "warmup", "config", "model_tflops", "roofline")}}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -295,6 +327,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="yolov5s_b1", choices=sorted(WORKLOADS))
     ap.add_argument("--layer-profile", default=None, help="write a per-launch CSV (event-timed eager pass) to this path")
+    ap.add_argument("--secondary", default="auto", help="also measure this workload (device-resident value + roofline) and report it "
+                    "under 'secondary'; 'auto' = yolov5l_b16 when the primary is yolov5s_b1 on 1 GPU; 'none' disables")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

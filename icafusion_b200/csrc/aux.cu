@@ -87,6 +87,49 @@ __global__ void sppf_pool_kernel(const __half* __restrict__ x, long long x_ld, _
   *reinterpret_cast<uint4*>(y3 + o) = m13;
 }
 
+// Fast path for maps of <= 1024 pixels (the P5 map of any input up to 1024x1024): one block per (image, 8-channel
+// chunk) keeps the whole map in shared memory and runs the three chained pools as separable 5-tap row / column passes.
+__global__ void __launch_bounds__(1024) sppf_pool_smem_kernel(const __half* __restrict__ x, long long x_ld, __half* y1, __half* y2,
+                                                              __half* y3, long long y_ld, int H, int W, int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ uint4 sp[];                 // [2][H*W]
+  const int HW = H * W;
+  uint4* a = sp;
+  uint4* t = sp + HW;
+  const int b = blockIdx.x / C8, c = blockIdx.x % C8;
+  const int p = threadIdx.x;
+  const int py = p / W, px = p - py * W;
+  const long long pix = (long long)b * HW + p;
+  if (p < HW) a[p] = ldg16(x + pix * x_ld + c * 8);
+  __syncthreads();
+  __half* outs[3] = {y1, y2, y3};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (p < HW) {                                // row pass: max over x-2..x+2 (clipped = -inf padding)
+      uint4 m = a[p];
+#pragma unroll
+      for (int d = 1; d <= 2; ++d) {
+        if (px - d >= 0) m = hmax8(m, a[p - d]);
+        if (px + d < W) m = hmax8(m, a[p + d]);
+      }
+      t[p] = m;
+    }
+    __syncthreads();
+    if (p < HW) {                                // column pass
+      uint4 m = t[p];
+#pragma unroll
+      for (int d = 1; d <= 2; ++d) {
+        if (py - d >= 0) m = hmax8(m, t[p - d * W]);
+        if (py + d < H) m = hmax8(m, t[p + d * W]);
+      }
+      a[p] = m;                                  // input of the next chained pool (each thread rewrites only its own pixel)
+      *reinterpret_cast<uint4*>(outs[k] + pix * y_ld + c * 8) = m;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const __half* __restrict__ x, long long x_ld, __half* __restrict__ y, long long y_ld,
                                   int B, int H, int W, int C8) {
@@ -331,6 +374,12 @@ extern "C" int icaf_pack_image(const void* src, int src_dtype, float scale, int 
 extern "C" int icaf_sppf_pool(const void* x, int64_t x_ld, void* y1, void* y2, void* y3, int64_t y_ld, int B, int H,
                               int W, int C, void* stream) {
   if (!x || !y1 || !y2 || !y3 || C % 8 || x_ld % 8 || y_ld % 8) return set_error(ICAF_ERR_BAD_ARG, "sppf_pool: bad argument");
+  if (H * W <= 1024) {
+    int threads = (H * W + 31) / 32 * 32;
+    launch_k(sppf_pool_smem_kernel, dim3(B * (C / 8)), dim3(threads), (size_t)(2 * H * W * sizeof(uint4)), (cudaStream_t)stream,
+             (const __half*)x, x_ld, (__half*)y1, (__half*)y2, (__half*)y3, y_ld, H, W, C / 8);
+    return check_launch("sppf_pool");
+  }
   long long total = (long long)B * H * W * (C / 8);
   launch_k(sppf_pool_kernel, dim3(blocks_for(total, 128)), dim3(128), 0, (cudaStream_t)stream, (const __half*)x, x_ld, (__half*)y1, (__half*)y2,
                                                                             (__half*)y3, y_ld, B, H, W, C / 8);

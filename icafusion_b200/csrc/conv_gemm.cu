@@ -42,6 +42,7 @@ struct ConvParams {
   int act, epi;
   int a_mode, tw, th, tiles_x, tiles_y;   // A_TMA4D: tile = th x tw output pixels (tw*th <= 128), tiles per image
   int stages;                             // smem ring depth (runtime: deep rings for small grids, 2 CTAs/SM otherwise)
+  int splits;                             // split-K factor = cluster size along x (1 = no cluster); partial sums meet in DSMEM
 };
 struct ConvMaps {          // TMA descriptors, passed by value as a __grid_constant__ kernel parameter
   CUtensorMap w[2];
@@ -143,15 +144,21 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
   const int tid = threadIdx.x;
   const ConvProblem pr = pick_problem(P, blockIdx.z);   // by value: a dynamic param index would spill to local
   const int n0 = blockIdx.y * BN;
-  const int nkb = P.k_pad / BK;
   const int a_mode = P.a_mode;
+  // split-K: the `splits` CTAs of a cluster (consecutive blockIdx.x) share one output tile and take a K range each
+  const int splits = P.splits;
+  const uint32_t crank = splits > 1 ? cluster_ctarank() : 0u;
+  const int mtile = splits > 1 ? blockIdx.x / splits : blockIdx.x;
+  const int nkb_all = P.k_pad / BK;
+  const int kb_begin = (nkb_all * int(crank)) / splits;
+  const int nkb = (nkb_all * (int(crank) + 1)) / splits - kb_begin;
   // tile origin: linear rows (gather / 2-D) or a th x tw patch of image tb (4-D)
-  int m0 = blockIdx.x * BM, tb = 0, oy0 = 0, ox0 = 0;
+  int m0 = mtile * BM, tb = 0, oy0 = 0, ox0 = 0;
   if (a_mode == A_TMA4D) {
     const int per_img = P.tiles_x * P.tiles_y;
     m0 = 0;
-    tb = blockIdx.x / per_img;
-    const int t = blockIdx.x - tb * per_img;
+    tb = mtile / per_img;
+    const int t = mtile - tb * per_img;
     oy0 = (t / P.tiles_x) * P.th;
     ox0 = (t % P.tiles_x) * P.tw;
   }
@@ -171,8 +178,6 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
     if (a_mode != A_GATHER) tma_prefetch_desc(blockIdx.z ? &maps.a[1] : &maps.a[0]);
   }
   float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256);
-  for (int i = tid; i < BN; i += kThreads)
-    sbias[i] = (pr.bias && !(P.epi & ICAF_EPI_BIAS_ROW) && n0 + i < P.N) ? pr.bias[n0 + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -180,6 +185,16 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
   const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * kMaxStages + 1));
 
   if (warp < 4) {
+    // Epilogue operands that do not depend on the main loop are fetched now so their DRAM latency hides behind it:
+    // bias slice and (alpha, beta) into registers, this thread's residual row into L2.
+    float bias_r[(BN + 127) / 128];
+#pragma unroll
+    for (int i = 0; i < (BN + 127) / 128; ++i) {
+      const int col = tid + 128 * i;
+      bias_r[i] = (col < BN && pr.bias && !(P.epi & ICAF_EPI_BIAS_ROW) && n0 + col < P.N) ? __ldg(pr.bias + n0 + col) : 0.f;
+    }
+    float alpha = 0.f, beta = 1.f;
+    if (P.epi & ICAF_EPI_SCALED_RES) { alpha = __ldg(pr.alpha); beta = __ldg(pr.beta); }
     if (a_mode == A_GATHER) {
       // ---------------------------------------------------------------- cp.async gather producers
       const int c = tid & 7;          // 16-byte chunk within the 128-byte K row
@@ -205,7 +220,7 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t sa = smem_base + s * L::kStageBytes;
-        const int k0 = kb * BK + c * 8;
+        const int k0 = (kb_begin + kb) * BK + c * 8;
         const bool kvalid = k0 < P.K;
         const int tap = k0 / P.Cin;
         const int ch = k0 - tap * P.Cin;
@@ -236,8 +251,6 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
     }
 
     // ------------------------------------------------------------------ epilogue
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
     const int row = tid;                   // TMEM lane == tile row
     int m;
     bool mvalid;
@@ -250,37 +263,83 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
       mvalid = m < P.M;
     }
     const uint32_t trow = tmem_d + (uint32_t(warp * 32) << 16);
-    float alpha = 0.f, beta = 1.f;
-    if (P.epi & ICAF_EPI_SCALED_RES) { alpha = *pr.alpha; beta = *pr.beta; }
-    const float rbias = ((P.epi & ICAF_EPI_BIAS_ROW) && pr.bias && mvalid) ? pr.bias[m] : 0.f;
+    const float rbias = ((P.epi & ICAF_EPI_BIAS_ROW) && pr.bias && mvalid) ? __ldg(pr.bias + m) : 0.f;
     __half* yrow = pr.y + size_t(mvalid ? m : 0) * pr.y_ld;
     const __half* rrow = pr.res ? pr.res + size_t(mvalid ? m : 0) * pr.res_ld : nullptr;
     const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : (rrow ? 1 : 0);
+    if (rrow && mvalid) {
+      for (int cb = 0; cb < BN && n0 + cb < P.N; cb += 64) prefetch_l2(rrow + n0 + cb);   // 128-byte lines of the residual row
+    }
+#pragma unroll
+    for (int i = 0; i < (BN + 127) / 128; ++i)
+      if (tid + 128 * i < BN) sbias[tid + 128 * i] = bias_r[i];
+    named_bar_sync(1, 128);                // bias tile visible to the four epilogue warps
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int mode_act = P.act * 3 + mode;
+    if (splits > 1) {
+      // ---- split-K reduction through distributed shared memory ----
+      // Every CTA's ring is idle once its accumulator is complete.  Barrier A: all accumulators done (so the leader's
+      // ring may be overwritten); CTAs 1..S-1 then push their fp32 partial tile into the leader's ring; barrier B:
+      // the leader adds them to its own accumulator and runs the real epilogue.
+      constexpr int kPitch = BN + 4;                 // floats per staged row (+4: spreads the rows over the banks)
+      cluster_arrive();
+      cluster_wait();
+      if (crank != 0) {
+        const uint32_t dst0 = map_to_cta(smem_base, 0) + uint32_t(((crank - 1) * BM + row) * kPitch) * 4u;
 #pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      uint32_t acc[32];
-      __syncwarp();
-      tmem_ld32(trow + cb, acc);      // .sync.aligned: executed by the whole (converged) warp
-      tmem_ld_wait();
-      const int nb = n0 + cb;
-      if (mvalid && nb < P.N) {
-        const int ncols = min(32, P.N - nb);
-        const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(yrow + nb) & 15) == 0) &&
-                         (!rrow || (reinterpret_cast<uintptr_t>(rrow + nb) & 15) == 0);
-        const float* sb = sbias + cb;
-        const __half* rp = rrow ? rrow + nb : nullptr;
-        __half* yp = yrow + nb;
-        // act / residual mode are warp-uniform: dispatch once per chunk to straight-line specialisations
-        switch (P.act * 3 + mode) {
-          case 0: epi_chunk<0, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          case 1: epi_chunk<0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          case 2: epi_chunk<0, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          case 3: epi_chunk<1, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          case 4: epi_chunk<1, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          case 5: epi_chunk<1, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          case 6: epi_chunk<2, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          case 7: epi_chunk<2, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          default: epi_chunk<2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t acc[32];
+          __syncwarp();
+          tmem_ld32(trow + cb, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            st_cluster_v4(dst0 + uint32_t(cb + 4 * q) * 4u, acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        }
+      }
+      cluster_arrive();
+      cluster_wait();
+    }
+    if (crank == 0) {
+      const float* part = reinterpret_cast<const float*>(smem_gen) + size_t(row) * (BN + 4);
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t acc[32];
+        __syncwarp();
+        tmem_ld32(trow + cb, acc);      // .sync.aligned: executed by the whole (converged) warp
+        tmem_ld_wait();
+        for (int r = 1; r < splits; ++r) {
+          const float4* pp = reinterpret_cast<const float4*>(part + size_t(r - 1) * BM * (BN + 4) + cb);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v = pp[q];
+            acc[4 * q] = __float_as_uint(__uint_as_float(acc[4 * q]) + v.x);
+            acc[4 * q + 1] = __float_as_uint(__uint_as_float(acc[4 * q + 1]) + v.y);
+            acc[4 * q + 2] = __float_as_uint(__uint_as_float(acc[4 * q + 2]) + v.z);
+            acc[4 * q + 3] = __float_as_uint(__uint_as_float(acc[4 * q + 3]) + v.w);
+          }
+        }
+        const int nb = n0 + cb;
+        if (mvalid && nb < P.N) {
+          const int ncols = min(32, P.N - nb);
+          const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(yrow + nb) & 15) == 0) &&
+                           (!rrow || (reinterpret_cast<uintptr_t>(rrow + nb) & 15) == 0);
+          const float* sb = sbias + cb;
+          const __half* rp = rrow ? rrow + nb : nullptr;
+          __half* yp = yrow + nb;
+          // act / residual mode are warp-uniform: dispatch once per chunk to straight-line specialisations
+          switch (mode_act) {
+            case 0: epi_chunk<0, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            case 1: epi_chunk<0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            case 2: epi_chunk<0, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            case 3: epi_chunk<1, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            case 4: epi_chunk<1, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            case 5: epi_chunk<1, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            case 6: epi_chunk<2, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            case 7: epi_chunk<2, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            default: epi_chunk<2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+          }
         }
       }
     }
@@ -305,6 +364,7 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
       __syncwarp();
       if (++s == kStages) { s = 0; ph ^= 1; }
     }
+    if (splits > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
   } else {
     // ------------------------------------------------------------------ TMA producer (warp 5, one thread)
     if (elect_one()) {
@@ -318,11 +378,11 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t sa = smem_base + s * L::kStageBytes;
         mbar_arrive_expect_tx(full_bar(s), bytes);
-        tma_load_2d(sa + L::kABytes, mw, full_bar(s), kb * BK, n0);
+        tma_load_2d(sa + L::kABytes, mw, full_bar(s), (kb_begin + kb) * BK, n0);
         if (a_mode == A_TMA2D) {
-          tma_load_2d(sa, ma, full_bar(s), kb * BK, m0);
+          tma_load_2d(sa, ma, full_bar(s), (kb_begin + kb) * BK, m0);
         } else if (a_mode == A_TMA4D) {
-          const int k0 = kb * BK;
+          const int k0 = (kb_begin + kb) * BK;
           const int tap = k0 / P.Cin;
           const int ch = k0 - tap * P.Cin;
           const int ky = tap / P.kw, kx = tap - ky * P.kw;
@@ -332,6 +392,7 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
       }
     }
     __syncwarp();
+    if (splits > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -389,7 +450,7 @@ static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io
   P.M = int(M); P.N = g->Cout; P.K = g->kh * g->kw * g->Cin; P.k_pad = g->k_pad;
   P.B = g->B; P.Hi = g->Hi; P.Wi = g->Wi; P.Cin = g->Cin; P.Ho = g->Ho; P.Wo = g->Wo;
   P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad = g->pad; P.act = g->act; P.epi = g->epi;
-  P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0;
+  P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.stages = 2; P.splits = 1;
   for (int i = 0; i < 2; ++i) {
     const icaf_conv_io& s = io[i < n_io ? i : 0];
     bool need_res = g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES);
@@ -451,7 +512,24 @@ static int launch_tc(ConvParams& P, const __half* const (&w)[2], const icaf_conv
   if (stages > nkb) stages = nkb;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
+  // Split-K: a grid that leaves most SMs idle on a deep K loop is spread over clusters of `splits` CTAs per tile.
+  int splits = 1;
+  if (ctas * 2 <= sm_count_cached() && nkb >= 8) {
+    splits = int(sm_count_cached() / ctas);
+    if (splits > 8) splits = 8;                    // portable cluster size
+    if (splits > nkb / 4) splits = nkb / 4;        // >= 4 K blocks per CTA
+    const int per_split = BM * (BN + 4) * 4;       // staged fp32 partial tile in the leader's ring
+    while (splits > 1 && (splits - 1) * per_split > stages * L::kStageBytes) --splits;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1) {
+    const int per = (nkb + splits - 1) / splits;
+    if (stages > per) stages = per < 2 ? 2 : per;
+    while ((splits - 1) * (BM * (BN + 4) * 4) > stages * L::kStageBytes) ++stages;   // keep room for the partial tiles
+    grid.x *= splits;
+  }
   P.stages = stages;
+  P.splits = splits;
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < n_io; ++i) {
@@ -466,7 +544,7 @@ static int launch_tc(ConvParams& P, const __half* const (&w)[2], const icaf_conv
     if (rc) return rc;
   }
   if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
-  launch_k(conv_gemm_tc_kernel<BN>, grid, dim3(kThreads), (size_t)L::total(stages), st, P, maps);
+  launch_kc(conv_gemm_tc_kernel<BN>, grid, dim3(kThreads), (size_t)L::total(stages), st, (unsigned)splits, P, maps);
   return check_launch("conv2d_fwd");
 }
 

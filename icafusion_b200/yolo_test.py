@@ -59,24 +59,30 @@ class Detect(nn.Module):
             cache[i] = (key, ops.pack_conv_weight(conv.weight, conv.bias, 1, 0, ACT_NONE))
         return cache[i][1]
 
-    def run(self, vs: List[torch.Tensor]):
-        """vs: NHWC maps of the nl levels."""
-        B = vs[0].shape[0]
-        rows = [self.na * v.shape[1] * v.shape[2] for v in vs]
+    def alloc_outputs(self, B: int, level_hw, device):
+        """(z, logits, row offsets) for levels of spatial sizes level_hw = [(ny, nx), ...]."""
+        rows = [self.na * ny * nx for ny, nx in level_hw]
         total = sum(rows)
+        z = torch.empty(B, total, self.no, dtype=torch.float16, device=device)
+        logits = torch.empty(B, total, self.no - 5, dtype=torch.float16, device=device)
+        offs = [sum(rows[:i]) for i in range(len(rows))]
+        return z, logits, offs
+
+    def run_level(self, i: int, v: torch.Tensor, z, logits, off: int):
+        """One detection level: 1x1 conv (yolo_test.py:49) + decode (:50-63) into rows [off, off+na*ny*nx) of z/logits."""
         if self.training:
             raise NotImplementedError("Detect: training-mode forward is not built yet in icafusion_b200")
-        z = torch.empty(B, total, self.no, dtype=torch.float16, device=vs[0].device)
-        logits = torch.empty(B, total, self.no - 5, dtype=torch.float16, device=vs[0].device)
         anchor_px = self.__dict__.get("_icaf_anchor_px")
         if anchor_px is None:                      # host copy of anchor_grid (pixels); constant after build
             anchor_px = self.anchor_grid.detach().float().cpu().view(self.nl, -1).tolist()
             self.__dict__["_icaf_anchor_px"] = anchor_px
-        xs, off = [], 0
-        for i, v in enumerate(vs):
-            p = ops.conv2d([v], [self._packed(i)])[0]                                   # yolo_test.py:49
-            xs.append(ops.detect_decode(p, self.na, self.no, z, logits, off, float(self.stride[i]), anchor_px[i]))
-            off += rows[i]
+        p = ops.conv2d([v], [self._packed(i)])[0]
+        return ops.detect_decode(p, self.na, self.no, z, logits, off, float(self.stride[i]), anchor_px[i])
+
+    def run(self, vs: List[torch.Tensor]):
+        """vs: NHWC maps of the nl levels."""
+        z, logits, offs = self.alloc_outputs(vs[0].shape[0], [(v.shape[1], v.shape[2]) for v in vs], vs[0].device)
+        xs = [self.run_level(i, v, z, logits, offs[i]) for i, v in enumerate(vs)]
         return z, logits, xs
 
     def forward(self, x):
@@ -267,23 +273,37 @@ class Model(nn.Module):
             img = img.float()
         return ops.pack_image(img, 1.0 / 255.0 if img.dtype == torch.uint8 else 1.0)
 
+    def _side_streams(self, device, n: int):
+        pool = self.__dict__.setdefault("_icaf_streams", {})
+        lst = pool.setdefault(device, [])
+        while len(lst) < n:
+            lst.append(torch.cuda.Stream(device))
+        return lst
+
     def _forward_nhwc(self, rgb, ir):
+        """Layer walk with branch-level concurrency: the RGB/IR streams run as grouped launches on the current stream;
+        a DMFF block is forked onto a side stream as soon as both of its inputs exist (P3 and P4 fusion overlap the rest of
+        the backbone), Detect levels are forked as soon as their head output exists; consumers join before they read."""
         layers = list(self.model)
         y: List = [None] * len(layers)
-        v_rgb, v_ir = self._stage(rgb), self._stage(ir)
-        start = 0
-        if self._ir_start is not None:
-            s = self._ir_start
-            a, b = v_rgb, v_ir
-            for k in range(s):                       # both streams, one grouped launch per operator
-                ma, mb = layers[k], layers[s + k]
-                run = Conv.run if isinstance(ma, Conv) else C3.run if isinstance(ma, C3) else SPPF.run
-                a, b = run([ma, mb], [a, b])
-                y[k], y[s + k] = a, b
-            start = 2 * s
-            x = b
-        else:
-            x = v_rgb
+        dev = rgb.device
+        main = torch.cuda.current_stream(dev)
+        forked = {}                               # layer index -> side stream its result is being produced on
+        n_side = [0]
+        concurrent = self.__dict__.get("_icaf_concurrent", True)
+
+        def fork():
+            st = self._side_streams(dev, n_side[0] + 1)[n_side[0]]
+            n_side[0] += 1
+            st.wait_stream(main)
+            return st
+
+        def join(idxs):
+            for j in idxs:
+                st = forked.pop(j, None)
+                if st is not None:
+                    main.wait_stream(st)
+
         cats = {}                                 # concat layer index -> its (lazily allocated) output buffer
 
         def dest(m, shape_hw):
@@ -294,15 +314,63 @@ class Model(nn.Module):
             ci, off = d
             if ci not in cats:
                 B, H, W = shape_hw
-                cats[ci] = torch.empty(B, H, W, self._concat_width[ci], dtype=torch.float16, device=v_rgb.device)
+                cats[ci] = torch.empty(B, H, W, self._concat_width[ci], dtype=torch.float16, device=dev)
             return cats[ci][..., off:off + self._layer_ch[m.i]]
 
+        v_rgb, v_ir = self._stage(rgb), self._stage(ir)
+        start = 0
+        if self._ir_start is not None:
+            s = self._ir_start
+            fusion = [m for m in layers[2 * s:] if isinstance(m, TransformerFusionBlock) and isinstance(m.f, (list, tuple))
+                      and all(0 <= j < 2 * s for j in m.f)]
+            a, b = v_rgb, v_ir
+            for k in range(s):                       # both streams, one grouped launch per operator
+                ma, mb = layers[k], layers[s + k]
+                run = Conv.run if isinstance(ma, Conv) else C3.run if isinstance(ma, C3) else SPPF.run
+                a, b = run([ma, mb], [a, b])
+                y[k], y[s + k] = a, b
+                if concurrent:
+                    for m in fusion[:-1]:            # the last fusion block feeds the head directly: it stays in order
+                        if y[m.i] is None and all(y[j] is not None for j in m.f):
+                            xa, xb = y[m.f[0]], y[m.f[1]]
+                            out = dest(m, (xa.shape[0], xa.shape[1], xa.shape[2]))     # allocated on the main stream
+                            st = fork()
+                            with torch.cuda.stream(st):
+                                y[m.i] = m.run(xa, xb, out)
+                            forked[m.i] = st
+            start = 2 * s
+            x = b
+        else:
+            x = v_rgb
+
+        det = layers[-1] if isinstance(layers[-1], Detect) and isinstance(layers[-1].f, (list, tuple)) else None
+        det_state = None
         for m in layers[start:]:
+            if y[m.i] is not None and m.i in forked or (y[m.i] is not None and isinstance(m, TransformerFusionBlock)):
+                x = y[m.i]                         # already produced (possibly still in flight on a side stream)
+                continue
+            srcs = [m.i - 1] if m.f == -1 else ([] if m.f == -4 else ([m.f] if isinstance(m.f, int) else
+                                                                         [m.i - 1 if j == -1 else j for j in m.f]))
             if m.f == -4:
                 x = v_ir
             elif m.f != -1:
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+            if m is det and concurrent and det_state is not None:
+                # levels whose inputs were ready were forked earlier; run the rest here and join everything
+                z, logits, offs, xs = det_state
+                for i, j in enumerate(m.f):
+                    if xs[i] is None:
+                        join([j])
+                        xs[i] = m.run_level(i, y[j], z, logits, offs[i])
+                for st in list(forked.values()):
+                    main.wait_stream(st)
+                forked.clear()
+                x = (z, logits, xs)
+                y[m.i] = x
+                continue
+            join(srcs)
             if isinstance(m, Concat) and m.i in cats:
+                join([j for j, (ci, _) in self._concat_dst.items() if ci == m.i])
                 x = cats[m.i]                      # every source already wrote its slice
             else:
                 out = None
@@ -317,6 +385,23 @@ class Model(nn.Module):
                     out = dest(m, (B, H, W))
                 x = self._run_layer(m, x, out)
             y[m.i] = x
+            # fork Detect levels as soon as their input exists (all but the last one, which closes the forward)
+            if det is not None and concurrent and m.i in det.f and m.i != det.f[-1] and not isinstance(x, (list, tuple)):
+                if det_state is None:
+                    B = x.shape[0]
+                    Himg, Wimg = rgb.shape[2], rgb.shape[3]
+                    hw = [(int(Himg // float(st_)), int(Wimg // float(st_))) for st_ in det.stride]
+                    z, logits, offs = det.alloc_outputs(B, hw, dev)
+                    det_state = (z, logits, offs, [None] * det.nl)
+                i = det.f.index(m.i)
+                z, logits, offs, xs = det_state
+                if (x.shape[1], x.shape[2]) == (int(rgb.shape[2] // float(det.stride[i])), int(rgb.shape[3] // float(det.stride[i]))):
+                    st = fork()
+                    with torch.cuda.stream(st):
+                        xs[i] = det.run_level(i, x, z, logits, offs[i])
+                    forked[("det", i)] = st
+        for st in forked.values():                 # nothing may outlive the forward on a side stream
+            main.wait_stream(st)
         return x
 
     def fuse(self):

@@ -21,10 +21,11 @@ def test_pack_image(cuda_device, dtype, scale):
     assert torch.equal(out[..., :3], ref.permute(0, 2, 3, 1)) and float(out[..., 3].abs().max()) == 0
 
 
-def test_sppf_pool_bit_exact(cuda_device):
+@pytest.mark.parametrize("H,W", [(16, 20), (20, 20), (36, 40)])      # <=1024 px: smem kernel; 36x40: direct-window kernel
+def test_sppf_pool_bit_exact(cuda_device, H, W):
     from icafusion_b200 import ops
-    x = torch.randn(2, 64, 16, 20).half()
-    cat = torch.zeros(2, 16, 20, 256, dtype=torch.float16, device=cuda_device)
+    x = torch.randn(2, 64, H, W).half()
+    cat = torch.zeros(2, H, W, 256, dtype=torch.float16, device=cuda_device)
     cat[..., :64] = nhwc(x).to(cuda_device)
     ops.sppf_pool(cat[..., :64], cat[..., 64:128], cat[..., 128:192], cat[..., 192:])
     y1 = F.max_pool2d(x.float(), 5, 1, 2); y2 = F.max_pool2d(y1, 5, 1, 2); y3 = F.max_pool2d(y2, 5, 1, 2)   # common.py:259-266

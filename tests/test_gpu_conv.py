@@ -43,7 +43,10 @@ CASES = [
     (2, 64, 32, 40, 128, 3, 2, 1, 1),     # 3x3 stride 2 via 4-D TMA (traversal stride 2, negative start coordinate)
     (2, 128, 32, 40, 64, 3, 1, 1, 1),     # 3x3 stride 1 via 4-D TMA, tile 16 rows x 8 cols, two K blocks per tap
     (16, 64, 32, 40, 512, 1, 1, 0, 1),    # BN=256 tiles (1 CTA/SM, 256 TMEM columns)
-    (1, 64, 16, 20, 64, 3, 1, 1, 1),      # 20-wide map: no 128-pixel rectangle -> gather path with TMA filters
+    (1, 64, 16, 20, 64, 3, 1, 1, 1),      # 20-wide map: 6x20 tiles (120 of 128 MMA rows, last tile hangs over the map), split-K
+    (2, 128, 16, 20, 128, 3, 2, 1, 1),    # stride 2 onto an 8x10 map: 10-wide tiles
+    (1, 512, 16, 20, 512, 3, 1, 1, 1),    # P5 of yolov5l at batch 1: 72 K blocks over an 8-CTA cluster (DSMEM split-K reduction)
+    (1, 2048, 1, 104, 512, 1, 1, 0, 0),   # MLP fc2 shape (rows as pixels): K=2048, split-K over clusters, 2-D TMA
 ]
 
 

@@ -57,7 +57,8 @@ def test_operator_modules_vs_oracle(cuda_device):
 
 def test_batch_independence(cuda_device):
     """Size-independent property at full 512x640 size: each pair's result does not depend on its batch neighbours
-    (what makes batch-dim sharding across GPUs exact)."""
+    (what makes batch-dim sharding across GPUs valid).  Equality is up to fp32 summation order only: the split-K factor
+    of the small deep layers is chosen from the grid size, i.e. from the batch."""
     from icafusion_b200 import Model
     model = Model("yolov5s_Transfusion_kaist").eval()
     load_synth(model, 3)
@@ -67,4 +68,8 @@ def test_batch_independence(cuda_device):
     with torch.no_grad():
         z_all = model(rgb, ir)[0]
         z_1 = model(rgb[1:2], ir[1:2])[0]
-    assert torch.equal(z_all[1:2], z_1)
+    assert err(z_all[1:2], z_1) < 1e-3
+    model.__dict__["_icaf_concurrent"] = False          # same walk without the side-stream forks
+    with torch.no_grad():
+        z_seq = model(rgb[1:2], ir[1:2])[0]
+    assert torch.equal(z_seq, z_1)
