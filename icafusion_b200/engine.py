@@ -9,7 +9,7 @@ reference's ``img.half() / 255`` staging (detect_twostream.py:70-80).
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Iterable, Iterator, Optional, Tuple
 
 import torch
 
@@ -65,3 +65,56 @@ class GraphedDetector:
         self._z_host.copy_(self.z, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._z_host
+
+
+class PipelinedDetector:
+    """Streaming front end: `depth` captured replicas of the forward (shared weights, private static buffers) used round
+    robin so that the H2D copy of frame i+1 (copy stream) overlaps the forward of frame i (compute stream) and the host
+    only blocks on the oldest frame in flight.  Every frame still pays its own H2D, forward and D2H.
+
+        for z_host in PipelinedDetector(model, 1, 512, 640).infer_stream(frames):   # frames: iterable of (rgb_u8, ir_u8) host tensors
+            ...                                                                     # z_host valid until `depth` more frames are submitted
+    """
+
+    def __init__(self, model: Model, batch: int, height: int, width: int, in_dtype: torch.dtype = torch.uint8,
+                 device: Optional[torch.device] = None, depth: int = 2):
+        self.replicas = [GraphedDetector(model, batch, height, width, in_dtype, device) for _ in range(depth)]
+        self.device = self.replicas[0].device
+        self.compute = torch.cuda.Stream(self.device)
+        self.copy = torch.cuda.Stream(self.device)
+        self.launches_per_step = self.replicas[0].launches_per_step
+        for r in self.replicas:
+            r._h2d_ev = torch.cuda.Event()
+            r._done_ev = torch.cuda.Event()
+            r._done_ev.record(self.compute)
+
+    def submit(self, i: int, rgb_host: torch.Tensor, ir_host: torch.Tensor) -> None:
+        r = self.replicas[i % len(self.replicas)]
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(r._done_ev)            # replica's previous frame fully retired (inputs + z free)
+            r.rgb.copy_(rgb_host, non_blocking=True)
+            r.ir.copy_(ir_host, non_blocking=True)
+            r._h2d_ev.record(self.copy)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(r._h2d_ev)
+            r.graph.replay()
+            r._z_host.copy_(r.z, non_blocking=True)
+            r._done_ev.record(self.compute)
+
+    def collect(self, i: int) -> torch.Tensor:
+        r = self.replicas[i % len(self.replicas)]
+        r._done_ev.synchronize()
+        return r._z_host
+
+    def infer_stream(self, frames: Iterable[Tuple[torch.Tensor, torch.Tensor]]) -> Iterator[torch.Tensor]:
+        depth = len(self.replicas)
+        submitted = collected = 0
+        for rgb, ir in frames:
+            if submitted - collected >= depth:          # oldest frame in flight; retiring it frees its replica
+                yield self.collect(collected)
+                collected += 1
+            self.submit(submitted, rgb, ir)
+            submitted += 1
+        while collected < submitted:
+            yield self.collect(collected)
+            collected += 1

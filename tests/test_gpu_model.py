@@ -73,3 +73,26 @@ def test_batch_independence(cuda_device):
     with torch.no_grad():
         z_seq = model(rgb[1:2], ir[1:2])[0]
     assert torch.equal(z_seq, z_1)
+
+
+def test_graph_engines_match_eager(cuda_device):
+    """CUDA-graph replay (GraphedDetector) and the depth-2 streaming front end (PipelinedDetector) return exactly what the
+    eager forward returns, frame after frame, from host uint8 frames."""
+    from icafusion_b200 import Model
+    from icafusion_b200.engine import GraphedDetector, PipelinedDetector
+    model = Model("yolov5s_Transfusion_kaist").eval()
+    load_synth(model, 5)
+    model = model.fuse().half().to(cuda_device)
+    frames = []
+    for sd in range(5):
+        a, b = synth.synth_images(1, 320, 320, 100 + sd)
+        frames.append(((a * 255).to(torch.uint8).pin_memory(), (b * 255).to(torch.uint8).pin_memory()))
+    with torch.no_grad():
+        want = [model(a.to(cuda_device), b.to(cuda_device))[0].cpu() for a, b in frames]
+    eng = GraphedDetector(model, 1, 320, 320, in_dtype=torch.uint8, device=cuda_device)
+    for (a, b), w in zip(frames, want):
+        assert torch.equal(eng.infer_to_host(a, b).clone(), w)
+    pipe = PipelinedDetector(model, 1, 320, 320, device=cuda_device, depth=2)
+    got = [z.clone() for z in pipe.infer_stream(frames)]
+    assert len(got) == len(want) and all(torch.equal(g, w) for g, w in zip(got, want))
+    assert eng.launches_per_step > 50
