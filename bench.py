@@ -28,6 +28,10 @@ import sys
 import threading
 import time
 
+# NCCL's version / debug banner goes to stdout by default; stdout of this script carries exactly one JSON line.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

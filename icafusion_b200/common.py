@@ -395,7 +395,9 @@ class CrossTransformerBlock(nn.Module):
             # fused [Q|K] projections, both modalities in one launch   common.py:661-662,666-667
             qk_v, qk_i = ops.linear([rn, inn], [P["qk_vis"], P["qk_ir"]])
             # V^T = Wv . LN(x)^T (swap-AB: the token matrix is the "filter")   common.py:663,668
-            tok_as_w = [PackedConv(t, None, C, rows, 1, 1, 1, 0, ACT_NONE) for t in (rn, inn)]
+            tok_as_w = [PackedConv(t, None, C, rows, 1, 1, 1, 0, ACT_NONE, is_weight=False) for t in (rn, inn)]
+            ops.note_weight(P, "wv_vis")
+            ops.note_weight(P, "wv_ir")
             for t, b in zip(tok_as_w, (P["bv_vis"], P["bv_ir"])):
                 t.bias = b
             vt_v, vt_i = ops.linear([P["wv_vis"], P["wv_ir"]], tok_as_w, bias_row=True)

@@ -189,14 +189,27 @@ __global__ void dmff_pool_tokens_kernel(const PoolTokParams P) {
   float sum[8], mx[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sum[e] = 0.f; mx[e] = -INFINITY; }
-  for (int ky = 0; ky < P.kh; ++ky)
-    for (int kx = 0; kx < P.kw; ++kx) {
-      int yy = ty * P.sh + ky, xx = tx * P.sw + kx;
-      float f[8];
-      unpack8(ldg16(x + ((long long)(b * P.H + yy) * P.W + xx) * P.x_ld + c * 8), f);
+  // window elements are fetched 8 at a time (independent 16-byte loads in flight) before they are reduced
+  const __half* x0 = x + ((long long)(b * P.H + ty * P.sh) * P.W + tx * P.sw) * P.x_ld + c * 8;
+  const int wn = P.kh * P.kw;
+  for (int w0 = 0; w0 < wn; w0 += 8) {
+    uint4 v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { sum[e] += f[e]; mx[e] = fmaxf(mx[e], f[e]); }
+    for (int j = 0; j < 8; ++j) {
+      int w = w0 + j;
+      int ky = w / P.kw, kx = w - ky * P.kw;
+      if (w < wn) v[j] = ldg16(x0 + ((long long)ky * P.W + kx) * P.x_ld);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (w0 + j < wn) {
+        float f[8];
+        unpack8(v[j], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sum[e] += f[e]; mx[e] = fmaxf(mx[e], f[e]); }
+      }
+    }
+  }
   const float w1 = P.mix[mod * 2], w2 = P.mix[mod * 2 + 1];
   const float inv = 1.f / float(P.kh * P.kw);
   float pe[8], o[8];
@@ -353,6 +366,13 @@ __global__ void detect_decode_kernel(const DetectParams P) {
   }
 }
 
+__global__ void prefetch_l2_kernel(const char* __restrict__ p, size_t bytes) {
+  pdl_launch_dependents();          // no pdl_wait: the region holds parameters, no kernel writes it
+  size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 128;
+  const size_t stride = size_t(gridDim.x) * blockDim.x * 128;
+  for (; i < bytes; i += stride) prefetch_l2(p + i);
+}
+
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace icaf
@@ -391,6 +411,15 @@ extern "C" int icaf_upsample2x(const void* x, int64_t x_ld, void* y, int64_t y_l
   long long total = (long long)B * 4 * H * W * (C / 8);
   launch_k(upsample2x_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, x_ld, (__half*)y, y_ld, B, H, W, C / 8);
   return check_launch("upsample2x");
+}
+
+extern "C" int icaf_prefetch_l2(const void* ptr, size_t bytes, void* stream) {
+  if (!ptr || bytes == 0) return set_error(ICAF_ERR_BAD_ARG, "prefetch_l2: bad argument");
+  size_t lines = (bytes + 127) / 128;
+  unsigned blocks = (unsigned)((lines + 255) / 256);
+  if (blocks > 148u * 8u) blocks = 148u * 8u;
+  launch_k(prefetch_l2_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const char*)ptr, bytes);
+  return check_launch("prefetch_l2");
 }
 
 extern "C" int icaf_copy_channels(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t pixels, int C, void* stream) {

@@ -53,6 +53,61 @@ class profile:
         return out
 
 
+_WEIGHT_TRACE = None   # when a list: (container, key) of every weight tensor a forward consumes
+
+
+def note_weight(container, key) -> None:
+    if _WEIGHT_TRACE is not None:
+        _WEIGHT_TRACE.append((container, key))
+
+
+class trace_weights:
+    """Context manager: record which packed weight tensors a forward touches (for consolidate_weights)."""
+
+    def __enter__(self):
+        global _WEIGHT_TRACE
+        self.items = []
+        _WEIGHT_TRACE = self.items
+        return self
+
+    def __exit__(self, *a):
+        global _WEIGHT_TRACE
+        _WEIGHT_TRACE = None
+
+
+def consolidate_weights(items):
+    """Move every traced weight tensor into one contiguous fp16 arena (in use order) and rebind its owner to the arena
+    view; returns the arena.  One arena = one L2 prefetch per step and sequential DRAM pages for the filter stream."""
+    seen, uniq = set(), []
+    for cont, key in items:
+        k = (id(cont), key)
+        if k not in seen:
+            seen.add(k)
+            uniq.append((cont, key))
+    def get(cont, key):
+        return cont[key] if isinstance(cont, dict) else getattr(cont, key)
+    sizes = [round_up(get(c, k).numel(), 128) for c, k in uniq]
+    dev = get(*uniq[0]).device
+    arena = torch.zeros(sum(sizes), dtype=torch.float16, device=dev)
+    off = 0
+    for (cont, key), sz in zip(uniq, sizes):
+        t = get(cont, key)
+        assert t.dtype == torch.float16 and t.is_contiguous()
+        view = arena[off:off + t.numel()].view(t.shape)
+        view.copy_(t)
+        if isinstance(cont, dict):
+            cont[key] = view
+        else:
+            setattr(cont, key, view)
+        off += sz
+    return arena
+
+
+def prefetch_l2(t: torch.Tensor) -> None:
+    _call("icaf_prefetch_l2", _lib.lib().icaf_prefetch_l2, (_ptr(t), t.numel() * t.element_size()),
+          {"bytes": float(t.numel() * t.element_size())})
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -101,6 +156,7 @@ class PackedConv:
     stride: int
     pad: int
     act: int
+    is_weight: bool = True            # False when the "filter" operand is an activation (swap-AB linears)
 
 
 def pack_conv_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, pad: int, act: int,
@@ -153,6 +209,8 @@ def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Option
     ios = (_lib.ConvIO * n)()
     for i in range(n):
         pk = packs[i]
+        if pk.is_weight:
+            note_weight(pk, "w")
         if (pk.cin, pk.cout, pk.kh, pk.kw, pk.stride, pk.pad, pk.act) != (p0.cin, p0.cout, p0.kh, p0.kw, p0.stride, p0.pad, p0.act) \
                 or tuple(xs[i].shape) != tuple(xs[0].shape):
             raise ValueError("conv2d: grouped problems must share one geometry")

@@ -95,6 +95,10 @@ int icaf_sppf_pool(const void* x, int64_t x_ld, void* y1, void* y2, void* y3, in
 /* nn.Upsample(None, 2, 'nearest') (yolov5l_Transfusion_kaist.yaml:48,53) into a channel slice. */
 int icaf_upsample2x(const void* x, int64_t x_ld, void* y, int64_t y_ld, int B, int H, int W, int C, void* stream);
 
+/* Pull a read-only region (packed filters) into L2 ahead of its consumers: after an L2 flush every layer would
+ * otherwise pay a DRAM round trip for its first filter tile.  Touches no data; purely a cache hint. */
+int icaf_prefetch_l2(const void* ptr, size_t bytes, void* stream);
+
 /* Copy a channel slice (Concat, models/common.py:313-321, when producer-side slice writes are not possible). */
 int icaf_copy_channels(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t pixels, int C, void* stream);
 
