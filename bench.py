@@ -258,12 +258,15 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
         model(eng.rgb, eng.ir)
         torch.cuda.synchronize()
         reps = 3
+        model.__dict__["_icaf_concurrent"] = False          # one stream: every launch is timed against its predecessor
         with ops.profile() as prof:
             for _ in range(reps):
                 flush.zero_()
-                torch.cuda._sleep(int(6e6))
+                torch.cuda._sleep(int(8e6))
+                prof.mark()
                 model(eng.rgb, eng.ir)
                 torch.cuda.synchronize()
+        model.__dict__["_icaf_concurrent"] = True
     summ = prof.summary()
     if primary and args.layer_profile:           # per-launch table of the last profiled step (geometry, us, TFLOP/s, GB/s)
         pl = prof.per_launch()

@@ -1,0 +1,101 @@
+// Shared pieces of the implicit-GEMM conv kernels (one-tile-per-CTA kernel in conv_gemm.cu, persistent kernel in
+// conv_persist.cu): problem descriptors, TMA descriptor bundle, epilogue chunk.
+#pragma once
+#include "icaf_internal.cuh"
+
+namespace icaf {
+
+constexpr int BM = 128;
+constexpr int BK = 64;              // 64 halfs = one 128-byte swizzle atom row
+constexpr int kLag = 2;             // cp.async groups kept in flight per gather thread
+constexpr int kThreads = 192;
+
+enum AMode { A_GATHER = 0, A_TMA2D = 1, A_TMA4D = 2 };
+
+struct ConvProblem {
+  const __half* x; const float* bias; const __half* res; __half* y;
+  const float* alpha; const float* beta;
+  long long x_ld, res_ld, y_ld;
+};
+struct ConvParams {
+  ConvProblem p[2];
+  int M, N, K, k_pad;
+  int B, Hi, Wi, Cin, Ho, Wo, kh, kw, stride, pad;
+  int act, epi;
+  int a_mode, tw, th, tiles_x, tiles_y;   // A_TMA4D: tile = th x tw output pixels (tw*th <= 128), tiles per image
+  int stages;                             // smem ring depth (runtime: deep rings for small grids, 2 CTAs/SM otherwise)
+  int splits;                             // split-K factor = cluster size along x (1 = no cluster); partial sums meet in DSMEM
+};
+struct ConvMaps {          // TMA descriptors, passed by value as a __grid_constant__ kernel parameter
+  CUtensorMap w[2];
+  CUtensorMap a[2];
+};
+
+__device__ __forceinline__ ConvProblem pick_problem(const ConvParams& P, unsigned z) {
+  ConvProblem r;
+  r.x = z ? P.p[1].x : P.p[0].x;          r.bias = z ? P.p[1].bias : P.p[0].bias;
+  r.res = z ? P.p[1].res : P.p[0].res;    r.y = z ? P.p[1].y : P.p[0].y;
+  r.alpha = z ? P.p[1].alpha : P.p[0].alpha; r.beta = z ? P.p[1].beta : P.p[0].beta;
+  r.x_ld = z ? P.p[1].x_ld : P.p[0].x_ld; r.res_ld = z ? P.p[1].res_ld : P.p[0].res_ld;
+  r.y_ld = z ? P.p[1].y_ld : P.p[0].y_ld;
+  return r;
+}
+
+// One 32-column chunk of one output row: + bias, activation, residual, fp16 store.
+// ACT: 0 none, 1 SiLU, 2 GELU(erf).  RES: 0 none, 1 y = act(v) + res, 2 y = alpha*res + beta*v.
+template <int ACT, int RES>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float* __restrict__ sb, float rbias,
+                                          float alpha, float beta, const __half* __restrict__ rp,
+                                          __half* __restrict__ yp, bool vec, int ncols) {
+  auto f = [&](int j) {
+    float t = __uint_as_float(acc[j]) + sb[j] + rbias;
+    if (ACT == ICAF_ACT_SILU) t = silu_f(t);
+    if (ACT == ICAF_ACT_GELU) t = gelu_erf_f(t);
+    return t;
+  };
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = f(q * 8 + e);
+      if (RES != 0) {
+        uint4 rr = *reinterpret_cast<const uint4*>(rp + q * 8);
+        const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 rf = __half22float2(rh[e]);
+          if (RES == 2) {
+            v[2 * e] = alpha * rf.x + beta * v[2 * e];
+            v[2 * e + 1] = alpha * rf.y + beta * v[2 * e + 1];
+          } else {
+            v[2 * e] += rf.x;
+            v[2 * e + 1] += rf.y;
+          }
+        }
+      }
+      uint4 o;
+      o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
+      o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(yp + q * 8) = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) {
+        float t = f(j);
+        if (RES != 0) {
+          float rf = __half2float(rp[j]);
+          t = RES == 2 ? alpha * rf + beta * t : t + rf;
+        }
+        yp[j] = __float2half_rn(t);
+      }
+    }
+  }
+}
+
+// persistent kernel (conv_persist.cu)
+template <int BN>
+int launch_persist(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
+
+}  // namespace icaf

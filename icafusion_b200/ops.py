@@ -25,18 +25,25 @@ def launch_count() -> int:
 
 
 class profile:
-    """Context manager: bracket every libicaf_b200 launch with CUDA events on its stream.
-    `with ops.profile() as recs: ...; torch.cuda.synchronize(); recs.summary()`"""
+    """Context manager: time every libicaf_b200 launch with CUDA events on its stream.  One event is recorded after
+    each launch; a launch's duration is the gap to the previous event (so with the launches queued back to back it is
+    kernel time + inter-kernel gap).  Use on a single stream: `with ops.profile() as p: ...; torch.cuda.synchronize()`."""
 
     def __enter__(self):
         global _PROFILE
         self.records = []
-        _PROFILE = self.records
+        _PROFILE = self
+        self.last = None
         return self
 
     def __exit__(self, *a):
         global _PROFILE
         _PROFILE = None
+
+    def mark(self):
+        """Start a new timing chain (call after queueing work that must not be attributed to the next launch)."""
+        self.last = torch.cuda.Event(enable_timing=True)
+        self.last.record()
 
     def per_launch(self):
         """[(name, tag, ms, flops, bytes)] in launch order (call after a device synchronize)."""
@@ -116,11 +123,13 @@ def _call(name: str, fn, args, work=None):
     """Invoke one C-ABI kernel launcher on the current stream (optionally event-bracketed)."""
     global _LAUNCHES
     if _PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        if _PROFILE.last is None:
+            _PROFILE.mark()
         rc = fn(*args, _stream())
+        e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        _PROFILE.append((name, work or {}, e0, e1))
+        _PROFILE.records.append((name, work or {}, _PROFILE.last, e1))
+        _PROFILE.last = e1
     else:
         rc = fn(*args, _stream())
     _lib.check(rc, name)

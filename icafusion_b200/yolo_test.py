@@ -318,7 +318,7 @@ class Model(nn.Module):
             return cats[ci][..., off:off + self._layer_ch[m.i]]
 
         arena = self.__dict__.get("_icaf_arena")
-        if arena is not None and arena.numel() * 2 <= (96 << 20):
+        if concurrent and arena is not None and arena.numel() * 2 <= (96 << 20):
             # the whole packed filter set fits the 126 MB L2: stream it in once, concurrently with the first layers
             st = fork()
             with torch.cuda.stream(st):

@@ -47,6 +47,10 @@ CASES = [
     (2, 128, 16, 20, 128, 3, 2, 1, 1),    # stride 2 onto an 8x10 map: 10-wide tiles
     (1, 512, 16, 20, 512, 3, 1, 1, 1),    # P5 of yolov5l at batch 1: 72 K blocks over an 8-CTA cluster (DSMEM split-K reduction)
     (1, 2048, 1, 104, 512, 1, 1, 0, 0),   # MLP fc2 shape (rows as pixels): K=2048, split-K over clusters, 2-D TMA
+    (8, 64, 64, 80, 64, 3, 1, 1, 1),      # 320 tiles -> persistent kernel, 4-D TMA, BN=64
+    (8, 3, 128, 160, 32, 6, 2, 2, 1),     # 320 tiles -> persistent kernel, cp.async gather (image stem), BN=32
+    (4, 128, 64, 80, 256, 3, 2, 1, 1),    # persistent, 4-D TMA stride 2, BN=128, 18 K blocks per tile
+    (3, 64, 100, 84, 96, 1, 1, 0, 2),     # persistent, 2-D TMA, ragged M (25200 rows) and N (96), GELU
 ]
 
 
@@ -86,6 +90,24 @@ def test_grouped_residual_and_slices(cuda_device):
     for i in range(2):
         assert err(nchw(outs[i]), refs[i]) < TOL
         assert float(xs[i][..., :C].abs().max()) == 0 and float(xs[i][..., 2 * C:].abs().max()) == 0   # neighbours untouched
+
+
+def test_persistent_grouped_residual(cuda_device):
+    """Persistent kernel with two problems per launch, fused residual and channel-slice output (640 tiles)."""
+    from icafusion_b200 import ops
+    B, C, H, W = 8, 64, 64, 80
+    packs, xin, ress, outs, refs = [], [], [], [], []
+    for i in range(2):
+        x, w, b = _mk(B, C, H, W, C, 3, 1, 1, seed=20 + i)
+        res = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(30 + i)).half()
+        wide = torch.zeros(B, H, W, 2 * C, dtype=torch.float16, device=cuda_device)
+        xin.append(nhwc(x).to(cuda_device)); ress.append(nhwc(res).to(cuda_device)); outs.append(wide[..., C:])
+        packs.append(ops.pack_conv_weight(w.float(), b, 1, 1, 1, device=cuda_device))
+        refs.append(_ref(x, w, b, 1, 1, 1) + res.float())
+    ops.conv2d(xin, packs, outs, ress)
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert err(nchw(outs[i]), refs[i]) < TOL
 
 
 def test_linear_epilogues(cuda_device):
