@@ -319,6 +319,28 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
     return out
 
 
+def dmff_block_metrics(dev):
+    """Second half of the BASELINE metric: DMFF-block GFLOP/s vs roofline on BASELINE configs[0]'s block
+    (C=256, 32x40 map, batch 1, fp16), as shipped (pooled to 16x16 tokens) and un-pooled (1280 tokens)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from dmff_sweep import peaks, time_block
+    from oracle import icaf_oracle as O
+    tf_peak, hbm = peaks()
+    out = {}
+    for name, (va, ha) in (("pooled_16x16", (16, 16)), ("unpooled_32x40", (32, 40))):
+        C, H, W, B = 256, 32, 40, 1
+        ms = time_block(C, H, W, va, ha, 1, B, dev)
+        F = O.dmff_flops(B, C, H, W, va * ha, 1)
+        by = 2.0 * (3 * B * C * H * W + 2 * va * ha * C + 26 * C * C)
+        t_bound = max(F / (tf_peak * 1e12), by / (hbm * 1e9))
+        out[name] = {"ms": round(ms, 4), "gflops": round(F / ms / 1e6, 1), "algorithmic_gflop": round(F / 1e9, 3),
+                     "frac_of_roofline": round(t_bound / (ms * 1e-3), 4),
+                     "bound": "tensor" if F / (tf_peak * 1e12) > by / (hbm * 1e9) else "hbm"}
+    out["note"] = ("TransformerFusionBlock(256) on 1x256x32x40 RGB+IR maps, CUDA-graph replay, L2 flushed; roofline time = "
+                   "max(F/peak_tensor, ideal_bytes/peak_hbm); latency-bound at batch 1 (13 kernels)")
+    return out
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -340,11 +362,14 @@ def run_ours(args, wl):
         sec = _measure(args, WORKLOADS[sec_name], max(5, min(K, 20)), 3, dev, world, rank, local, primary=False)
     if rank == 0:
         cb = cpu_reference_throughput(wl, budget_s=20.0)
+        dm = dmff_block_metrics(dev) if world == 1 else None
         line = {"metric": METRIC, "value": m["value"], "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16", "data": "synthetic", "config": m["config"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"],
                 "model_tflops": m["model_tflops"], "wall_s_timed_region": m["wall_s_timed_region"], "clocks": m["clocks"],
                 "roofline": m["roofline"], "cpu_baseline": cb}
+        if dm is not None:
+            line["dmff_block"] = dm
         if sec is not None:
             line["secondary"] = {"note": "same detector path at BASELINE configs[2] (compute-bound regime of the same kernels)",
                                  "metric": METRIC, "unit": "pairs/s", **{k: sec[k] for k in

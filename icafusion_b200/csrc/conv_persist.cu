@@ -229,6 +229,9 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
     const int c8 = pt & 7;            // 16-byte chunk within the 128-byte K row
     const int r0 = pt >> 3;           // rows r0 + 16*i
     const uint32_t sw = uint32_t(c8 ^ (r0 & 7)) << 4;
+    // cp.async groups kept in flight per thread: the gather is latency-bound (one L2 round trip per K block), so the
+    // deeper the better, bounded by the ring depth of this tile width
+    constexpr int kGLag = BN <= 64 ? 6 : (BN == 128 ? 4 : 2);
     int s = 0, s_done = 0, pending = 0;
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -267,8 +270,8 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         }
         cp_async_commit();
         if (++s == kStages) { s = 0; ph ^= 1; }
-        if (++pending > kLag) {           // hand the oldest in-flight stage to the MMA warp
-          cp_async_wait<kLag>();
+        if (++pending > kGLag) {          // hand the oldest in-flight stage to the MMA warp
+          cp_async_wait<kGLag>();
           fence_proxy_async_smem();
           mbar_arrive(full_bar(s_done));
           if (++s_done == kStages) s_done = 0;
