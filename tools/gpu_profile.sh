@@ -6,7 +6,7 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_ten
 for wl in yolov5s_b1 yolov5l_b16; do
   ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/step_$wl.csv python tools/profile_step.py --workload $wl --steps 2 > gpurun_out/ncu_step_$wl.log 2>&1; tail -n 1 gpurun_out/ncu_step_$wl.log
 done
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_gemm_tc -s 34 -c 5 -o gpurun_out/full_conv_l_b16 python tools/profile_step.py --workload yolov5l_b16 --steps 2 > gpurun_out/ncu_full_l.log 2>&1; tail -n 1 gpurun_out/ncu_full_l.log
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_gemm_tc -s 18 -c 4 -o gpurun_out/full_conv_s_b1 python tools/profile_step.py --workload yolov5s_b1 --steps 2 > gpurun_out/ncu_full_s.log 2>&1; tail -n 1 gpurun_out/ncu_full_s.log
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_gemm_ -s 34 -c 5 -o gpurun_out/full_conv_l_b16 python tools/profile_step.py --workload yolov5l_b16 --steps 2 > gpurun_out/ncu_full_l.log 2>&1; tail -n 1 gpurun_out/ncu_full_l.log
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_gemm_ -s 18 -c 4 -o gpurun_out/full_conv_s_b1 python tools/profile_step.py --workload yolov5s_b1 --steps 2 > gpurun_out/ncu_full_s.log 2>&1; tail -n 1 gpurun_out/ncu_full_s.log
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:cross_attn_tc -c 3 -o gpurun_out/full_attn_l_b16 python tools/profile_step.py --workload yolov5l_b16 --steps 2 > gpurun_out/ncu_full_a.log 2>&1; tail -n 1 gpurun_out/ncu_full_a.log
 ls -la gpurun_out | head -40; du -sh gpurun_out

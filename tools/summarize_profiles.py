@@ -60,7 +60,7 @@ def step_summary(wl):
         md.append(f"| {i} | `{x['kernel']}` | {x['grid']} | {x['us']:.1f} | {x.get('rd', 0) / 1e6:.2f} | {x.get('wr', 0) / 1e6:.2f} | "
                   f"{x.get('tensor_pct', 0):.1f} | {x.get('sm_pct', 0):.1f} |")
     open(os.path.join(OUT, f"{tag}_step_{wl}.md"), "w").write("\n".join(md) + "\n")
-    conv = [x for x in L if "conv_gemm_tc" in x["kernel"]]
+    conv = [x for x in L if "conv_gemm_" in x["kernel"]]
     return {"launches": len(L), "sum_us": tot, "conv_launches": len(conv), "conv_us": sum(x["us"] for x in conv),
             "conv_dram_bytes_per_launch": sum(x.get("rd", 0) + x.get("wr", 0) for x in conv) / max(1, len(conv)),
             "conv_dram_bytes_per_step": sum(x.get("rd", 0) + x.get("wr", 0) for x in conv)}
