@@ -256,27 +256,26 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
       }
     }
   } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer (one thread runs the whole loop)
-    if (lane_id() == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      const uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61) | (uint64_t(1) << 16);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t sa = smem_base + s * L::kStageBytes;
-        const uint64_t ad = desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
-        const uint64_t bd = desc_hi | uint64_t(((sa + L::kABytes) & 0x3FFFF) >> 4);
+        const uint64_t ad = umma_desc_sw128(sa);
+        const uint64_t bd = umma_desc_sw128(sa + L::kABytes);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
           umma_f16_ss(tmem_d, ad + uint64_t(2 * k), bd + uint64_t(2 * k), idesc, (kb | k) != 0);
         umma_commit(empty_bar(s));
         if (kb == nkb - 1) umma_commit(accum_bar);
-        if (++s == kStages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == kStages) { s = 0; ph ^= 1; }
     }
-    __syncwarp();
     if (splits > 1) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
   } else {
     // ------------------------------------------------------------------ TMA producer (warp 5, one thread)
