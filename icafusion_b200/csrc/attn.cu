@@ -9,6 +9,7 @@
 // Layouts (see include/icaf_b200.h): qk (B, Npad, 2C) = [q | k] rows; vt (C, B*Npad) = V^T; out (B, Npad, C).
 // CTA = (128-query tile, batch*head, direction); 160 threads: warps 0-3 gather + softmax, warp 4 MMA issuer.
 #include <cmath>
+#include <cstdlib>
 
 #include "icaf_internal.cuh"
 
@@ -255,6 +256,251 @@ __global__ void __launch_bounds__(160, 1) cross_attn_tc_kernel(const AttnParams 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Software-pipelined variant for head dims <= 64 (everything in yolov5s, P3/P4 of yolov5l, the whole DMFF sweep):
+// S, P and O are double-buffered (TMEM: S0|S1|O0|O1 = 512 columns; smem: two P tiles), so
+//   * the tensor core computes S(j+1) = Q K(j+1)^T while the softmax threads are still reducing S(j), and
+//   * the threads fold O(j-1) = P(j-1) V(j-1) into their registers only after they have handed P(j) to the tensor
+//     core, i.e. the PV MMA latency is hidden behind the next tile's softmax.
+// exp2 goes through MUFU.EX2 directly (ex2.approx.ftz).
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+struct AttnSmemP {
+  static constexpr int kQBytes = kQT * 128;
+  static constexpr int kKBytes = kKV * 128;             // per buffer (one 64-wide K block, D <= 64)
+  static constexpr int kVBytes = 2 * D * 128;
+  static constexpr int kVStride = (kVBytes + 1023) / 1024 * 1024;
+  static constexpr int kPBytes = 2 * kQT * 128;         // per buffer
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = kQOff + kQBytes;
+  static constexpr int kVOff = kKOff + 2 * kKBytes;
+  static constexpr int kPOff = kVOff + 2 * kVStride;
+  static constexpr int kBarOff = kPOff + 2 * kPBytes;
+  static constexpr int kTotal = kBarOff + 128 + 1024;
+};
+
+template <int D>
+__global__ void __launch_bounds__(160, 1) cross_attn_pipe_kernel(const AttnParams P) {
+  static_assert(D <= 64, "pipelined variant: one 64-wide K block per Q/K row");
+  using L = AttnSmemP<D>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar = sbase + L::kBarOff;
+  const uint32_t q_full = bar;
+  auto s_full = [&](int i) { return bar + 8u + 8u * i; };
+  auto p_full = [&](int i) { return bar + 24u + 8u * i; };
+  auto o_full = [&](int i) { return bar + 40u + 8u * i; };
+  auto kv_full = [&](int i) { return bar + 56u + 8u * i; };
+  auto kv_empty = [&](int i) { return bar + 72u + 8u * i; };
+  const uint32_t tmem_slot = bar + 88;
+
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int dir = blockIdx.z;
+  const int b = blockIdx.y / P.heads, head = blockIdx.y % P.heads;
+  const int q0 = blockIdx.x * kQT;
+  const __half* qsrc = dir == 0 ? P.qk[1] : P.qk[0];
+  const __half* ksrc = dir == 0 ? P.qk[0] : P.qk[1];
+  const __half* vsrc = dir == 0 ? P.vt[0] : P.vt[1];
+  __half* outp = dir == 0 ? P.out[0] : P.out[1];
+  const int C = P.C, N = P.N, n_pad = P.n_pad;
+  const int nkv = (N + kKV - 1) / kKV;
+
+  if (tid == 0) {
+    mbar_init(q_full, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1); mbar_init(p_full(i), 128); mbar_init(o_full(i), 1);
+      mbar_init(kv_full(i), 128); mbar_init(kv_empty(i), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + L::kBarOff + 88);
+  auto tmem_S = [&](int i) { return tmem + uint32_t(i) * kKV; };
+  auto tmem_O = [&](int i) { return tmem + 256u + uint32_t(i) * 128u; };
+
+  if (warp < 4) {
+    constexpr int CPR = D / 8;
+    auto load_rows = [&](uint32_t dst_base, const __half* src, int row0, int col0) {
+      for (int id = tid; id < 128 * CPR; id += 128) {
+        int row = id / CPR, cc = id % CPR;
+        int n = row0 + row;
+        bool ok = n < N;
+        const __half* g = src + (size_t(b) * n_pad + (ok ? n : 0)) * (2 * C) + col0 + cc * 8;
+        cp_async16(dst_base + uint32_t(row) * 128u + (uint32_t(cc ^ (row & 7)) << 4), g, ok);
+      }
+    };
+    auto load_vt = [&](uint32_t dst_base, int kv0) {
+      for (int id = tid; id < D * 16; id += 128) {
+        int row = id >> 4, cc = id & 15;
+        int key = kv0 + cc * 8;
+        bool ok = key < n_pad;
+        const __half* g = vsrc + size_t(head * D + row) * (size_t(P.B) * n_pad) + size_t(b) * n_pad + (ok ? key : 0);
+        cp_async16(dst_base + uint32_t(cc >> 3) * uint32_t(D * 128) + uint32_t(row) * 128u + (uint32_t((cc & 7) ^ (row & 7)) << 4), g, ok);
+      }
+    };
+    load_rows(sbase + L::kQOff, qsrc, q0, head * D);
+    cp_async_arrive_on(q_full);                // asynchronous arrivals: nobody blocks on the loads
+    load_rows(sbase + L::kKOff, ksrc, 0, C + head * D);
+    load_vt(sbase + L::kVOff, 0);
+    cp_async_arrive_on(kv_full(0));
+
+    const int row = tid;
+    const int qn = q0 + row;
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 0.f;
+    float acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.f;
+
+    auto fold_o = [&](int t, float corr) {           // acc = acc*corr + O(t)
+      mbar_wait(o_full(t & 1), (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+#pragma unroll
+      for (int cb = 0; cb < D; cb += 32) {
+        __syncwarp();
+        tmem_ld32(tmem_O(t & 1) + lane_off + cb, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (cb + i < D) acc[cb + i] = acc[cb + i] * corr + __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+    };
+
+    for (int j = 0; j < nkv; ++j) {
+      const int kv0 = j * kKV, sb = j & 1;
+      if (j + 1 < nkv) {                       // prefetch tile j+1 (its buffer is free once PV(j-1) has completed)
+        const int nb = (j + 1) & 1;
+        mbar_wait(kv_empty(nb), (((j + 1) >> 1) & 1) ^ 1);
+        load_rows(sbase + L::kKOff + nb * L::kKBytes, ksrc, kv0 + kKV, C + head * D);
+        load_vt(sbase + L::kVOff + nb * L::kVStride, kv0 + kKV);
+        cp_async_arrive_on(kv_full(nb));       // lands during this tile's softmax; the MMA warp issues S(j+1) right then
+      }
+      mbar_wait(s_full(sb), (j >> 1) & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cb = 0; cb < kKV; cb += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_S(sb) + lane_off + cb, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (kv0 + cb + i < N) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = fast_exp2((m_run - m_new) * P.scale_log2);
+      const float moff = m_new * P.scale_log2;
+      float rs = 0.f;
+      uint8_t* pbuf = sgen + L::kPOff + sb * L::kPBytes;
+#pragma unroll 1
+      for (int cb = 0; cb < kKV; cb += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_S(sb) + lane_off + cb, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (kv0 + cb + i < N) ? fast_exp2(fmaf(__uint_as_float(r[i]), P.scale_log2, -moff)) : 0.f;
+          float p1 = (kv0 + cb + i + 1 < N) ? fast_exp2(fmaf(__uint_as_float(r[i + 1]), P.scale_log2, -moff)) : 0.f;
+          __half2 h = __floats2half2_rn(p0, p1);
+          float2 hf = __half22float2(h);
+          rs += hf.x + hf.y;
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint8_t* prow = pbuf + (cb >> 6) * (kQT * 128) + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int c = ((cb & 63) >> 3) + q;
+          *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full(sb));                 // P(j) handed over; S buffer sb is free for S(j+2)
+      if (j >= 1) fold_o(j - 1, corr_prev);    // PV(j-1) ran while this tile's softmax was computed
+      corr_prev = corr;
+    }
+    fold_o(nkv - 1, corr_prev);
+    if (qn < n_pad) {
+      const float inv = qn < N ? 1.f / l_run : 0.f;
+      __half* o = outp + (size_t(b) * n_pad + qn) * C + head * D;
+#pragma unroll
+      for (int i = 0; i < D; i += 8) {
+        uint4 v;
+        v.x = pack_half2(acc[i] * inv, acc[i + 1] * inv);
+        v.y = pack_half2(acc[i + 2] * inv, acc[i + 3] * inv);
+        v.z = pack_half2(acc[i + 4] * inv, acc[i + 5] * inv);
+        v.w = pack_half2(acc[i + 6] * inv, acc[i + 7] * inv);
+        *reinterpret_cast<uint4*>(o + i) = v;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_f16(kQT, kKV);
+    constexpr uint32_t idesc_o = umma_idesc_f16(kQT, D);
+    auto issue_s = [&](int t) {                // S(t) = Q K(t)^T into S buffer t&1
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          uint64_t ad = umma_desc_sw128(sbase + L::kQOff) + uint64_t(2 * k);
+          uint64_t bd = umma_desc_sw128(sbase + L::kKOff + (t & 1) * L::kKBytes) + uint64_t(2 * k);
+          umma_f16_ss(tmem_S(t & 1), ad, bd, idesc_s, k != 0);
+        }
+        umma_commit(s_full(t & 1));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(kv_full(0), 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      const int buf = j & 1;
+      if (j + 1 < nkv) {                       // next tile's scores while the softmax threads work on S(j)
+        mbar_wait(kv_full((j + 1) & 1), ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_s(j + 1);                        // S buffer (j+1)&1 was released by p_full(j-1), waited for last iteration
+      }
+      mbar_wait(p_full(buf), (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kKV / 16; ++k) {
+          uint64_t ad = umma_desc_sw128(sbase + L::kPOff + buf * L::kPBytes + (k >> 2) * (kQT * 128)) + uint64_t(2 * (k & 3));
+          uint64_t bd = umma_desc_sw128(sbase + L::kVOff + buf * L::kVStride + (k >> 2) * (D * 128)) + uint64_t(2 * (k & 3));
+          umma_f16_ss(tmem_O(buf), ad, bd, idesc_o, k != 0);
+        }
+        umma_commit(o_full(buf));
+        umma_commit(kv_empty(buf));
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // CUDA-core reference, one thread per (query, head, batch, direction). Tests only.
 __global__ void cross_attn_simt_kernel(const AttnParams P) {
   pdl_launch_dependents();
@@ -314,6 +560,20 @@ static int fill_attn(const void* qk_vis, const void* qk_ir, const void* vt_vis, 
 }
 
 template <int D>
+static int launch_attn_pipe(const AttnParams& P, cudaStream_t st) {
+  using L = AttnSmemP<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(cross_attn_pipe_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return set_cuda_error(e, "cross_attention: cudaFuncSetAttribute");
+    configured = true;
+  }
+  dim3 grid((P.n_pad + kQT - 1) / kQT, P.B * P.heads, 2);
+  launch_k(cross_attn_pipe_kernel<D>, dim3(grid), dim3(160), L::kTotal, st, P);
+  return check_launch("cross_attention");
+}
+
+template <int D>
 static int launch_attn(const AttnParams& P, cudaStream_t st) {
   using L = AttnSmem<D>;
   static bool configured = false;
@@ -337,10 +597,11 @@ extern "C" int icaf_cross_attention(const void* qk_vis, const void* qk_ir, const
   int rc = fill_attn(qk_vis, qk_ir, vt_vis, vt_ir, out_vis, out_ir, B, N, n_pad, C, heads, P);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool pipe_on = []() { const char* e = getenv("ICAF_ATTN_PIPE"); return !(e && e[0] == '0'); }();
   switch (C / heads) {
-    case 16: return launch_attn<16>(P, st);
-    case 32: return launch_attn<32>(P, st);
-    case 64: return launch_attn<64>(P, st);
+    case 16: return pipe_on ? launch_attn_pipe<16>(P, st) : launch_attn<16>(P, st);
+    case 32: return pipe_on ? launch_attn_pipe<32>(P, st) : launch_attn<32>(P, st);
+    case 64: return pipe_on ? launch_attn_pipe<64>(P, st) : launch_attn<64>(P, st);
     default: return launch_attn<128>(P, st);
   }
 }

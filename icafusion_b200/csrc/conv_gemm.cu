@@ -127,7 +127,7 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
         iy0[i] = mv ? oy * P.stride - P.pad : -100000;   // invalid rows fall out of bounds -> zero fill
         ix0[i] = ox * P.stride - P.pad;
       }
-      int s = 0, s_done = 0;          // stage being filled / next stage to hand to the MMA warp
+      int s = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1);
@@ -145,20 +145,8 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
           size_t off = ok ? (size_t(base[i] + uint32_t(iy * P.Wi + ix)) * size_t(pr.x_ld) + ch) : 0;
           cp_async16(sa + uint32_t(r0 + 16 * i) * 128u + sw, pr.x + off, ok);
         }
-        cp_async_commit();
+        cp_async_arrive_on(full_bar(s));     // asynchronous arrival when this thread's chunks have landed: no wait_group
         if (++s == kStages) { s = 0; ph ^= 1; }
-        if (kb >= kLag) {
-          cp_async_wait<kLag>();
-          fence_proxy_async_smem();
-          mbar_arrive(full_bar(s_done));
-          if (++s_done == kStages) s_done = 0;
-        }
-      }
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      for (int kb = (nkb > kLag ? nkb - kLag : 0); kb < nkb; ++kb) {
-        mbar_arrive(full_bar(s_done));
-        if (++s_done == kStages) s_done = 0;
       }
     }
 

@@ -229,10 +229,7 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
     const int c8 = pt & 7;            // 16-byte chunk within the 128-byte K row
     const int r0 = pt >> 3;           // rows r0 + 16*i
     const uint32_t sw = uint32_t(c8 ^ (r0 & 7)) << 4;
-    // cp.async groups kept in flight per thread: the gather is latency-bound (one L2 round trip per K block), so the
-    // deeper the better, bounded by the ring depth of this tile width
-    constexpr int kGLag = BN <= 64 ? 6 : (BN == 128 ? 4 : 2);
-    int s = 0, s_done = 0, pending = 0;
+    int s = 0;
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord c = tile_coord(P, t, n_tiles, m_tiles, BN);
@@ -268,22 +265,9 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
           size_t off = ok ? (size_t(base[i] + uint32_t(iy * P.Wi + ix)) * size_t(pr.x_ld) + ch) : 0;
           cp_async16(sa + uint32_t(r0 + 16 * i) * 128u + sw, pr.x + off, ok);
         }
-        cp_async_commit();
+        cp_async_arrive_on(full_bar(s));     // asynchronous arrival: the whole ring can be in flight, nobody blocks
         if (++s == kStages) { s = 0; ph ^= 1; }
-        if (++pending > kGLag) {          // hand the oldest in-flight stage to the MMA warp
-          cp_async_wait<kGLag>();
-          fence_proxy_async_smem();
-          mbar_arrive(full_bar(s_done));
-          if (++s_done == kStages) s_done = 0;
-          --pending;
-        }
       }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (; pending > 0; --pending) {
-      mbar_arrive(full_bar(s_done));
-      if (++s_done == kStages) s_done = 0;
     }
   }
   tc_fence_before();

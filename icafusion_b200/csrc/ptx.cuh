@@ -80,6 +80,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   uint32_t n = valid ? 16u : 0u;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
+// Arrive on `bar` (counts as this thread's arrival, .noinc) once every cp.async this thread has issued so far has landed.
+// Non-blocking: the producer keeps issuing; this is how CUTLASS' sm100 cp.async mainloops hand stages to tcgen05.mma.
+__device__ __forceinline__ void cp_async_arrive_on(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
