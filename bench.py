@@ -177,11 +177,9 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
     primary workload, K end-to-end steps from pinned host frames; profile the kernels of one step.  Returns a dict on rank 0."""
     import torch
     import torch.distributed as dist
-    from helpers import load_synth
-    from icafusion_b200 import Model, ops
+    from icafusion_b200 import Model, ops, synth
     from icafusion_b200.engine import GraphedDetector
-    from oracle import icaf_oracle as O
-    from oracle import synth
+    from icafusion_b200.synth import load_synth
 
     B, H, W = wl["batch"], wl["H"], wl["W"]
     model = Model(f"yolov5{wl['size']}_Transfusion_kaist").eval()
@@ -296,11 +294,11 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
                 "avg_launch_us": round(1e3 * conv["ms"] / max(1, conv["launches"]), 2),
                 "share_of_step_kernel_time": round(conv["ms"] / total_ms, 3),
                 "per_kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(summ.items())}}
-    flops_pair = O.model_conv_flops(model.yaml, H, W)
+    flops_pair = sum(v["flops"] for v in summ.values()) / reps / B     # algorithmic 2*M*N*K (+ 8*N^2*C attention) of one step
     pairs = world * B * K
     out = {"value": round(pairs / (dev_ms * 1e-3), 2), "ms_per_step": round(dev_ms / K, 4), "steps": K, "warmup": Wm,
            "config": {"workload": wl["desc"], "pairs_per_gpu_per_step": B, "gflop_per_pair": round(flops_pair / 1e9, 2),
-                      "weights": "seeded synthetic (oracle/synth.py), BN folded (Model.fuse())",
+                      "weights": "seeded synthetic (icafusion_b200/synth.py), BN folded (Model.fuse())",
                       "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
                       "execution": "CUDA graph replay of libicaf_b200 kernels (programmatic dependent launch)",
                       "parallelism": f"dp{world} (batch-sharded replicas, no collective)"},
@@ -323,14 +321,13 @@ def dmff_block_metrics(dev):
     """Second half of the BASELINE metric: DMFF-block GFLOP/s vs roofline on BASELINE configs[0]'s block
     (C=256, 32x40 map, batch 1, fp16), as shipped (pooled to 16x16 tokens) and un-pooled (1280 tokens)."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    from dmff_sweep import peaks, time_block
-    from oracle import icaf_oracle as O
+    from dmff_sweep import dmff_flops, peaks, time_block
     tf_peak, hbm = peaks()
     out = {}
     for name, (va, ha) in (("pooled_16x16", (16, 16)), ("unpooled_32x40", (32, 40))):
         C, H, W, B = 256, 32, 40, 1
         ms = time_block(C, H, W, va, ha, 1, B, dev)
-        F = O.dmff_flops(B, C, H, W, va * ha, 1)
+        F = dmff_flops(B, C, H, W, va * ha, 1)
         by = 2.0 * (3 * B * C * H * W + 2 * va * ha * C + 26 * C * C)
         t_bound = max(F / (tf_peak * 1e12), by / (hbm * 1e9))
         out[name] = {"ms": round(ms, 4), "gflops": round(F / ms / 1e6, 1), "algorithmic_gflop": round(F / 1e9, 3),

@@ -7,15 +7,7 @@ import torch
 from oracle import synth
 
 
-def load_synth(module: torch.nn.Module, seed: int, prefix: str = ""):
-    """Fill `module` with the seeded synthetic state_dict (same values gen_golden loaded into the reference)."""
-    own = module.state_dict()
-    shapes = {prefix + k: tuple(v.shape) for k, v in own.items() if not k.endswith(("anchors", "anchor_grid"))}
-    sd = synth.synth_state_dict(shapes, seed)
-    res = module.load_state_dict({k[len(prefix):]: v for k, v in sd.items()}, strict=False)
-    assert not res.unexpected_keys
-    assert all(k.endswith(("anchors", "anchor_grid")) for k in res.missing_keys), res.missing_keys
-    return sd
+from icafusion_b200.synth import load_synth  # noqa: E402,F401  (same loader the benchmark uses)
 
 
 def nhwc(x_nchw: torch.Tensor) -> torch.Tensor:

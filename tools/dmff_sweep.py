@@ -17,9 +17,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 
-from helpers import load_synth  # noqa: E402
 from icafusion_b200 import TransformerFusionBlock  # noqa: E402
-from oracle import icaf_oracle as O  # noqa: E402
+from icafusion_b200.synth import load_synth  # noqa: E402
+
+
+def dmff_flops(B, C, H, W, N, loops=1):
+    """F_dmff = B*[L*(48 N C^2 + 8 N^2 C) + 4 H W C^2]  """
+    return B * (loops * (48 * N * C * C + 8 * N * N * C) + 4 * H * W * C * C)
 
 
 def peaks():
@@ -83,7 +87,7 @@ def main():
                         if B == 16 and N >= 5120 and (C == 512 or L > 1):
                             continue                      # keeps the sweep within the GPU-minute budget
                         ms = time_block(C, H, W, va, ha, L, B, dev)
-                        F = O.dmff_flops(B, C, H, W, N, L)
+                        F = dmff_flops(B, C, H, W, N, L)
                         bytes_ideal = 2.0 * (3 * B * C * H * W + 2 * N * C + 26 * C * C)
                         t_bound = max(F / (tf_peak * 1e12), bytes_ideal / (hbm * 1e9))
                         rows.append(dict(B=B, C=C, H=H, W=W, tokens=N, mode=mode, loops=L, ms=round(ms, 4),

@@ -13,9 +13,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 from bench import WORKLOADS  # noqa: E402
-from helpers import load_synth  # noqa: E402
-from icafusion_b200 import Model  # noqa: E402
-from oracle import synth  # noqa: E402
+from icafusion_b200 import Model, synth  # noqa: E402
+from icafusion_b200.synth import load_synth  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="yolov5s_b1")
