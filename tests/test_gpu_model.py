@@ -96,3 +96,21 @@ def test_graph_engines_match_eager(cuda_device):
     got = [z.clone() for z in pipe.infer_stream(frames)]
     assert len(got) == len(want) and all(torch.equal(g, w) for g, w in zip(got, want))
     assert eng.launches_per_step > 50
+
+
+def test_letterboxed_640x640_vs_oracle(cuda_device):
+    """The reference's detect_twostream.py feeds letterboxed 640x640 frames (utils/datasets.py:1404-1444): P3 80x80 pools
+    with k=s=(4,4), P4 40x40 -> 16x16 with k=(10,10) s=(2,2), P5 20x20 with k=s=(2,2).  Checked against the CPU oracle."""
+    from icafusion_b200 import Model
+    from icafusion_b200.cfg import load_cfg
+    cfg = load_cfg("yolov5s_Transfusion_kaist")
+    model = Model(cfg).eval()
+    sd = load_synth(model, 21)
+    model = model.fuse().to(cuda_device)
+    rgb, ir = synth.synth_images(1, 640, 640, 21)
+    with torch.no_grad():
+        z = model(rgb.to(cuda_device), ir.to(cuda_device))[0]
+        zr = O.model_forward(O.fold_bn(sd), cfg, rgb, ir)[0]
+    e = err(z, zr)
+    print(f"\n[yolov5s 640x640] z {e:.2e}")
+    assert tuple(z.shape) == (1, 25200, 6) and e < TOL_MODEL
