@@ -107,13 +107,10 @@ __global__ void __launch_bounds__(160, 1) cross_attn_tc_kernel(const AttnParams 
     };
 
     load_rows(sbase + L::kQOff, qsrc, q0, head * D);                 // Q tile (q part: cols [0,C))
+    cp_async_arrive_on(q_full);                                      // asynchronous arrivals: nobody blocks on the loads
     load_rows(sbase + L::kKOff, ksrc, 0, C + head * D);              // K tile 0 (k part: cols [C,2C))
     load_vt(sbase + L::kVOff, 0);
-    cp_async_commit();
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    mbar_arrive(q_full);
-    mbar_arrive(kv_full(0));
+    cp_async_arrive_on(kv_full(0));
 
     const int row = tid;
     const int qn = q0 + row;
@@ -130,7 +127,7 @@ __global__ void __launch_bounds__(160, 1) cross_attn_tc_kernel(const AttnParams 
         mbar_wait(kv_empty(nb), (((j + 1) >> 1) & 1) ^ 1);
         load_rows(sbase + L::kKOff + nb * L::kKBytes, ksrc, kv0 + kKV, C + head * D);
         load_vt(sbase + L::kVOff + nb * L::kVStride, kv0 + kKV);
-        cp_async_commit();
+        cp_async_arrive_on(kv_full(nb));
       }
       // ---- online softmax on S (TMEM lanes = query rows) ----
       mbar_wait(s_full, j & 1);
@@ -179,11 +176,6 @@ __global__ void __launch_bounds__(160, 1) cross_attn_tc_kernel(const AttnParams 
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
-      if (j + 1 < nkv) {                       // next tile has landed by now (overlapped with the softmax)
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        mbar_arrive(kv_full((j + 1) & 1));
-      }
       // ---- O_tile = P V ; fold into the running accumulator ----
       mbar_wait(o_full, j & 1);
       tc_fence_after();
@@ -599,8 +591,10 @@ extern "C" int icaf_cross_attention(const void* qk_vis, const void* qk_ir, const
   cudaStream_t st = (cudaStream_t)stream;
   static const bool pipe_on = []() { const char* e = getenv("ICAF_ATTN_PIPE"); return !(e && e[0] == '0'); }();
   switch (C / heads) {
-    case 16: return pipe_on ? launch_attn_pipe<16>(P, st) : launch_attn<16>(P, st);
-    case 32: return pipe_on ? launch_attn_pipe<32>(P, st) : launch_attn<32>(P, st);
+    // the pipelined kernel pays off where the two MMAs are a visible share of a tile (d = 64: -28 % at 5120 tokens);
+    // at d = 16 / 32 the tile is exp-bound (4*d flop per MUFU.EX2) and the serial kernel is 4-8 % faster
+    case 16: return launch_attn<16>(P, st);
+    case 32: return launch_attn<32>(P, st);
     case 64: return pipe_on ? launch_attn_pipe<64>(P, st) : launch_attn<64>(P, st);
     default: return launch_attn<128>(P, st);
   }

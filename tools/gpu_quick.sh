@@ -1,7 +1,8 @@
 #!/bin/bash
-# Quick GPU session: parity tests + bench (primary + secondary workload) + DMFF sweep.
+# Quick GPU session: parity tests + smoke + bench (primary + secondary workload).
 mkdir -p gpurun_out
 python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 15 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2
 python bench.py --steps 200 --warmup 20 --layer-profile gpurun_out/layers_s_b1.csv > gpurun_out/bench_s_b1.json 2> gpurun_out/bench_s_b1.err; cut -c1-300 gpurun_out/bench_s_b1.json; tail -n 3 gpurun_out/bench_s_b1.err
 python bench.py --workload yolov5l_b16 --secondary none --steps 20 --warmup 5 --layer-profile gpurun_out/layers_l_b16.csv > gpurun_out/bench_l_b16.json 2> gpurun_out/bench_l_b16.err; cut -c1-300 gpurun_out/bench_l_b16.json; tail -n 3 gpurun_out/bench_l_b16.err
-python tools/dmff_sweep.py --quick --out gpurun_out/dmff_sweep.json > gpurun_out/dmff_sweep.log 2>&1; tail -n 3 gpurun_out/dmff_sweep.log
+ICAF_BRES=0 python bench.py --workload yolov5l_b16 --secondary none --steps 20 --warmup 5 > gpurun_out/bench_l_b16_nobres.json 2> gpurun_out/bench_l_b16_nobres.err; cut -c1-200 gpurun_out/bench_l_b16_nobres.json
