@@ -36,6 +36,7 @@ SIGNATURES = {
     "icaf_conv2d_fwd": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
     "icaf_conv2d_fwd_simt": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
     "icaf_pack_image": [_vp, _i, _f, _i, _i, _i, _vp, _vp],
+    "icaf_pack_image_s2d": [_vp, _i, _f, _i, _i, _i, _vp, _vp],
     "icaf_sppf_pool": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "icaf_upsample2x": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp],
     "icaf_copy_channels": [_vp, _i64, _vp, _i64, _i64, _i, _vp],

@@ -98,9 +98,27 @@ class Conv(nn.Module):
             scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
             w = w * scale.view(-1, 1, 1, 1)
             b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
-        pk = ops.pack_conv_weight(w, b, conv.stride[0], conv.padding[0], act)
+        if self.is_s2d_stem():
+            pk = ops.pack_stem_weight(w, b, act)          # 6x6/s2/p2 over the image == 3x3/s1/p1 over its space-to-depth form
+        else:
+            pk = ops.pack_conv_weight(w, b, conv.stride[0], conv.padding[0], act)
         self.__dict__["_icaf_pack"] = (key, pk)
         return pk
+
+    def is_s2d_stem(self) -> bool:
+        """The yolov5 image stem `Conv(3, c, 6, 2, 2)`: staged as a space-to-depth image (see ops.pack_stem_weight)."""
+        c = self.conv
+        return c.in_channels == 3 and c.kernel_size == (6, 6) and c.stride == (2, 2) and c.padding == (2, 2)
+
+    def stage_image(self, img: torch.Tensor) -> torch.Tensor:
+        """Planar (B,3,H,W) image -> the NHWC tensor this stem consumes (uint8 is scaled by 1/255 on the fly)."""
+        if img.dtype not in (torch.float16, torch.float32, torch.uint8):
+            img = img.float()
+        scale = 1.0 / 255.0 if img.dtype == torch.uint8 else 1.0
+        s2d = self.is_s2d_stem() and img.shape[2] % 2 == 0 and img.shape[3] % 2 == 0
+        if self.is_s2d_stem() and not s2d:
+            raise ValueError("the 6x6/s2 image stem needs even image height and width")
+        return ops.pack_image(img, scale, s2d=s2d)
 
     @staticmethod
     def run(mods: Sequence["Conv"], xs: Sequence[torch.Tensor], outs=None, res=None) -> List[torch.Tensor]:
@@ -111,8 +129,10 @@ class Conv(nn.Module):
         return ops.conv2d(list(xs), [m.packed() for m in mods], outs, res)
 
     def forward(self, x):
-        if x.shape[1] == 3 and self.conv.in_channels == 3:     # image stem: planar -> packed NHWC4
-            v = ops.pack_image(x if x.dtype in (torch.float16, torch.float32, torch.uint8) else x.float())
+        if x.shape[1] == 3 and self.conv.in_channels == 3:     # image stem: planar -> packed NHWC4 / space-to-depth
+            if not x.is_cuda:
+                raise RuntimeError("icafusion_b200 operators run on CUDA tensors only (no CPU fallback)")
+            v = self.stage_image(x)
         else:
             v = to_nhwc(x)
         return to_nchw(Conv.run([self], [v])[0])

@@ -49,6 +49,31 @@ __global__ void pack_image_kernel(const T* __restrict__ src, float scale, long l
   reinterpret_cast<uint2*>(dst)[i] = o;
 }
 
+// (B,3,H,W) planar -> (B,H/2,W/2,16) fp16 space-to-depth: one thread per output pixel (2x2 input pixels x 4 channels)
+template <typename T>
+__global__ void pack_image_s2d_kernel(const T* __restrict__ src, float scale, int B, int H, int W, __half* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int W2 = W >> 1, H2 = H >> 1;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * H2 * W2) return;
+  const int x = int(i % W2);
+  long long t = i / W2;
+  const int y = int(t % H2), b = int(t / H2);
+  const long long hw = (long long)H * W;
+  const T* s = src + (long long)b * 3 * hw + (long long)(2 * y) * W + 2 * x;
+  uint32_t o[8];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {                      // d = dy*2 + dx
+    const T* p = s + (d >> 1) * W + (d & 1);
+    o[2 * d] = pack_half2(float(p[0]) * scale, float(p[hw]) * scale);
+    o[2 * d + 1] = pack_half2(float(p[2 * hw]) * scale, 0.f);
+  }
+  uint4* out = reinterpret_cast<uint4*>(dst + i * 16);
+  out[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  out[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // SPPF: three chained 5x5/s1/p2 max pools == 5x5, 9x9, 13x13 windows clipped to the map (-inf padding)
 __global__ void sppf_pool_kernel(const __half* __restrict__ x, long long x_ld, __half* y1, __half* y2, __half* y3,
@@ -389,6 +414,17 @@ extern "C" int icaf_pack_image(const void* src, int src_dtype, float scale, int 
   else if (src_dtype == 2) launch_k(pack_image_kernel<uint8_t>, dim3(g), dim3(256), 0, st, (const uint8_t*)src, scale, npix, hw, (__half*)dst);
   else return set_error(ICAF_ERR_BAD_ARG, "pack_image: src_dtype must be 0 (fp16), 1 (fp32) or 2 (uint8)");
   return check_launch("pack_image");
+}
+
+extern "C" int icaf_pack_image_s2d(const void* src, int src_dtype, float scale, int B, int H, int W, void* dst, void* stream) {
+  if (!src || !dst || B < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return set_error(ICAF_ERR_BAD_ARG, "pack_image_s2d: H and W must be even");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned g = blocks_for((long long)B * (H / 2) * (W / 2), 256);
+  if (src_dtype == 0) launch_k(pack_image_s2d_kernel<__half>, dim3(g), dim3(256), 0, st, (const __half*)src, scale, B, H, W, (__half*)dst);
+  else if (src_dtype == 1) launch_k(pack_image_s2d_kernel<float>, dim3(g), dim3(256), 0, st, (const float*)src, scale, B, H, W, (__half*)dst);
+  else if (src_dtype == 2) launch_k(pack_image_s2d_kernel<uint8_t>, dim3(g), dim3(256), 0, st, (const uint8_t*)src, scale, B, H, W, (__half*)dst);
+  else return set_error(ICAF_ERR_BAD_ARG, "pack_image_s2d: src_dtype must be 0 (fp16), 1 (fp32) or 2 (uint8)");
+  return check_launch("pack_image_s2d");
 }
 
 extern "C" int icaf_sppf_pool(const void* x, int64_t x_ld, void* y1, void* y2, void* y3, int64_t y_ld, int B, int H,

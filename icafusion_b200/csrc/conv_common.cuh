@@ -25,6 +25,7 @@ struct ConvParams {
   int a_mode, tw, th, tiles_x, tiles_y;   // A_TMA4D: tile = th x tw output pixels (tw*th <= 128), tiles per image
   int stages;                             // smem ring depth (runtime: deep rings for small grids, 2 CTAs/SM otherwise)
   int splits;                             // split-K factor = cluster size along x (1 = no cluster); partial sums meet in DSMEM
+  int cblk;                               // A_TMA4D: channels per TMA box = min(Cin, 64); < 64 only in the persistent kernel
 };
 struct ConvMaps {          // TMA descriptors, passed by value as a __grid_constant__ kernel parameter
   CUtensorMap w[2];

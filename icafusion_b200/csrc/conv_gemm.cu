@@ -350,7 +350,7 @@ static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io
   P.M = int(M); P.N = g->Cout; P.K = g->kh * g->kw * g->Cin; P.k_pad = g->k_pad;
   P.B = g->B; P.Hi = g->Hi; P.Wi = g->Wi; P.Cin = g->Cin; P.Ho = g->Ho; P.Wo = g->Wo;
   P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad = g->pad; P.act = g->act; P.epi = g->epi;
-  P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.stages = 2; P.splits = 1;
+  P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.stages = 2; P.splits = 1; P.cblk = 64;
   for (int i = 0; i < 2; ++i) {
     const icaf_conv_io& s = io[i < n_io ? i : 0];
     bool need_res = g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES);
@@ -372,7 +372,7 @@ static void plan_a_mode(const icaf_conv_geom* g, ConvParams& P) {
     P.a_mode = A_TMA2D;
     return;
   }
-  if (g->Cin % 64 == 0 && g->stride <= 2) {
+  if ((g->Cin % 64 == 0 || g->Cin == 32 || g->Cin == 16) && g->stride <= 2) {
     // tile = th x tw output pixels of one image, tw | Wo, tw*th <= 128: maximise the fraction of useful MMA rows
     int best_tw = 0, best_th = 0;
     double best_u = 0.0;
@@ -387,6 +387,7 @@ static void plan_a_mode(const icaf_conv_geom* g, ConvParams& P) {
     }
     if (best_u >= 0.6) {
       P.a_mode = A_TMA4D; P.tw = best_tw; P.th = best_th; P.tiles_x = g->Wo / best_tw; P.tiles_y = (g->Ho + best_th - 1) / best_th;
+      P.cblk = g->Cin < 64 ? g->Cin : 64;
     }
   }
 }
@@ -470,7 +471,11 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   else if (P.N > 32 && ctas(64) >= sms) bn = 64;
   // Many tiles per SM: the persistent kernel overlaps main loop and epilogue across tiles (conv_persist.cu).
   static const bool persist_on = []() { const char* e = getenv("ICAF_PERSISTENT"); return !(e && e[0] == '0'); }();
-  if (persist_on && ctas(bn) >= 2 * sms) {
+  const bool persistent = persist_on && ctas(bn) >= 2 * sms;
+  if (P.a_mode == A_TMA4D && P.cblk < 64 && !persistent) {      // small-Cin TMA staging exists in the persistent kernel only
+    P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.cblk = 64;
+  }
+  if (persistent) {
     switch (bn) {
       case 256: return launch_persist<256>(P, w, g, n_io, st);
       case 128: return launch_persist<128>(P, w, g, n_io, st);

@@ -73,6 +73,8 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
   const int tid = threadIdx.x;
   const int nkb = P.k_pad / BK;
   const int a_mode = P.a_mode;
+  const uint32_t cblk = uint32_t(P.cblk);                 // channels per A box (64, or Cin for the small-Cin layers)
+  const uint32_t sub_bytes = uint32_t(BM) * cblk * 2u;    // one per-tap sub-tile of the stage
 
   if (tid == 0) {
     const uint32_t nfull = a_mode == A_GATHER ? 129u : 1u;
@@ -181,11 +183,21 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_base + s * L::kStageBytes;
-          const uint64_t ad = umma_desc_sw128(sa);
           const uint64_t bd = umma_desc_sw128(sa + L::kABytes);
+          if (cblk == 64) {
+            const uint64_t ad = umma_desc_sw128(sa);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16_ss(tmem_d, ad + uint64_t(2 * k), bd + uint64_t(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss(tmem_d, ad + uint64_t(2 * k), bd + uint64_t(2 * k), idesc, (kb | k) != 0);
+          } else {
+            // small-Cin staging: the K block is 64/cblk per-tap sub-tiles [128 rows][cblk] with 32B / 64B swizzle
+            const int nks = min(BK / 16, (P.K - kb * BK) / 16);
+            for (int k = 0; k < nks; ++k) {
+              const uint32_t e = uint32_t(k * 16);
+              const uint64_t ad = umma_desc_kmajor(sa + (e / cblk) * sub_bytes + (e % cblk) * 2u, cblk * 2u);
+              umma_f16_ss(tmem_d, ad, bd + uint64_t(2 * k), idesc, (kb | k) != 0);
+            }
+          }
           umma_commit(empty_bar(s));
           if (kb == nkb - 1) umma_commit(tfull_bar(buf));
         }
@@ -207,6 +219,22 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * L::kStageBytes;
+          if (a_mode == A_TMA4D && cblk < 64) {
+            // one box per filter tap inside this K block; the tail block of K = 9*Cin holds fewer taps
+            const int nsub = min(int(BK / cblk), (P.K - kb * BK) / int(cblk));
+            mbar_arrive_expect_tx(full_bar(s), L::kBBytes + uint32_t(nsub) * uint32_t(P.tw * P.th) * cblk * 2u);
+            tma_load_2d(sa + L::kABytes, mw, full_bar(s), kb * BK, c.n0);
+            for (int j = 0; j < nsub; ++j) {
+              const int k0 = kb * BK + j * int(cblk);
+              const int tap = k0 / P.Cin;
+              const int ch = k0 - tap * P.Cin;
+              const int ky = tap / P.kw, kx = tap - ky * P.kw;
+              tma_load_4d(sa + uint32_t(j) * sub_bytes, ma, full_bar(s), ch, c.ox0 * P.stride - P.pad + kx,
+                          c.oy0 * P.stride - P.pad + ky, c.tb);
+            }
+            if (++s == kStages) { s = 0; ph ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(full_bar(s), bytes);
           tma_load_2d(sa + L::kABytes, mw, full_bar(s), kb * BK, c.n0);
           if (a_mode == A_TMA2D) {
@@ -304,8 +332,8 @@ int launch_persist(ConvParams& P, const __half* const (&w)[2], const icaf_conv_g
     if (P.a_mode == A_TMA2D)
       rc = encode_tmap_2d(&maps.a[i], pr.x, (uint64_t)P.Cin, (uint64_t)P.M, (uint64_t)pr.x_ld * 2, BK, BM);
     else if (P.a_mode == A_TMA4D)
-      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, P.tw * P.stride, P.th * P.stride, P.stride,
-                            P.stride);
+      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, (uint32_t)P.cblk, P.tw * P.stride, P.th * P.stride,
+                            P.stride, P.stride);
     if (rc) return rc;
   }
   if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }

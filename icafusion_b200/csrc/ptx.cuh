@@ -144,6 +144,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
+// K-major tile whose rows are `row_bytes` (32 / 64 / 128) wide with the matching 32B / 64B / 128B swizzle: 8-row groups are
+// 8*row_bytes apart.  layout type field: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t row_bytes) {
+  const uint64_t lt = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFF) >> 4);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t((8 * row_bytes) >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= lt << 61;
+  return d;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             bool accumulate) {

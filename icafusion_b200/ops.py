@@ -255,8 +255,20 @@ def linear(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs=None, r
     return [t[0, 0] for t in o]
 
 
-def pack_image(img: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
-    """(B,3,H,W) fp16 / fp32 / uint8 planar image -> (B,H,W,4) fp16."""
+def pack_stem_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], act: int, device=None) -> "PackedConv":
+    """(Cout,3,6,6) stride-2 pad-2 stem filter (BN folded) -> the equivalent 3x3 / stride 1 / pad 1 filter over the
+    space-to-depth image (16 channels: (dy*2+dx)*4 + c), packed for the implicit-GEMM kernel.  ky = 2*ty+dy, kx = 2*tx+dx."""
+    cout, cin, kh, kw = weight.shape
+    assert (cin, kh, kw) == (3, 6, 6)
+    w = weight.detach().float()
+    w4 = torch.cat([w, w.new_zeros(cout, 1, 6, 6)], 1)                       # (n, c4, ky, kx)
+    w4 = w4.view(cout, 4, 3, 2, 3, 2)                                        # (n, c, ty, dy, tx, dx)
+    ws = w4.permute(0, 3, 5, 1, 2, 4).reshape(cout, 16, 3, 3)                # (n, (dy,dx,c), ty, tx)
+    return pack_conv_weight(ws, bias, 1, 1, act, device)
+
+
+def pack_image(img: torch.Tensor, scale: float = 1.0, s2d: bool = False) -> torch.Tensor:
+    """(B,3,H,W) fp16 / fp32 / uint8 planar image -> (B,H,W,4) fp16, or with `s2d` -> (B,H/2,W/2,16) space-to-depth."""
     if img.dim() != 4 or img.shape[1] != 3 or not img.is_cuda:
         raise ValueError(f"pack_image: expected a CUDA (B,3,H,W) tensor, got {tuple(img.shape)}")
     code = {torch.float16: 0, torch.float32: 1, torch.uint8: 2}.get(img.dtype)
@@ -264,6 +276,11 @@ def pack_image(img: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
         raise ValueError(f"pack_image: unsupported dtype {img.dtype}")
     img = img.contiguous()
     B, _, H, W = img.shape
+    if s2d:
+        out = torch.empty(B, H // 2, W // 2, 16, dtype=torch.float16, device=img.device)
+        _call("icaf_pack_image", _lib.lib().icaf_pack_image_s2d, (_ptr(img), code, float(scale), B, H, W, _ptr(out)),
+              {"bytes": float(img.numel() * img.element_size() + out.numel() * 2)})
+        return out
     out = torch.empty(B, H, W, 4, dtype=torch.float16, device=img.device)
     _call("icaf_pack_image", _lib.lib().icaf_pack_image, (_ptr(img), code, float(scale), B, H, W, _ptr(out)),
           {"bytes": float(img.numel() * img.element_size() + out.numel() * 2)})

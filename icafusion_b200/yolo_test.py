@@ -263,12 +263,14 @@ class Model(nn.Module):
             return m.run(list(v))
         raise NotImplementedError(type(m).__name__)
 
-    @staticmethod
-    def _stage(img):
+    def _stage(self, img, stem):
+        """Image staging for the stem layer `stem` (a Conv taking the 3-channel image)."""
         if img.dim() != 4 or img.shape[1] != 3:
             raise ValueError(f"expected (B,3,H,W) images, got {tuple(img.shape)}")
         if not img.is_cuda:
             raise RuntimeError("icafusion_b200 runs on CUDA tensors only (no CPU fallback)")
+        if isinstance(stem, Conv) and stem.conv.in_channels == 3:
+            return stem.stage_image(img)
         if img.dtype not in (torch.float16, torch.float32, torch.uint8):
             img = img.float()
         return ops.pack_image(img, 1.0 / 255.0 if img.dtype == torch.uint8 else 1.0)
@@ -324,7 +326,8 @@ class Model(nn.Module):
             with torch.cuda.stream(st):
                 ops.prefetch_l2(arena)
             forked[("prefetch",)] = st
-        v_rgb, v_ir = self._stage(rgb), self._stage(ir)
+        ir_first = next((m for m in layers if m.f == -4), layers[0])
+        v_rgb, v_ir = self._stage(rgb, layers[0]), self._stage(ir, ir_first)
         start = 0
         if self._ir_start is not None:
             s = self._ir_start

@@ -87,6 +87,11 @@ int icaf_conv2d_fwd_simt(const icaf_conv_geom* g, const icaf_conv_io* io, int n_
  * ------------------------------------------------------------------------------------------- */
 int icaf_pack_image(const void* src, int src_dtype, float scale, int B, int H, int W, void* dst, void* stream);
 
+/* Same staging, space-to-depth layout: dst is (B, H/2, W/2, 16) fp16 with channel (dy*2+dx)*4 + c (c = r,g,b,0).
+ * A 6x6 / stride 2 / pad 2 stem convolution over the image (yolov5 "P1/2" row of the model YAML) is then exactly a
+ * 3x3 / stride 1 / pad 1 convolution over this tensor (ky = 2*ty+dy, kx = 2*tx+dx), which runs on the TMA path. H, W even. */
+int icaf_pack_image_s2d(const void* src, int src_dtype, float scale, int B, int H, int W, void* dst, void* stream);
+
 /* SPPF's three chained MaxPool2d(5,1,2) (models/common.py:259-266): y1,y2,y3 written as channel
  * slices; x is (B,H,W,C) view. */
 int icaf_sppf_pool(const void* x, int64_t x_ld, void* y1, void* y2, void* y3, int64_t y_ld, int B, int H, int W,

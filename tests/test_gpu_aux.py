@@ -21,6 +21,17 @@ def test_pack_image(cuda_device, dtype, scale):
     assert torch.equal(out[..., :3], ref.permute(0, 2, 3, 1)) and float(out[..., 3].abs().max()) == 0
 
 
+def test_pack_image_space_to_depth(cuda_device):
+    from icafusion_b200 import ops
+    img = (torch.rand(2, 3, 12, 16) * 255).to(torch.uint8)
+    out = ops.pack_image(img.to(cuda_device), 1 / 255.0, s2d=True).cpu()
+    assert out.shape == (2, 6, 8, 16)
+    ref = (img.float() / 255.0).half()                                    # (b,c,H,W)
+    ref4 = torch.cat([ref, torch.zeros(2, 1, 12, 16, dtype=torch.float16)], 1)
+    want = ref4.view(2, 4, 6, 2, 8, 2).permute(0, 2, 4, 3, 5, 1).reshape(2, 6, 8, 16)    # channel = (dy*2+dx)*4 + c
+    assert torch.equal(out, want)
+
+
 @pytest.mark.parametrize("H,W", [(16, 20), (20, 20), (36, 40)])      # <=1024 px: smem kernel; 36x40: direct-window kernel
 def test_sppf_pool_bit_exact(cuda_device, H, W):
     from icafusion_b200 import ops

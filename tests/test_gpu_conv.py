@@ -51,6 +51,10 @@ CASES = [
     (8, 3, 128, 160, 32, 6, 2, 2, 1),     # 320 tiles -> persistent kernel, cp.async gather (image stem), BN=32
     (4, 128, 64, 80, 256, 3, 2, 1, 1),    # persistent, 4-D TMA stride 2, BN=128, 18 K blocks per tile
     (3, 64, 100, 84, 96, 1, 1, 0, 2),     # persistent, 2-D TMA, ragged M (25200 rows) and N (96), GELU
+    (8, 32, 64, 80, 64, 3, 1, 1, 1),      # persistent, small-Cin TMA staging: per-tap boxes of 32 channels, 64-byte swizzle
+    (8, 32, 128, 160, 64, 3, 2, 1, 1),    # ... stride 2 (yolov5s layer 1 geometry)
+    (8, 16, 64, 80, 32, 3, 1, 1, 1),      # ... 16 channels, 32-byte swizzle, K = 144 (tail K block holds one tap)
+    (1, 16, 16, 20, 32, 3, 1, 1, 1),      # 16 channels on a small grid: cp.async gather path
 ]
 
 
@@ -90,6 +94,21 @@ def test_grouped_residual_and_slices(cuda_device):
     for i in range(2):
         assert err(nchw(outs[i]), refs[i]) < TOL
         assert float(xs[i][..., :C].abs().max()) == 0 and float(xs[i][..., 2 * C:].abs().max()) == 0   # neighbours untouched
+
+
+@pytest.mark.parametrize("B,H,W,Cout", [(1, 64, 80, 32), (8, 256, 320, 32), (2, 128, 160, 64)])
+def test_stem_space_to_depth(cuda_device, B, H, W, Cout):
+    """Image stem Conv(3, c, 6, 2, 2) run as a 3x3/s1/p1 conv over the space-to-depth image (small grid: gather path,
+    large grid: persistent kernel with 16-channel TMA boxes) vs the plain 6x6 stride-2 convolution on the CPU."""
+    from icafusion_b200 import ops
+    x, w, b = _mk(B, 3, H, W, Cout, 6, 2, 2, seed=5)
+    pk = ops.pack_stem_weight(w.float(), b, 1, device=cuda_device)
+    assert (pk.cin, pk.kh, pk.stride, pk.pad) == (16, 3, 1, 1)
+    xv = ops.pack_image(x.to(cuda_device), s2d=True)
+    assert tuple(xv.shape) == (B, H // 2, W // 2, 16)
+    y = ops.conv2d([xv], [pk])[0]
+    torch.cuda.synchronize()
+    assert err(nchw(y), _ref(x, w, b, 2, 2, 1)) < TOL
 
 
 def test_persistent_grouped_residual(cuda_device):

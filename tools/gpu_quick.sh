@@ -5,4 +5,3 @@ python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/pytest_gpu.log 2>
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2
 python bench.py --steps 200 --warmup 20 --layer-profile gpurun_out/layers_s_b1.csv > gpurun_out/bench_s_b1.json 2> gpurun_out/bench_s_b1.err; cut -c1-300 gpurun_out/bench_s_b1.json; tail -n 3 gpurun_out/bench_s_b1.err
 python bench.py --workload yolov5l_b16 --secondary none --steps 20 --warmup 5 --layer-profile gpurun_out/layers_l_b16.csv > gpurun_out/bench_l_b16.json 2> gpurun_out/bench_l_b16.err; cut -c1-300 gpurun_out/bench_l_b16.json; tail -n 3 gpurun_out/bench_l_b16.err
-ICAF_BRES=0 python bench.py --workload yolov5l_b16 --secondary none --steps 20 --warmup 5 > gpurun_out/bench_l_b16_nobres.json 2> gpurun_out/bench_l_b16_nobres.err; cut -c1-200 gpurun_out/bench_l_b16_nobres.json
