@@ -33,6 +33,7 @@ SIGNATURES = {
     "icaf_version": [],
     "icaf_last_error": [],
     "icaf_sm_count": [],
+    "icaf_kernel_launches": [],
     "icaf_conv2d_fwd": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
     "icaf_conv2d_fwd_simt": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
     "icaf_pack_image": [_vp, _i, _f, _i, _i, _i, _vp, _vp],
@@ -67,7 +68,7 @@ def lib() -> C.CDLL:
         for name, argtypes in SIGNATURES.items():
             fn = getattr(L, name)            # AttributeError here = header/.so drift
             fn.argtypes = argtypes
-            fn.restype = C.c_char_p if name == "icaf_last_error" else C.c_int
+            fn.restype = C.c_char_p if name == "icaf_last_error" else (C.c_longlong if name == "icaf_kernel_launches" else C.c_int)
         _lib = L
     return _lib
 

@@ -1,4 +1,5 @@
 // Library-wide state of libicaf_b200: version, thread-local error string, device properties.
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -55,6 +56,17 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// 256-byte L2 promotion pulls the neighbouring 128-byte line along with every miss: right for dense rows (the neighbour
+// is the next K block or the next pixel of the same box), wrong for a channel slice of a wider buffer whose last line
+// is followed by channels this tensor does not own (ncu: 2x DRAM reads on the 64-of-128-channel C3 inputs).
+static CUtensorMapL2promotion l2_promotion(uint64_t row_bytes, uint64_t pitch_bytes) {
+  return (pitch_bytes > row_bytes && (row_bytes % 256) != 0) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
+
 int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
                    uint32_t box_inner, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
@@ -64,7 +76,7 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(inner * 2, row_pitch_bytes),
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[160];
@@ -86,7 +98,7 @@ int encode_tmap_nhwc(CUtensorMap* out, const void* base, int C, int W, int H, in
   // rows of the staged tile are box_c*2 bytes wide; the swizzle span equals the row (32 / 64 / 128 B)
   const CUtensorMapSwizzle swz = box_c >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2_promotion(uint64_t(C) * 2, uint64_t(ld) * 2),
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[200];
@@ -101,6 +113,7 @@ int encode_tmap_nhwc(CUtensorMap* out, const void* base, int C, int W, int H, in
 
 extern "C" int icaf_version(void) { return 100; }   // 0.1.0
 extern "C" const char* icaf_last_error(void) { return icaf::g_err; }
+extern "C" long long icaf_kernel_launches(void) { return icaf::launches_so_far(); }
 extern "C" int icaf_sm_count(void) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;

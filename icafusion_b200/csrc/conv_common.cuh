@@ -26,6 +26,7 @@ struct ConvParams {
   int stages;                             // smem ring depth (runtime: deep rings for small grids, 2 CTAs/SM otherwise)
   int splits;                             // split-K factor = cluster size along x (1 = no cluster); partial sums meet in DSMEM
   int cblk;                               // A_TMA4D: channels per TMA box = min(Cin, 64); < 64 only in the persistent kernel
+  int dbg;                                // PROBE ONLY (icaf_debug_set): 1 no stores, 2 no activation, 8 no A loads, 16 no B loads, 32 no MMA
 };
 struct ConvMaps {          // TMA descriptors, passed by value as a __grid_constant__ kernel parameter
   CUtensorMap w[2];
@@ -47,7 +48,7 @@ __device__ __forceinline__ ConvProblem pick_problem(const ConvParams& P, unsigne
 template <int ACT, int RES>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float* __restrict__ sb, float rbias,
                                           float alpha, float beta, const __half* __restrict__ rp,
-                                          __half* __restrict__ yp, bool vec, int ncols) {
+                                          __half* __restrict__ yp, bool vec, int ncols, bool do_store = true) {
   auto f = [&](int j) {
     float t = __uint_as_float(acc[j]) + sb[j] + rbias;
     if (ACT == ICAF_ACT_SILU) t = silu_f(t);
@@ -78,7 +79,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float
       uint4 o;
       o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
       o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(yp + q * 8) = o;
+      if (do_store) *reinterpret_cast<uint4*>(yp + q * 8) = o;
     }
   } else {
 #pragma unroll
@@ -90,6 +91,77 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float
           t = RES == 2 ? alpha * rf + beta * t : t + rf;
         }
         yp[j] = __float2half_rn(t);
+      }
+    }
+  }
+}
+
+// Persistent-kernel flavour of epi_chunk, 16 columns of one output row.  Rows whose output (and residual) are 32-byte
+// aligned are written with one 256-bit store: a full L2 sector per lane and instruction.  `sb`: 16 bias floats (smem).
+// `al`: 2 = 32-byte aligned, 1 = 16-byte aligned, 0 = element-wise loads / stores of the first `ncols` columns (ragged N,
+// odd pitches); the math is shared by the three so the hot loop stays small (instruction cache, tools/conv_probe.py).
+template <int ACT, int RES>
+__device__ __forceinline__ void epi_chunk16(const uint32_t (&acc)[16], const float* __restrict__ sb, float rbias,
+                                            float alpha, float beta, const __half* __restrict__ rp,
+                                            __half* __restrict__ yp, int al, int ncols, bool do_store) {
+  auto act = [&](float t) {
+    if (ACT == ICAF_ACT_SILU) t = silu_f(t);
+    if (ACT == ICAF_ACT_GELU) t = gelu_erf_f(t);
+    return t;
+  };
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * q);
+    v[4 * q + 0] = act(__uint_as_float(acc[4 * q + 0]) + b4.x + rbias);
+    v[4 * q + 1] = act(__uint_as_float(acc[4 * q + 1]) + b4.y + rbias);
+    v[4 * q + 2] = act(__uint_as_float(acc[4 * q + 2]) + b4.z + rbias);
+    v[4 * q + 3] = act(__uint_as_float(acc[4 * q + 3]) + b4.w + rbias);
+  }
+  if (RES != 0) {
+    uint32_t rr[8];
+    if (al == 2) {
+      ld_global_nc_v8(rp, rr);
+    } else if (al == 1) {
+      uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
+      uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+      rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+    } else {
+      const unsigned short* rs = reinterpret_cast<const unsigned short*>(rp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t lo = 2 * e < ncols ? rs[2 * e] : 0u;
+        const uint32_t hi = 2 * e + 1 < ncols ? rs[2 * e + 1] : 0u;
+        rr[e] = lo | (hi << 16);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rr[e]));
+      if (RES == 2) {
+        v[2 * e] = alpha * rf.x + beta * v[2 * e];
+        v[2 * e + 1] = alpha * rf.y + beta * v[2 * e + 1];
+      } else {
+        v[2 * e] += rf.x;
+        v[2 * e + 1] += rf.y;
+      }
+    }
+  }
+  uint32_t o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = pack_half2(v[2 * e], v[2 * e + 1]);
+  if (do_store) {
+    if (al == 2) {
+      st_global_v8(yp, o);
+    } else if (al == 1) {
+      *reinterpret_cast<uint4*>(yp) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(yp + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+      unsigned short* ys = reinterpret_cast<unsigned short*>(yp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (2 * e < ncols) ys[2 * e] = (unsigned short)(o[e] & 0xffffu);
+        if (2 * e + 1 < ncols) ys[2 * e + 1] = (unsigned short)(o[e] >> 16);
       }
     }
   }

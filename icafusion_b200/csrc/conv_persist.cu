@@ -2,14 +2,17 @@
 //
 // One CTA per SM loops over output tiles (static round-robin).  The three pipelines of conv_gemm.cu are kept but
 // decoupled across tiles so that every unit stays busy:
-//   * the TMA / gather producers run ahead through the tile sequence, bounded only by the smem ring;
+//   * the TMA producer runs ahead through the tile sequence, bounded only by the smem ring;
 //   * the MMA warp accumulates tile i into TMEM buffer (i & 1) while
-//   * epilogue group (i & 1) -- four warps -- drains the previous tile of that buffer (bias, SiLU/GELU, residual,
-//     fp16 store).  Two epilogue groups alternate, so two tiles can be in their epilogue while a third is in the tensor
-//     core: for the 1x1 / small-K layers, whose main loop is shorter than their epilogue, that is what lets the kernel
-//     run at the HBM roofline instead of at the latency of one CTA's serial phases.
-// 448 threads: warps 0-3 epilogue group 0, warps 4-7 epilogue group 1, warp 8 MMA issuer + TMEM allocator,
-// warp 9 TMA producer, warps 10-13 cp.async gather producers (A_GATHER layers only).
+//   * the two epilogue groups of that buffer -- four warps each, one per half of the tile's columns -- drain the
+//     previous tile of the buffer (bias, SiLU/GELU, residual, fp16 store).  Four groups in total, so two tiles can be
+//     in their epilogue while a third is in the tensor core, and every tile's epilogue is spread over 256 threads:
+//     the short-K layers are bound by the latency of that chain, not by a throughput limit (tools/conv_probe.py).
+// Per-tile bookkeeping is kept off that chain: tile coordinates advance as a mixed-radix counter (no divisions), the
+// bias is read straight from global memory (L1-resident across tiles), TMEM loads are double-buffered against the math,
+// rows are written with 256-bit stores (full L2 sectors).
+// 576 threads: warps 0-15 epilogue groups 0-3 (group = 2*buffer + column half), warp 16 MMA issuer + TMEM allocator,
+// warp 17 TMA producer.  Both operands arrive by TMA; A_GATHER layers stay on conv_gemm_tc_kernel.
 // TMEM: 2 x BN fp32 columns.  Shared memory: the whole SM (ring of up to 10 stages).
 #include <cstring>
 
@@ -17,7 +20,8 @@
 
 namespace icaf {
 
-constexpr int kPThreads = 448;
+constexpr int kPEpiWarps = 16;
+constexpr int kPThreads = (kPEpiWarps + 2) * 32;
 constexpr int kPMaxStages = 10;
 
 template <int BN>
@@ -26,30 +30,83 @@ struct PSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  // [ring] [barriers 256 B] [bias 2 x BN fp32] ; + 1024 B alignment slack
-  static constexpr int kTailBytes = 256 + 2 * BN * 4 + 1024;
+  // [ring] [barriers 256 B] [bias: 4 groups x 2 tiles x BN/2 fp32] ; + 1024 B alignment slack
+  static constexpr int kTailBytes = 256 + 4 * 2 * (BN >= 64 ? BN / 2 : BN) * 4 + 1024;
   static int total(int stages) { return stages * kStageBytes + kTailBytes; }
+};
+
+// Tile sequence t, t + step, t + 2*step, ... as a mixed-radix counter (n fastest: CTAs working side by side share the
+// activation tile in L2).  Digits: n tile | x | y | image | problem.  For 2-D A tiles x is the M tile and y, image are unused.
+struct TileIter {
+  int d[5], st[5], r[4];
+  int t, step;
+  __device__ __forceinline__ void init(const ConvParams& P, int t0, int step_, int n_tiles, int m_tiles) {
+    const bool four = P.a_mode == A_TMA4D;
+    r[0] = n_tiles; r[1] = four ? P.tiles_x : m_tiles; r[2] = four ? P.tiles_y : 1; r[3] = four ? P.B : 1;
+    t = t0; step = step_;
+    int a = t0, b = step_;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      d[i] = a % r[i]; a /= r[i];
+      st[i] = b % r[i]; b /= r[i];
+    }
+    d[4] = a; st[4] = b;
+  }
+  __device__ __forceinline__ void next() {
+    t += step;
+    int carry = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int v = d[i] + st[i] + carry;
+      carry = v >= r[i];
+      d[i] = carry ? v - r[i] : v;
+    }
+    d[4] += st[4] + carry;
+  }
 };
 
 struct TileCoord { int z, m0, n0, tb, oy0, ox0; };
 
-__device__ __forceinline__ TileCoord tile_coord(const ConvParams& P, int t, int n_tiles, int m_tiles, int BN) {
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams& P, const TileIter& it, int BN) {
   TileCoord c;
-  const int per_z = m_tiles * n_tiles;
-  c.z = t / per_z;
-  t -= c.z * per_z;
-  const int mt = t / n_tiles;            // n fastest: CTAs working side by side share the activation tile in L2
-  c.n0 = (t - mt * n_tiles) * BN;
-  c.m0 = mt * BM; c.tb = 0; c.oy0 = 0; c.ox0 = 0;
-  if (P.a_mode == A_TMA4D) {
-    const int per_img = P.tiles_x * P.tiles_y;
-    c.tb = mt / per_img;
-    const int r = mt - c.tb * per_img;
-    c.oy0 = (r / P.tiles_x) * P.th;
-    c.ox0 = (r % P.tiles_x) * P.tw;
-    c.m0 = 0;
-  }
+  c.z = it.d[4]; c.n0 = it.d[0] * BN;
+  if (P.a_mode == A_TMA4D) { c.m0 = 0; c.ox0 = it.d[1] * P.tw; c.oy0 = it.d[2] * P.th; c.tb = it.d[3]; }
+  else { c.m0 = it.d[1] * BM; c.ox0 = 0; c.oy0 = 0; c.tb = 0; }
   return c;
+}
+
+// One epilogue group's share of a tile: CW accumulator columns of this thread's row in 16-column chunks.  The TMEM load
+// of chunk i+1 is in flight during the math of chunk i (two register buffers, loop unrolled by two only: the hot loop
+// must fit the instruction cache); the accumulator buffer goes back to the MMA warp as soon as the last chunk sits in
+// registers.
+template <int CW, int ACT, int RES>
+__device__ __forceinline__ void epi_tile(uint32_t trow, uint32_t tempty, const float* sb, float rbias, float alpha,
+                                         float beta, const __half* rrow, __half* yrow, int al_row, bool mvalid, int nrem,
+                                         bool do_store) {
+  static_assert(CW % 32 == 0, "two chunks per iteration");
+  uint32_t acc0[16], acc1[16];
+  auto chunk = [&](const uint32_t (&acc)[16], int cb) {
+    const int nc = nrem - cb;
+    if (mvalid && nc > 0)
+      epi_chunk16<ACT, RES>(acc, sb + cb, rbias, alpha, beta, rrow ? rrow + cb : nullptr, yrow + cb, nc >= 16 ? al_row : 0, nc,
+                            do_store);
+  };
+  tmem_ld16(trow, acc0);
+#pragma unroll 1
+  for (int cb = 0; cb < CW; cb += 32) {
+    tmem_ld_wait();
+    tmem_ld16(trow + cb + 16, acc1);
+    chunk(acc0, cb);
+    tmem_ld_wait();
+    if (cb + 32 < CW) {
+      tmem_ld16(trow + cb + 32, acc0);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(tempty);
+    }
+    chunk(acc1, cb + 16);
+  }
 }
 
 template <int BN>
@@ -58,6 +115,8 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   using L = PSmem<BN>;
+  constexpr int kHalves = BN >= 64 ? 2 : 1;      // epilogue groups per accumulator buffer
+  constexpr int kCW = BN / kHalves;              // columns per group
   const int kStages = P.stages;
   const uint32_t bar_off = uint32_t(kStages) * L::kStageBytes;
   const uint32_t bar_base = smem_base + bar_off;
@@ -77,22 +136,22 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
   const uint32_t sub_bytes = uint32_t(BM) * cblk * 2u;    // one per-tap sub-tile of the stage
 
   if (tid == 0) {
-    const uint32_t nfull = a_mode == A_GATHER ? 129u : 1u;
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), nfull);
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), 4 * kHalves);     // one elected arrival per epilogue warp of the buffer
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<L::kTmemCols>(tmem_slot);
-  if (warp == 9 && lane_id() == 0) {
+  if (warp == kPEpiWarps) tmem_alloc<L::kTmemCols>(tmem_slot);
+  if (warp == kPEpiWarps + 1 && lane_id() == 0) {
     tma_prefetch_desc(&maps.w[0]);
     tma_prefetch_desc(&maps.w[1]);
-    if (a_mode != A_GATHER) { tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]); }
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.a[1]);
   }
   tc_fence_before();
   __syncthreads();
@@ -100,74 +159,78 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
   pdl_wait();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * kPMaxStages + 4));
 
-  if (warp < 8) {
+  if (warp < kPEpiWarps) {
     // ------------------------------------------------------------------ epilogue groups
-    const int g = warp >> 2;                       // group = accumulator buffer
-    const int gt = tid & 127;                      // thread within the group == TMEM lane == tile row
-    float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256) + g * BN;
-    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-    int it = 0;                                    // tiles this group has drained
-    for (int i = g, t = blockIdx.x + g * gridDim.x; t < total_tiles; i += 2, t += 2 * gridDim.x, ++it) {
-      const TileCoord c = tile_coord(P, t, n_tiles, m_tiles, BN);
-      const ConvProblem pr = pick_problem(P, c.z);
-      int m;
-      bool mvalid;
-      if (a_mode == A_TMA4D) {
-        const int ry = gt / P.tw, rx = gt - ry * P.tw;
-        m = (c.tb * P.Ho + c.oy0 + ry) * P.Wo + c.ox0 + rx;
-        mvalid = ry < P.th && c.oy0 + ry < P.Ho;
-      } else {
-        m = c.m0 + gt;
-        mvalid = m < P.M;
-      }
-      float alpha = 0.f, beta = 1.f;
-      if (P.epi & ICAF_EPI_SCALED_RES) { alpha = __ldg(pr.alpha); beta = __ldg(pr.beta); }
-      const float rbias = ((P.epi & ICAF_EPI_BIAS_ROW) && pr.bias && mvalid) ? __ldg(pr.bias + m) : 0.f;
-      __half* yrow = pr.y + size_t(mvalid ? m : 0) * pr.y_ld;
-      const __half* rrow = pr.res ? pr.res + size_t(mvalid ? m : 0) * pr.res_ld : nullptr;
-      const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : (rrow ? 1 : 0);
-      if (rrow && mvalid) {
-        for (int cb = 0; cb < BN && c.n0 + cb < P.N; cb += 64) prefetch_l2(rrow + c.n0 + cb);
-      }
-      named_bar_sync(1 + g, 128);                  // previous tile's readers are done with this group's bias slice
-      for (int col = gt; col < BN; col += 128)
-        sbias[col] = (pr.bias && !(P.epi & ICAF_EPI_BIAS_ROW) && c.n0 + col < P.N) ? __ldg(pr.bias + c.n0 + col) : 0.f;
-      named_bar_sync(1 + g, 128);
-      mbar_wait(tfull_bar(g), it & 1);
-      tc_fence_after();
-      const uint32_t trow = tmem_base + uint32_t(g * BN) + lane_off;
-      const int mode_act = P.act * 3 + mode;
-#pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 32) {
-        uint32_t acc[32];
-        __syncwarp();
-        tmem_ld32(trow + cb, acc);
-        tmem_ld_wait();
-        const int nb = c.n0 + cb;
-        if (mvalid && nb < P.N) {
-          const int ncols = min(32, P.N - nb);
-          const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(yrow + nb) & 15) == 0) &&
-                           (!rrow || (reinterpret_cast<uintptr_t>(rrow + nb) & 15) == 0);
-          const float* sb = sbias + cb;
-          const __half* rp = rrow ? rrow + nb : nullptr;
-          __half* yp = yrow + nb;
-          switch (mode_act) {
-            case 0: epi_chunk<0, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 1: epi_chunk<0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 2: epi_chunk<0, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 3: epi_chunk<1, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 4: epi_chunk<1, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 5: epi_chunk<1, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 6: epi_chunk<2, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 7: epi_chunk<2, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            default: epi_chunk<2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-          }
+    const int eg = warp >> 2;                      // group
+    const int buf = eg >> 1;                       // accumulator buffer
+    const int half = eg & 1;                       // column half of the tile
+    if (half < kHalves) {
+      const int gt = tid & 127;                    // thread within the group == TMEM lane == tile row
+      const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+      const int ry = a_mode == A_TMA4D ? gt / P.tw : 0;
+      const int rx = a_mode == A_TMA4D ? gt - ry * P.tw : 0;
+      const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : ((P.epi & ICAF_EPI_ADD_RES) ? 1 : 0);
+      const int mode_act = (P.dbg & 2) ? mode : P.act * 3 + mode;
+      const bool dst = !(P.dbg & 1);
+      const bool row_bias = (P.epi & ICAF_EPI_BIAS_ROW) != 0;
+      float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256) + eg * 2 * kCW;   // [tile parity][kCW]
+      // this thread's bias column of a tile (fetched one tile ahead, so its latency hides behind the current tile)
+      auto bias_of = [&](const TileIter& q) -> float {
+        const float* pb = q.d[4] ? P.p[1].bias : P.p[0].bias;
+        const int n = q.d[0] * BN + half * kCW + gt;
+        return (gt < kCW && pb && !row_bias && q.t < total_tiles && n < P.N) ? __ldg(pb + n) : 0.f;
+      };
+      TileIter ti;
+      ti.init(P, blockIdx.x + buf * gridDim.x, 2 * gridDim.x, n_tiles, m_tiles);
+      float bnext = bias_of(ti);
+      for (int it = 0; ti.t < total_tiles; ++it) {
+        const TileCoord c = tile_coord(P, ti, BN);
+        const ConvProblem pr = pick_problem(P, c.z);
+        float* sb = sbias + (it & 1) * kCW;
+        if (gt < kCW) sb[gt] = bnext;
+        named_bar_sync(1 + eg, 128);               // slice (it & 1) was last read two tiles ago: no second barrier needed
+        ti.next();
+        bnext = bias_of(ti);
+        int m;
+        bool mvalid;
+        if (a_mode == A_TMA4D) {
+          m = (c.tb * P.Ho + c.oy0 + ry) * P.Wo + c.ox0 + rx;
+          mvalid = ry < P.th && c.oy0 + ry < P.Ho;
+        } else {
+          m = c.m0 + gt;
+          mvalid = m < P.M;
+        }
+        float alpha = 0.f, beta = 1.f;
+        if (mode == 2) { alpha = __ldg(pr.alpha); beta = __ldg(pr.beta); }
+        const float rbias = (row_bias && pr.bias && mvalid) ? __ldg(pr.bias + m) : 0.f;
+        const int nb0 = c.n0 + half * kCW;
+        __half* yrow = pr.y + size_t(mvalid ? m : 0) * pr.y_ld + nb0;
+        const __half* rrow = (mode != 0 && pr.res) ? pr.res + size_t(mvalid ? m : 0) * pr.res_ld + nb0 : nullptr;
+        if (rrow && mvalid) {
+          for (int cb = 0; cb < kCW && nb0 + cb < P.N; cb += 64) prefetch_l2(rrow + cb);
+        }
+        // alignment class of this row's 16-column chunks (chunks are 32 bytes apart, so one test covers them all)
+        const uintptr_t ua = reinterpret_cast<uintptr_t>(yrow) | (rrow ? reinterpret_cast<uintptr_t>(rrow) : 0);
+        const int al_row = (ua & 31) == 0 ? 2 : ((ua & 15) == 0 ? 1 : 0);
+        mbar_wait(tfull_bar(buf), it & 1);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + uint32_t(buf * BN + half * kCW) + lane_off;
+        const uint32_t te = tempty_bar(buf);
+        const int nrem = P.N - nb0;
+        switch (mode_act) {
+          case 0: epi_tile<kCW, 0, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          case 1: epi_tile<kCW, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          case 2: epi_tile<kCW, 0, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          case 3: epi_tile<kCW, 1, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          case 4: epi_tile<kCW, 1, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          case 5: epi_tile<kCW, 1, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          case 6: epi_tile<kCW, 2, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          case 7: epi_tile<kCW, 2, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          default: epi_tile<kCW, 2, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(g));                  // 128 arrivals: the MMA warp may overwrite this accumulator buffer
     }
-  } else if (warp == 8) {
+  } else if (warp == kPEpiWarps) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
     int s = 0;
@@ -175,7 +238,7 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
     int i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
-      mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);      // epilogue group has drained this buffer (first use: free)
+      mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);      // epilogue groups have drained this buffer (first use: free)
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
       for (int kb = 0; kb < nkb; ++kb) {
@@ -184,7 +247,8 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         if (elect_one()) {
           const uint32_t sa = smem_base + s * L::kStageBytes;
           const uint64_t bd = umma_desc_sw128(sa + L::kABytes);
-          if (cblk == 64) {
+          if (P.dbg & 32) {
+          } else if (cblk == 64) {
             const uint64_t ad = umma_desc_sw128(sa);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
@@ -205,15 +269,16 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kPEpiWarps + 1) {
     // ------------------------------------------------------------------ TMA producer (one thread)
     if (elect_one()) {
       const uint32_t a_bytes = a_mode == A_TMA2D ? L::kABytes : (a_mode == A_TMA4D ? uint32_t(P.tw * P.th) * 128u : 0u);
-      const uint32_t bytes = L::kBBytes + a_bytes;
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord c = tile_coord(P, t, n_tiles, m_tiles, BN);
+      TileIter ti;
+      ti.init(P, blockIdx.x, gridDim.x, n_tiles, m_tiles);
+      for (; ti.t < total_tiles; ti.next()) {
+        const TileCoord c = tile_coord(P, ti, BN);
         const CUtensorMap* mw = c.z ? &maps.w[1] : &maps.w[0];
         const CUtensorMap* ma = c.z ? &maps.a[1] : &maps.a[0];
         for (int kb = 0; kb < nkb; ++kb) {
@@ -235,9 +300,11 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
             if (++s == kStages) { s = 0; ph ^= 1; }
             continue;
           }
-          mbar_arrive_expect_tx(full_bar(s), bytes);
-          tma_load_2d(sa + L::kABytes, mw, full_bar(s), kb * BK, c.n0);
-          if (a_mode == A_TMA2D) {
+          const bool ldA = !(P.dbg & 8), ldB = !(P.dbg & 16);
+          mbar_arrive_expect_tx(full_bar(s), (ldB ? L::kBBytes : 0u) + (ldA ? a_bytes : 0u));
+          if (ldB) tma_load_2d(sa + L::kABytes, mw, full_bar(s), kb * BK, c.n0);
+          if (!ldA) {
+          } else if (a_mode == A_TMA2D) {
             tma_load_2d(sa, ma, full_bar(s), kb * BK, c.m0);
           } else if (a_mode == A_TMA4D) {
             const int k0 = kb * BK;
@@ -251,56 +318,10 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
       }
     }
     __syncwarp();
-  } else if (a_mode == A_GATHER) {
-    // ------------------------------------------------------------------ cp.async gather producers (warps 10-13)
-    const int pt = tid - 320;         // 0..127
-    const int c8 = pt & 7;            // 16-byte chunk within the 128-byte K row
-    const int r0 = pt >> 3;           // rows r0 + 16*i
-    const uint32_t sw = uint32_t(c8 ^ (r0 & 7)) << 4;
-    int s = 0;
-    uint32_t ph = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord c = tile_coord(P, t, n_tiles, m_tiles, BN);
-      const ConvProblem pr = pick_problem(P, c.z);
-      uint32_t base[8];
-      int iy0[8], ix0[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int m = c.m0 + r0 + 16 * i;
-        bool mv = m < P.M;
-        int mm = mv ? m : 0;
-        int ox = mm % P.Wo;
-        int q = mm / P.Wo;
-        int oy = q % P.Ho;
-        int b = q / P.Ho;
-        base[i] = uint32_t(b) * uint32_t(P.Hi * P.Wi);
-        iy0[i] = mv ? oy * P.stride - P.pad : -100000;
-        ix0[i] = ox * P.stride - P.pad;
-      }
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t sa = smem_base + s * L::kStageBytes;
-        const int k0 = kb * BK + c8 * 8;
-        const bool kvalid = k0 < P.K;
-        const int tap = k0 / P.Cin;
-        const int ch = k0 - tap * P.Cin;
-        const int ky = tap / P.kw;
-        const int kx = tap - ky * P.kw;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int iy = iy0[i] + ky, ix = ix0[i] + kx;
-          bool ok = kvalid && (unsigned)iy < (unsigned)P.Hi && (unsigned)ix < (unsigned)P.Wi;
-          size_t off = ok ? (size_t(base[i] + uint32_t(iy * P.Wi + ix)) * size_t(pr.x_ld) + ch) : 0;
-          cp_async16(sa + uint32_t(r0 + 16 * i) * 128u + sw, pr.x + off, ok);
-        }
-        cp_async_arrive_on(full_bar(s));     // asynchronous arrival: the whole ring can be in flight, nobody blocks
-        if (++s == kStages) { s = 0; ph ^= 1; }
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kPEpiWarps) {
     tc_fence_after();
     tmem_dealloc<L::kTmemCols>(tmem_base);
   }

@@ -18,6 +18,8 @@ bool pdl_enabled();        // programmatic dependent launch on every kernel (env
 
 // Launch with the programmatic-stream-serialization attribute when PDL is enabled (every kernel of this library
 // executes griddepcontrol.wait before it touches memory another kernel may have produced).
+void count_launch();   // api.cu: process-wide tally behind icaf_kernel_launches()
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_x,
                              Args&&... args) {
@@ -37,6 +39,7 @@ inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>

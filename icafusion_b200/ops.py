@@ -16,12 +16,12 @@ from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, EPI_ADD_RES, EPI_BIAS_ROW, EPI_SCALED_RES  # noqa: F401
 
 
-_LAUNCHES = 0          # kernels of libicaf_b200 enqueued so far (each C-ABI compute call launches exactly one)
 _PROFILE = None        # when a list: every call appends (name, work dict, start event, end event)
 
 
 def launch_count() -> int:
-    return _LAUNCHES
+    """Kernels of libicaf_b200 enqueued so far (the library's own tally: a C-ABI call may launch more than one)."""
+    return int(_lib.lib().icaf_kernel_launches())
 
 
 class profile:
@@ -121,7 +121,6 @@ def _stream() -> C.c_void_p:
 
 def _call(name: str, fn, args, work=None):
     """Invoke one C-ABI kernel launcher on the current stream (optionally event-bracketed)."""
-    global _LAUNCHES
     if _PROFILE is not None:
         if _PROFILE.last is None:
             _PROFILE.mark()
@@ -133,7 +132,6 @@ def _call(name: str, fn, args, work=None):
     else:
         rc = fn(*args, _stream())
     _lib.check(rc, name)
-    _LAUNCHES += 1
 
 
 def _check_view(t: torch.Tensor, what: str) -> int:

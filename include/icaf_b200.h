@@ -42,6 +42,9 @@ extern "C" {
 
 int icaf_version(void);
 const char* icaf_last_error(void);
+/* Kernels this library has enqueued so far in this process (monotonic; one C-ABI compute call may launch more than one
+ * kernel, e.g. a convolution whose last wave is peeled off as a split-K tail).  bench.py reports its per-step delta. */
+long long icaf_kernel_launches(void);
 /* Number of SMs of the current device (grid sizing of callers' workspaces); <0 on error. */
 int icaf_sm_count(void);
 

@@ -48,13 +48,15 @@ CASES = [
     (1, 512, 16, 20, 512, 3, 1, 1, 1),    # P5 of yolov5l at batch 1: 72 K blocks over an 8-CTA cluster (DSMEM split-K reduction)
     (1, 2048, 1, 104, 512, 1, 1, 0, 0),   # MLP fc2 shape (rows as pixels): K=2048, split-K over clusters, 2-D TMA
     (8, 64, 64, 80, 64, 3, 1, 1, 1),      # 320 tiles -> persistent kernel, 4-D TMA, BN=64
-    (8, 3, 128, 160, 32, 6, 2, 2, 1),     # 320 tiles -> persistent kernel, cp.async gather (image stem), BN=32
+    (8, 3, 128, 160, 32, 6, 2, 2, 1),     # 320 tiles, cp.async gather (6x6 image stem on the packed NHWC4 image), BN=32
     (4, 128, 64, 80, 256, 3, 2, 1, 1),    # persistent, 4-D TMA stride 2, BN=128, 18 K blocks per tile
     (3, 64, 100, 84, 96, 1, 1, 0, 2),     # persistent, 2-D TMA, ragged M (25200 rows) and N (96), GELU
     (8, 32, 64, 80, 64, 3, 1, 1, 1),      # persistent, small-Cin TMA staging: per-tap boxes of 32 channels, 64-byte swizzle
     (8, 32, 128, 160, 64, 3, 2, 1, 1),    # ... stride 2 (yolov5s layer 1 geometry)
     (8, 16, 64, 80, 32, 3, 1, 1, 1),      # ... 16 channels, 32-byte swizzle, K = 144 (tail K block holds one tap)
     (1, 16, 16, 20, 32, 3, 1, 1, 1),      # 16 channels on a small grid: cp.async gather path
+    (16, 256, 32, 40, 256, 3, 1, 1, 1),   # 320 BN=128 persistent tiles on 148 SMs (ragged last wave), 36 K blocks, N split over both epilogue column halves
+    (19, 1024, 32, 64, 256, 1, 1, 0, 0),  # 304 BN=256 persistent tiles, 2-D TMA, K=1024, no activation
 ]
 
 
