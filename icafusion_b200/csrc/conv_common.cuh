@@ -171,4 +171,8 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&acc)[16], const flo
 template <int BN>
 int launch_persist(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
 
+// CTA-pair kernel (conv_pair.cu): 256 x BN tiles over two SMs, tcgen05.mma.cta_group::2 (BN = 64, 128, 256)
+template <int BN>
+int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
+
 }  // namespace icaf

@@ -470,8 +470,22 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   const long long mt = P.a_mode == A_TMA4D ? (long long)P.B * P.tiles_x * P.tiles_y : (P.M + BM - 1) / BM;
   const int sms = sm_count_cached();
   auto ctas = [&](int bn) { return mt * ((P.N + bn - 1) / bn) * n_io; };
+  // CTA pairs (conv_pair.cu): two SMs share one 256 x BN tile and each loads only half of the filter tile.  Measured
+  // (yolov5l batch 16, profiles/): always a win at BN = 256 once a wave of clusters is full (or half full with a deep K
+  // loop); at BN = 128 / 64 only for the deep-K (3x3) layers -- the short-K 1x1 layers are HBM / epilogue bound and lose
+  // to the pair's extra synchronisation.  ICAF_PAIR=0 disables it, ICAF_PAIR=all forces it wherever it can run (tests).
+  static const int pair_env = []() { const char* e = getenv("ICAF_PAIR"); return !e ? 1 : (e[0] == '0' ? 0 : (e[0] == 'a' ? 2 : 1)); }();
+  const bool pair_ok = pair_env && (P.a_mode == A_TMA2D || (P.a_mode == A_TMA4D && P.cblk == 64));
+  const int nkb_all = P.k_pad / BK;
+  auto pair_wanted = [&](int b) {
+    if (!pair_ok || b < 64) return false;
+    if (pair_env == 2) return true;
+    const long long pairs = ctas(b) / 2;
+    if (b == 256) return pairs >= sms / 2 || (pairs >= sms / 4 && nkb_all >= 32);
+    return pairs >= sms / 2 && nkb_all >= 8;
+  };
   int bn = 32;
-  if (P.N >= 256 && ctas(256) >= 2 * sms) bn = 256;
+  if (P.N >= 256 && (ctas(256) >= 2 * sms || pair_wanted(256))) bn = 256;
   else if (P.N > 64 && ctas(128) >= sms) bn = 128;
   else if (P.N > 32 && ctas(64) >= sms) bn = 64;
   if (g_dbg_bn) bn = g_dbg_bn;
@@ -484,6 +498,13 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   // (A wave-tail scheme -- peel total % SMs tiles off into a split-K cluster launch -- was measured and dropped: these
   // layers are bound by chip-wide L2->SM bandwidth, so a partly filled last wave just streams the same bytes through
   // fewer, faster CTAs; the second launch only added its fixed cost: 65 -> 87 us on the 320-tile P4 3x3 layer.)
+  if (pair_wanted(bn)) {
+    switch (bn) {
+      case 256: return launch_pair<256>(P, w, g, n_io, st);
+      case 128: return launch_pair<128>(P, w, g, n_io, st);
+      default: return launch_pair<64>(P, w, g, n_io, st);
+    }
+  }
   if (persistent) {
     switch (bn) {
       case 256: return launch_persist<256>(P, w, g, n_io, st);

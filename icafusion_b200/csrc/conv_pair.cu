@@ -1,0 +1,367 @@
+// CTA-pair (tcgen05 cta_group::2) variant of the persistent implicit-GEMM conv kernel for the wide layers (N >= 256).
+//
+// Why: the wide 3x3 / 1x1 layers are bound by the bytes each SM has to pull out of L2 per K block, not by the tensor
+// pipe (tools/conv_probe.py: a 128x256 tile streams 16 KB of A + 32 KB of B per 512 MMA-clocks, the chip delivers
+// ~40 B/clk/SM).  Two SMs of a TPC therefore work as one: a cluster of two CTAs owns a 256 x 256 output tile, each CTA
+// loads its own 128 activation rows but only HALF of the filter tile (128 of the 256 output channels), and the leader
+// CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 256): each SM's tensor core reads its A rows and both halves of B
+// (its own and the peer's shared memory).  Bytes per SM and K block drop from 48 KB to 32 KB for the same MMA work.
+//
+// Protocol (per CTA the same barrier layout; "leader" = cluster rank 0):
+//   full[s]   leader only: 1 arrival (its producer's expect_tx of BOTH CTAs' bytes); both CTAs' TMA loads complete_tx on it
+//             (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address).
+//   empty[s]  both: tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11) from the leader's MMA thread.
+//   tfull[b]  both: same multicast commit after the last K block of a tile.
+//   tempty[b] leader only: 16 arrivals = one per epilogue warp of the buffer, both CTAs (the peer's arrive remotely).
+// Everything else (tile loop, four epilogue groups, bias staging, 256-bit stores) is conv_persist.cu's.
+// 576 threads per CTA: warps 0-15 epilogue, warp 16 MMA issuer (leader) + TMEM allocator (both), warp 17 TMA producer.
+#include <cstring>
+
+#include "conv_common.cuh"
+
+namespace icaf {
+
+constexpr int kQEpiWarps = 16;
+constexpr int kQThreads = (kQEpiWarps + 2) * 32;
+constexpr int kQMaxStages = 10;
+constexpr int kQABytes = BM * BK * 2;         // this CTA's 128 activation rows
+
+template <int BN>                             // BN = tile width = UMMA N (256, 128 or 64)
+struct QSmem {
+  static constexpr int kBBytes = (BN / 2) * BK * 2;   // this CTA's half of the filter tile
+  static constexpr int kStageBytes = kQABytes + kBBytes;
+  static constexpr int kCW = BN / 2;                  // columns per epilogue group
+  static constexpr int kTail = 256 + 4 * 2 * kCW * 4 + 1024;
+  static constexpr int kStagesFit = (227 * 1024 - kTail) / kStageBytes;
+  static constexpr int kStages = kStagesFit > kQMaxStages ? kQMaxStages : kStagesFit;
+  static constexpr int kSmem = kStages * kStageBytes + kTail;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+// ---- cta_group::2 PTX (same encodings CUTLASS' SM100_TMA_2SM_LOAD / umma_arrive_multicast_2x1SM use)
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst) {    // one warp in EACH CTA of the pair, same smem offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// Arrive on the barrier at this offset in both CTAs once every tcgen05 op issued so far by this thread has completed.
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+struct PairTile { int z, mtile, n0, tb, oy0, ox0, m0; };
+
+// pair-tile t -> this CTA's output tile.  Sequence: n fastest, then pair of M tiles, then problem.
+__device__ __forceinline__ PairTile pair_tile(const ConvParams& P, int t, int rank, int m_pairs, int n_tiles, int BN) {
+  PairTile c;
+  const int per_z = m_pairs * n_tiles;
+  c.z = t / per_z;
+  t -= c.z * per_z;
+  const int mp = t / n_tiles;
+  c.n0 = (t - mp * n_tiles) * BN;
+  c.mtile = 2 * mp + rank;
+  c.m0 = c.mtile * BM; c.tb = 0; c.oy0 = 0; c.ox0 = 0;
+  if (P.a_mode == A_TMA4D) {
+    const int per_img = P.tiles_x * P.tiles_y;
+    c.tb = c.mtile / per_img;                 // an odd tile count leaves the peer a tile past the last image: all zero fill
+    const int r = c.mtile - c.tb * per_img;
+    c.oy0 = (r / P.tiles_x) * P.th;
+    c.ox0 = (r % P.tiles_x) * P.tw;
+    c.m0 = 0;
+  }
+  return c;
+}
+
+// Same as conv_persist.cu's epi_tile, except that the accumulator buffer is handed back to the LEADER's MMA thread.
+template <int CW, int ACT, int RES>
+__device__ __forceinline__ void epi_tile_pair(uint32_t trow, uint32_t tempty_leader, const float* sb, float rbias, float alpha,
+                                              float beta, const __half* rrow, __half* yrow, int al_row, bool mvalid, int nrem) {
+  uint32_t acc0[16], acc1[16];
+  auto chunk = [&](const uint32_t (&acc)[16], int cb) {
+    const int nc = nrem - cb;
+    if (mvalid && nc > 0)
+      epi_chunk16<ACT, RES>(acc, sb + cb, rbias, alpha, beta, rrow ? rrow + cb : nullptr, yrow + cb, nc >= 16 ? al_row : 0, nc, true);
+  };
+  tmem_ld16(trow, acc0);
+#pragma unroll 1
+  for (int cb = 0; cb < CW; cb += 32) {
+    tmem_ld_wait();
+    tmem_ld16(trow + cb + 16, acc1);
+    chunk(acc0, cb);
+    tmem_ld_wait();
+    if (cb + 32 < CW) {
+      tmem_ld16(trow + cb + 32, acc0);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive_cluster(tempty_leader);
+    }
+    chunk(acc1, cb + 16);
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kQThreads, 1)
+conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps, int total_pairs, int m_tiles, int m_pairs, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  using L = QSmem<BN>;
+  constexpr int kQStages = L::kStages;
+  constexpr int kQStageBytes = L::kStageBytes;
+  constexpr int kQBBytes = L::kBBytes;
+  constexpr int kQCW = L::kCW;
+  constexpr int kQBN = BN;
+  const uint32_t bar_off = uint32_t(kQStages) * kQStageBytes;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kQStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kQStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kQStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kQStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  const int rank = int(cluster_ctarank());            // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int nkb = P.k_pad / BK;
+  const int a_mode = P.a_mode;
+
+  if (tid == 0) {
+    for (int s = 0; s < kQStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 16);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kQEpiWarps) tmem_alloc2<L::kTmemCols>(tmem_slot);
+  if (warp == kQEpiWarps + 1 && lane_id() == 0) {
+    tma_prefetch_desc(&maps.w[0]);
+    tma_prefetch_desc(&maps.w[1]);
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.a[1]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();                                   // the peer's barriers exist before anything is signalled across
+  cluster_wait();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * kQStages + 4));
+
+  if (warp < kQEpiWarps) {
+    // ------------------------------------------------------------------ epilogue groups (both CTAs, own 128 rows)
+    const int eg = warp >> 2;
+    const int buf = eg >> 1;
+    const int half = eg & 1;
+    const int gt = tid & 127;
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+    const int ry = a_mode == A_TMA4D ? gt / P.tw : 0;
+    const int rx = a_mode == A_TMA4D ? gt - ry * P.tw : 0;
+    const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : ((P.epi & ICAF_EPI_ADD_RES) ? 1 : 0);
+    const int mode_act = P.act * 3 + mode;
+    const bool row_bias = (P.epi & ICAF_EPI_BIAS_ROW) != 0;
+    float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256) + eg * 2 * kQCW;
+    const uint32_t tempty_leader = map_to_cta(tempty_bar(buf), 0);
+    auto bias_of = [&](int t) -> float {
+      if (t >= total_pairs || gt >= kQCW) return 0.f;
+      const PairTile q = pair_tile(P, t, rank, m_pairs, n_tiles, BN);
+      const float* pb = q.z ? P.p[1].bias : P.p[0].bias;
+      const int n = q.n0 + half * kQCW + gt;
+      return (pb && !row_bias && n < P.N) ? __ldg(pb + n) : 0.f;
+    };
+    const int step = 2 * n_clusters;
+    int t = cluster_id + buf * n_clusters;
+    float bnext = bias_of(t);
+    for (int it = 0; t < total_pairs; t += step, ++it) {
+      const PairTile c = pair_tile(P, t, rank, m_pairs, n_tiles, BN);
+      const ConvProblem pr = pick_problem(P, c.z);
+      float* sb = sbias + (it & 1) * kQCW;
+      if (gt < kQCW) sb[gt] = bnext;
+      named_bar_sync(1 + eg, 128);
+      bnext = bias_of(t + step);
+      int m;
+      bool mvalid;
+      if (a_mode == A_TMA4D) {
+        m = (c.tb * P.Ho + c.oy0 + ry) * P.Wo + c.ox0 + rx;
+        mvalid = c.mtile < m_tiles && ry < P.th && c.oy0 + ry < P.Ho;
+      } else {
+        m = c.m0 + gt;
+        mvalid = m < P.M;
+      }
+      float alpha = 0.f, beta = 1.f;
+      if (mode == 2) { alpha = __ldg(pr.alpha); beta = __ldg(pr.beta); }
+      const float rbias = (row_bias && pr.bias && mvalid) ? __ldg(pr.bias + m) : 0.f;
+      const int nb0 = c.n0 + half * kQCW;
+      __half* yrow = pr.y + size_t(mvalid ? m : 0) * pr.y_ld + nb0;
+      const __half* rrow = (mode != 0 && pr.res) ? pr.res + size_t(mvalid ? m : 0) * pr.res_ld + nb0 : nullptr;
+      if (rrow && mvalid) {
+        for (int cb = 0; cb < kQCW && nb0 + cb < P.N; cb += 64) prefetch_l2(rrow + cb);
+      }
+      const uintptr_t ua = reinterpret_cast<uintptr_t>(yrow) | (rrow ? reinterpret_cast<uintptr_t>(rrow) : 0);
+      const int al_row = (ua & 31) == 0 ? 2 : ((ua & 15) == 0 ? 1 : 0);
+      mbar_wait(tfull_bar(buf), it & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + uint32_t(buf * kQBN + half * kQCW) + lane_off;
+      const int nrem = P.N - nb0;
+      switch (mode_act) {
+        case 0: epi_tile_pair<kQCW, 0, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        case 1: epi_tile_pair<kQCW, 0, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        case 2: epi_tile_pair<kQCW, 0, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        case 3: epi_tile_pair<kQCW, 1, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        case 4: epi_tile_pair<kQCW, 1, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        case 5: epi_tile_pair<kQCW, 1, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        case 6: epi_tile_pair<kQCW, 2, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        case 7: epi_tile_pair<kQCW, 2, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        default: epi_tile_pair<kQCW, 2, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+      }
+    }
+  } else if (warp == kQEpiWarps) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, kQBN);
+      int s = 0;
+      uint32_t ph = 0;
+      int i = 0;
+      for (int t = cluster_id; t < total_pairs; t += n_clusters, ++i) {
+        const int buf = i & 1;
+        mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);      // both CTAs' epilogue groups have drained this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(buf * kQBN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(s), ph);                        // both CTAs' operands of this stage have landed
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_base + s * kQStageBytes;
+            const uint64_t ad = umma_desc_sw128(sa);
+            const uint64_t bd = umma_desc_sw128(sa + kQABytes);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma2_f16_ss(tmem_d, ad + uint64_t(2 * k), bd + uint64_t(2 * k), idesc, (kb | k) != 0);
+            umma2_commit_both(empty_bar(s));
+            if (kb == nkb - 1) umma2_commit_both(tfull_bar(buf));
+          }
+          __syncwarp();
+          if (++s == kQStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ TMA producer (one thread per CTA)
+    if (elect_one()) {
+      const uint32_t a_bytes = a_mode == A_TMA2D ? uint32_t(kQABytes) : uint32_t(P.tw * P.th) * 128u;
+      const uint32_t stage_tx = 2u * (uint32_t(kQBBytes) + a_bytes);   // both CTAs' loads complete on the leader's barrier
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = cluster_id; t < total_pairs; t += n_clusters) {
+        const PairTile c = pair_tile(P, t, rank, m_pairs, n_tiles, BN);
+        const CUtensorMap* mw = c.z ? &maps.w[1] : &maps.w[0];
+        const CUtensorMap* ma = c.z ? &maps.a[1] : &maps.a[0];
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = smem_base + s * kQStageBytes;
+          const uint32_t lfull = map_to_cta(full_bar(s), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), stage_tx);
+          tma2_load_2d(sa + kQABytes, mw, lfull, kb * BK, c.n0 + rank * (kQBN / 2));
+          if (a_mode == A_TMA2D) {
+            tma2_load_2d(sa, ma, lfull, kb * BK, c.m0);
+          } else {
+            const int k0 = kb * BK;
+            const int tap = k0 / P.Cin;
+            const int ch = k0 - tap * P.Cin;
+            const int ky = tap / P.kw, kx = tap - ky * P.kw;
+            tma2_load_4d(sa, ma, lfull, ch, c.ox0 * P.stride - P.pad + kx, c.oy0 * P.stride - P.pad + ky, c.tb);
+          }
+          if (++s == kQStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive();                                   // neither CTA may free TMEM / exit while the pair still works
+  cluster_wait();
+  if (warp == kQEpiWarps) {
+    tc_fence_after();
+    tmem_dealloc2<L::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+  using L = QSmem<BN>;
+  constexpr int kQBN = BN;
+  constexpr int kQSmem = L::kSmem;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute (pair)");
+    configured = true;
+  }
+  const int m_tiles = P.a_mode == A_TMA4D ? P.B * P.tiles_x * P.tiles_y : (P.M + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int n_tiles = (P.N + kQBN - 1) / kQBN;
+  const int total = m_pairs * n_tiles * n_io;
+  P.stages = L::kStages;
+  P.splits = 1;
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < n_io; ++i) {
+    int rc = encode_tmap_2d(&maps.w[i], w[i], (uint64_t)P.k_pad, (uint64_t)g->w_rows, (uint64_t)P.k_pad * 2, BK, kQBN / 2);
+    if (rc) return rc;
+    const ConvProblem& pr = P.p[i];
+    if (P.a_mode == A_TMA2D)
+      rc = encode_tmap_2d(&maps.a[i], pr.x, (uint64_t)P.Cin, (uint64_t)P.M, (uint64_t)pr.x_ld * 2, BK, BM);
+    else
+      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, P.tw * P.stride, P.th * P.stride, P.stride, P.stride);
+    if (rc) return rc;
+  }
+  if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
+  const int max_clusters = sm_count_cached() / 2;
+  const int waves = (total + max_clusters - 1) / max_clusters;
+  const int clusters = (total + waves - 1) / waves;
+  launch_kc(conv_gemm_pair_kernel<BN>, dim3(2 * clusters), dim3(kQThreads), (size_t)kQSmem, st, 2u, P, maps, total, m_tiles, m_pairs, n_tiles);
+  return check_launch("conv2d_fwd(pair)");
+}
+
+template int launch_pair<64>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
+template int launch_pair<128>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
+template int launch_pair<256>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
+
+}  // namespace icaf

@@ -220,8 +220,6 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// ------------------------------------------------------------------ small math helpers
-// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (rel. error ~1e-6, far below the fp16 output rounding)
 // ------------------------------------------------------------------ 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256)
 // One full 32-byte L2 sector per lane and instruction; the pointer must be 32-byte aligned.
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&o)[8]) {
@@ -233,6 +231,8 @@ __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t (&o)[8])
                "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "l"(p));
 }
 
+// ------------------------------------------------------------------ small math helpers
+// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (rel. error ~1e-6, far below the fp16 output rounding)
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {

@@ -56,7 +56,10 @@ CASES = [
     (8, 16, 64, 80, 32, 3, 1, 1, 1),      # ... 16 channels, 32-byte swizzle, K = 144 (tail K block holds one tap)
     (1, 16, 16, 20, 32, 3, 1, 1, 1),      # 16 channels on a small grid: cp.async gather path
     (16, 256, 32, 40, 256, 3, 1, 1, 1),   # 320 BN=128 persistent tiles on 148 SMs (ragged last wave), 36 K blocks, N split over both epilogue column halves
-    (19, 1024, 32, 64, 256, 1, 1, 0, 0),  # 304 BN=256 persistent tiles, 2-D TMA, K=1024, no activation
+    (19, 1024, 32, 64, 256, 1, 1, 0, 0),  # 304 BN=256 tiles -> CTA-pair kernel (cta_group::2), 2-D TMA, K=1024, no activation
+    (32, 128, 32, 40, 256, 3, 1, 1, 1),   # CTA-pair kernel, 4-D TMA (16x8 tiles), 320 M tiles = 160 pairs
+    (1, 64, 301, 128, 512, 1, 1, 0, 1),   # CTA-pair kernel, odd M-tile count (301): the last pair's peer tile is all padding
+    (99, 64, 16, 24, 256, 3, 1, 1, 1),    # CTA-pair kernel, 4-D TMA, 297 M tiles: peer tile past the last image
 ]
 
 
@@ -96,6 +99,38 @@ def test_grouped_residual_and_slices(cuda_device):
     for i in range(2):
         assert err(nchw(outs[i]), refs[i]) < TOL
         assert float(xs[i][..., :C].abs().max()) == 0 and float(xs[i][..., 2 * C:].abs().max()) == 0   # neighbours untouched
+
+
+def test_conv_suite_with_pairs_everywhere(cuda_device):
+    """The same conv cases with ICAF_PAIR=all: the CTA-pair kernel (BN 64/128/256, 2-D and 4-D TMA, ragged N, odd tile
+    counts, single-pair grids) replaces every persistent / one-tile launch it can run.  The switch is read once per
+    process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("ICAF_PAIR") == "all":
+        pytest.skip("already inside the pairs-everywhere run")
+    env = dict(os.environ, ICAF_PAIR="all")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k", "matches_oracle or grouped"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_pair_kernel_grouped_residual(cuda_device):
+    """CTA-pair kernel with two problems per launch (RGB / IR streams) and the fused Bottleneck residual."""
+    from icafusion_b200 import ops
+    B, C, H, W = 16, 256, 32, 40
+    xs, packs, ress, refs = [], [], [], []
+    for i in range(2):
+        x, w, b = _mk(B, C, H, W, C, 3, 1, 1, seed=20 + i)
+        res = torch.randn(B, C, H, W).half()
+        xs.append(nhwc(x).to(cuda_device)); ress.append(nhwc(res).to(cuda_device))
+        packs.append(ops.pack_conv_weight(w.float(), b, 1, 1, 1, device=cuda_device))
+        refs.append(_ref(x, w, b, 1, 1, 1) + res.float())
+    ys = ops.conv2d(xs, packs, None, ress)
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert err(nchw(ys[i]), refs[i]) < TOL
 
 
 @pytest.mark.parametrize("B,H,W,Cout", [(1, 64, 80, 32), (8, 256, 320, 32), (2, 128, 160, 64)])
