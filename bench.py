@@ -287,7 +287,7 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
     tf_peak, hbm_peak, peak_src = _peaks()
     ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
     total_ms = sum(v["ms"] for v in summ.values())
-    roofline = {"kernel": "conv_gemm_tc_kernel (icaf_conv2d_fwd: every Conv/Linear/Detect GEMM of a step)", "bound": "tensor",
+    roofline = {"kernel": "icaf_conv2d_fwd = conv_gemm_{tc,persist,pair}_kernel (every Conv/Linear/Detect GEMM of a step)", "bound": "tensor",
                 "achieved": round(ach, 3), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 5), "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": round(conv.get("bytes", 0.0) / max(1, conv["launches"])),
                 "peak_source": peak_src, "launches_per_step": conv["launches"] // reps,

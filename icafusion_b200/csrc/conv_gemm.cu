@@ -352,7 +352,7 @@ static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io
   P.M = int(M); P.N = g->Cout; P.K = g->kh * g->kw * g->Cin; P.k_pad = g->k_pad;
   P.B = g->B; P.Hi = g->Hi; P.Wi = g->Wi; P.Cin = g->Cin; P.Ho = g->Ho; P.Wo = g->Wo;
   P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad = g->pad; P.act = g->act; P.epi = g->epi;
-  P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.stages = 2; P.splits = 1; P.cblk = 64; P.dbg = g_dbg;
+  P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.stages = 2; P.splits = 1; P.cblk = 64; P.halo = 0; P.dbg = g_dbg;
   for (int i = 0; i < 2; ++i) {
     const icaf_conv_io& s = io[i < n_io ? i : 0];
     bool need_res = g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES);
@@ -499,6 +499,12 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   // layers are bound by chip-wide L2->SM bandwidth, so a partly filled last wave just streams the same bytes through
   // fewer, faster CTAs; the second launch only added its fixed cost: 65 -> 87 us on the 320-tile P4 3x3 layer.)
   if (pair_wanted(bn)) {
+    // 3x3 / stride 1 layers on 16 x 8 pixel tiles: every activation row is fetched three times instead of nine (conv_pair.cu)
+    static const bool halo_on = []() { const char* e = getenv("ICAF_HALO"); return !(e && e[0] == '0'); }();
+    if (halo_on && P.a_mode == A_TMA4D && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && g->Cin % 64 == 0 &&
+        g->Wo % 8 == 0 && g->Ho % 16 == 0) {
+      P.halo = 1; P.tw = 8; P.th = 16; P.tiles_x = g->Wo / 8; P.tiles_y = g->Ho / 16;
+    }
     switch (bn) {
       case 256: return launch_pair<256>(P, w, g, n_io, st);
       case 128: return launch_pair<128>(P, w, g, n_io, st);

@@ -14,6 +14,13 @@
 //   tfull[b]  both: same multicast commit after the last K block of a tile.
 //   tempty[b] leader only: 16 arrivals = one per epilogue warp of the buffer, both CTAs (the peer's arrive remotely).
 // Everything else (tile loop, four epilogue groups, bias staging, 256-bit stores) is conv_persist.cu's.
+//
+// Halo mode (P.halo, 3x3 / stride 1 / pad 1 layers, tile = 16 rows x 8 pixels): the nine taps of a 64-channel block read
+// the same (16+2) x (8+2) pixel patch.  Instead of nine shifted TMA boxes, three x-shifted copies of the 18-row patch are
+// loaded (box 64 ch x 8 px x 18 rows at x0-1+kx); a copy is 18 swizzle atoms of 8 pixels x 128 B, so the tap (ky, kx) is
+// the plain K-major operand that starts ky atoms (ky * 1024 B) into copy kx -- a 1024-byte aligned descriptor, nothing
+// exotic.  K loop: channel block -> kx (one copy) -> ky (one filter half-tile per tap); two smem rings (copies, filter
+// tiles).  Activation bytes per SM drop 2.7x (9 x 16 KB -> 3 x 18 KB per channel block).
 // 576 threads per CTA: warps 0-15 epilogue, warp 16 MMA issuer (leader) + TMEM allocator (both), warp 17 TMA producer.
 #include <cstring>
 
@@ -25,17 +32,25 @@ constexpr int kQEpiWarps = 16;
 constexpr int kQThreads = (kQEpiWarps + 2) * 32;
 constexpr int kQMaxStages = 10;
 constexpr int kQABytes = BM * BK * 2;         // this CTA's 128 activation rows
+constexpr int kQHaloABytes = 18 * 8 * 128;    // halo mode: (16 + 2) rows x 8 pixels x 64 channels of one x-shifted copy
 
 template <int BN>                             // BN = tile width = UMMA N (256, 128 or 64)
 struct QSmem {
   static constexpr int kBBytes = (BN / 2) * BK * 2;   // this CTA's half of the filter tile
   static constexpr int kStageBytes = kQABytes + kBBytes;
   static constexpr int kCW = BN / 2;                  // columns per epilogue group
-  static constexpr int kTail = 256 + 4 * 2 * kCW * 4 + 1024;
+  static constexpr int kBarBytes = 512;               // barrier block (see the index map in the kernel)
+  static constexpr int kTail = kBarBytes + 4 * 2 * kCW * 4 + 1024;
   static constexpr int kStagesFit = (227 * 1024 - kTail) / kStageBytes;
   static constexpr int kStages = kStagesFit > kQMaxStages ? kQMaxStages : kStagesFit;
   static constexpr int kSmem = kStages * kStageBytes + kTail;
   static constexpr int kTmemCols = 2 * BN;
+  // halo mode (3x3 / stride 1): a ring of activation copies and a ring of per-tap filter half-tiles
+  static constexpr int kHaloNA = 4;
+  static constexpr int kHaloNBFit = (227 * 1024 - kTail - kHaloNA * kQHaloABytes) / kBBytes;
+  static constexpr int kHaloNB = kHaloNBFit > kQMaxStages ? kQMaxStages : kHaloNBFit;
+  static constexpr int kHaloRing = kHaloNA * kQHaloABytes + kHaloNB * kBBytes;
+  static constexpr int kHaloSmem = kHaloRing + kTail;
 };
 
 // ---- cta_group::2 PTX (same encodings CUTLASS' SM100_TMA_2SM_LOAD / umma_arrive_multicast_2x1SM use)
@@ -140,13 +155,18 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   constexpr int kQBBytes = L::kBBytes;
   constexpr int kQCW = L::kCW;
   constexpr int kQBN = BN;
-  const uint32_t bar_off = uint32_t(kQStages) * kQStageBytes;
+  const bool halo = P.halo != 0;
+  const uint32_t bar_off = halo ? uint32_t(L::kHaloRing) : uint32_t(kQStages) * kQStageBytes;
   const uint32_t bar_base = smem_base + bar_off;
+  // barrier block (8-byte slots): 0-9 full / copy full, 10-19 empty / copy empty, 20-29 filter full, 30-39 filter empty
+  // (halo mode), 40-41 accumulator full, 42-43 accumulator empty, 44 TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kQStages + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kQStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kQStages + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kQStages + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (10 + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (20 + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (30 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (40 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (42 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 44;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   pdl_launch_dependents();
@@ -159,9 +179,11 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   const int a_mode = P.a_mode;
 
   if (tid == 0) {
-    for (int s = 0; s < kQStages; ++s) {
+    for (int s = 0; s < kQMaxStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
@@ -182,7 +204,7 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   cluster_wait();
   tc_fence_after();
   pdl_wait();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * kQStages + 4));
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * 44);
 
   if (warp < kQEpiWarps) {
     // ------------------------------------------------------------------ epilogue groups (both CTAs, own 128 rows)
@@ -196,7 +218,7 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
     const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : ((P.epi & ICAF_EPI_ADD_RES) ? 1 : 0);
     const int mode_act = P.act * 3 + mode;
     const bool row_bias = (P.epi & ICAF_EPI_BIAS_ROW) != 0;
-    float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256) + eg * 2 * kQCW;
+    float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + L::kBarBytes) + eg * 2 * kQCW;
     const uint32_t tempty_leader = map_to_cta(tempty_bar(buf), 0);
     auto bias_of = [&](int t) -> float {
       if (t >= total_pairs || gt >= kQCW) return 0.f;
@@ -257,12 +279,42 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       constexpr uint32_t idesc = umma_idesc_f16(2 * BM, kQBN);
       int s = 0;
       uint32_t ph = 0;
+      int ha = 0, hb = 0;                                    // halo mode: copy ring / filter ring positions and phases
+      uint32_t hpa = 0, hpb = 0;
       int i = 0;
       for (int t = cluster_id; t < total_pairs; t += n_clusters, ++i) {
         const int buf = i & 1;
         mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);      // both CTAs' epilogue groups have drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(buf * kQBN);
+        if (halo) {
+          const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
+          bool first = true;
+          for (int cbk = 0; cbk < P.Cin / BK; ++cbk) {
+            for (int kx = 0; kx < 3; ++kx) {
+              mbar_wait(full_bar(ha), hpa);                  // copy kx of this channel block (both CTAs)
+              for (int ky = 0; ky < 3; ++ky) {
+                mbar_wait(bfull_bar(hb), hpb);               // filter half-tiles of tap (ky, kx)
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint64_t ad = umma_desc_sw128(smem_base + ha * kQHaloABytes + ky * 1024);
+                  const uint64_t bd = umma_desc_sw128(b_ring + hb * kQBBytes);
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma2_f16_ss(tmem_d, ad + uint64_t(2 * k), bd + uint64_t(2 * k), idesc, !first || k != 0);
+                  umma2_commit_both(bempty_bar(hb));
+                  if (ky == 2) umma2_commit_both(empty_bar(ha));
+                  if (ky == 2 && kx == 2 && cbk == P.Cin / BK - 1) umma2_commit_both(tfull_bar(buf));
+                }
+                __syncwarp();
+                first = false;
+                if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
+              }
+              if (++ha == L::kHaloNA) { ha = 0; hpa ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(s), ph);                        // both CTAs' operands of this stage have landed
           tc_fence_after();
@@ -288,10 +340,31 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       const uint32_t stage_tx = 2u * (uint32_t(kQBBytes) + a_bytes);   // both CTAs' loads complete on the leader's barrier
       int s = 0;
       uint32_t ph = 0;
+      int ha = 0, hb = 0;
+      uint32_t hpa = 0, hpb = 0;
       for (int t = cluster_id; t < total_pairs; t += n_clusters) {
         const PairTile c = pair_tile(P, t, rank, m_pairs, n_tiles, BN);
         const CUtensorMap* mw = c.z ? &maps.w[1] : &maps.w[0];
         const CUtensorMap* ma = c.z ? &maps.a[1] : &maps.a[0];
+        if (halo) {
+          const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
+          for (int cbk = 0; cbk < P.Cin / BK; ++cbk) {
+            for (int kx = 0; kx < 3; ++kx) {
+              mbar_wait(empty_bar(ha), hpa ^ 1);
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(ha), 2u * kQHaloABytes);
+              tma2_load_4d(smem_base + ha * kQHaloABytes, ma, map_to_cta(full_bar(ha), 0), cbk * BK, c.ox0 - 1 + kx, c.oy0 - 1, c.tb);
+              if (++ha == L::kHaloNA) { ha = 0; hpa ^= 1; }
+              for (int ky = 0; ky < 3; ++ky) {
+                mbar_wait(bempty_bar(hb), hpb ^ 1);
+                if (rank == 0) mbar_arrive_expect_tx(bfull_bar(hb), 2u * kQBBytes);
+                tma2_load_2d(b_ring + hb * kQBBytes, mw, map_to_cta(bfull_bar(hb), 0), (ky * 3 + kx) * P.Cin + cbk * BK,
+                             c.n0 + rank * (kQBN / 2));
+                if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
+              }
+            }
+          }
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * kQStageBytes;
@@ -330,7 +403,8 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
   constexpr int kQSmem = L::kSmem;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kQSmem > L::kHaloSmem ? kQSmem : L::kHaloSmem);
     if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute (pair)");
     configured = true;
   }
@@ -348,6 +422,8 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
     const ConvProblem& pr = P.p[i];
     if (P.a_mode == A_TMA2D)
       rc = encode_tmap_2d(&maps.a[i], pr.x, (uint64_t)P.Cin, (uint64_t)P.M, (uint64_t)pr.x_ld * 2, BK, BM);
+    else if (P.halo)
+      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, 8, 18, 1, 1);   // one x-shifted copy: 8 px x (16+2) rows
     else
       rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, P.tw * P.stride, P.th * P.stride, P.stride, P.stride);
     if (rc) return rc;
@@ -356,7 +432,7 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
   const int max_clusters = sm_count_cached() / 2;
   const int waves = (total + max_clusters - 1) / max_clusters;
   const int clusters = (total + waves - 1) / waves;
-  launch_kc(conv_gemm_pair_kernel<BN>, dim3(2 * clusters), dim3(kQThreads), (size_t)kQSmem, st, 2u, P, maps, total, m_tiles, m_pairs, n_tiles);
+  launch_kc(conv_gemm_pair_kernel<BN>, dim3(2 * clusters), dim3(kQThreads), (size_t)(P.halo ? L::kHaloSmem : kQSmem), st, 2u, P, maps, total, m_tiles, m_pairs, n_tiles);
   return check_launch("conv2d_fwd(pair)");
 }
 
