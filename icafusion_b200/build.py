@@ -39,6 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     objs = []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("ICAF_PROBE") == "1":      # diagnostic build for tools/conv_probe.py (stage switches in the conv kernels)
+        flags.append("-DICAF_PROBE")
     procs = []
     for s in SOURCES:
         obj = os.path.join(CSRC, s[:-3] + ".o")

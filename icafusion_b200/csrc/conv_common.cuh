@@ -17,6 +17,13 @@ struct ConvProblem {
   const float* alpha; const float* beta;
   long long x_ld, res_ld, y_ld;
 };
+// ICAF_DBG(P, bit): compile-time false unless the library is built with -DICAF_PROBE (ICAF_PROBE=1 python -m icafusion_b200.build)
+#ifdef ICAF_PROBE
+#define ICAF_DBG(P, bit) (((P).dbg & (bit)) != 0)
+#else
+#define ICAF_DBG(P, bit) false
+#endif
+
 struct ConvParams {
   ConvProblem p[2];
   int M, N, K, k_pad;
@@ -27,7 +34,8 @@ struct ConvParams {
   int splits;                             // split-K factor = cluster size along x (1 = no cluster); partial sums meet in DSMEM
   int cblk;                               // A_TMA4D: channels per TMA box = min(Cin, 64); < 64 only in the persistent kernel
   int halo;                               // conv_pair.cu: 3x3/s1 layers stage three x-shifted (th+2)-row copies per channel block
-  int dbg;                                // PROBE ONLY (icaf_debug_set): 1 no stores, 2 no activation, 8 no A loads, 16 no B loads, 32 no MMA
+  int dbg;                                // probe builds (-DICAF_PROBE, tools/conv_probe.py): 1 no stores, 2 no activation,
+                                          // 8 no A loads, 16 no B loads, 32 no MMA; always 0 in the shipped library
 };
 struct ConvMaps {          // TMA descriptors, passed by value as a __grid_constant__ kernel parameter
   CUtensorMap w[2];

@@ -336,7 +336,11 @@ __global__ void conv_gemm_simt_kernel(const SimtParams S) {
   pr.y[size_t(m) * pr.y_ld + n] = __float2half_rn(acc);
 }
 
-static int g_dbg = 0;
+#ifdef ICAF_PROBE
+static int g_dbg = 0, g_dbg_bn = 0;       // probe builds only: see icaf_debug_set below
+#else
+constexpr int g_dbg = 0, g_dbg_bn = 0;
+#endif
 static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, ConvParams& P, const __half* (&w)[2]) {
   if (!g || !io || n_io < 1 || n_io > 2) return set_error(ICAF_ERR_BAD_ARG, "conv2d: need 1 or 2 problems");
   if (!(g->Cin == 4 || g->Cin % 8 == 0)) return set_error(ICAF_ERR_UNSUPPORTED, "conv2d: Cin must be 4 or a multiple of 8");
@@ -455,8 +459,10 @@ static int launch_tc(ConvParams& P, const __half* const (&w)[2], const icaf_conv
 
 using namespace icaf;
 
-static int g_dbg_bn = 0;
-extern "C" void icaf_debug_set(int dbg, int bn) { g_dbg = dbg; g_dbg_bn = bn; }   // PROBE ONLY, not part of the ABI
+#ifdef ICAF_PROBE
+// Probe builds only (not part of the ABI, absent from the shipped library): kernel-stage switches + forced tile width.
+extern "C" void icaf_debug_set(int dbg, int bn) { g_dbg = dbg; g_dbg_bn = bn; }
+#endif
 
 extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream) {
   ConvParams P;
@@ -501,9 +507,11 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   if (pair_wanted(bn)) {
     // 3x3 / stride 1 layers on 16 x 8 pixel tiles: every activation row is fetched three times instead of nine (conv_pair.cu)
     static const bool halo_on = []() { const char* e = getenv("ICAF_HALO"); return !(e && e[0] == '0'); }();
-    if (halo_on && P.a_mode == A_TMA4D && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && g->Cin % 64 == 0 &&
-        g->Wo % 8 == 0 && g->Ho % 16 == 0) {
-      P.halo = 1; P.tw = 8; P.th = 16; P.tiles_x = g->Wo / 8; P.tiles_y = g->Ho / 16;
+    if (halo_on && P.a_mode == A_TMA4D && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && g->Cin % 64 == 0) {
+      const int tx = (g->Wo + 7) / 8, ty = (g->Ho + 15) / 16;     // tiles may hang over the right / bottom edge (P5: 16 x 20)
+      if (double(g->Wo) * g->Ho >= 0.6 * (double(tx) * ty * 128.0)) {
+        P.halo = 1; P.tw = 8; P.th = 16; P.tiles_x = tx; P.tiles_y = ty;
+      }
     }
     switch (bn) {
       case 256: return launch_pair<256>(P, w, g, n_io, st);

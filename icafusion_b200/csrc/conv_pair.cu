@@ -241,7 +241,7 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       bool mvalid;
       if (a_mode == A_TMA4D) {
         m = (c.tb * P.Ho + c.oy0 + ry) * P.Wo + c.ox0 + rx;
-        mvalid = c.mtile < m_tiles && ry < P.th && c.oy0 + ry < P.Ho;
+        mvalid = c.mtile < m_tiles && ry < P.th && c.oy0 + ry < P.Ho && c.ox0 + rx < P.Wo;   // halo tiles may hang over in x too
       } else {
         m = c.m0 + gt;
         mvalid = m < P.M;

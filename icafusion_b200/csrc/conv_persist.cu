@@ -170,8 +170,8 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
       const int ry = a_mode == A_TMA4D ? gt / P.tw : 0;
       const int rx = a_mode == A_TMA4D ? gt - ry * P.tw : 0;
       const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : ((P.epi & ICAF_EPI_ADD_RES) ? 1 : 0);
-      const int mode_act = (P.dbg & 2) ? mode : P.act * 3 + mode;
-      const bool dst = !(P.dbg & 1);
+      const int mode_act = ICAF_DBG(P, 2) ? mode : P.act * 3 + mode;
+      const bool dst = !ICAF_DBG(P, 1);
       const bool row_bias = (P.epi & ICAF_EPI_BIAS_ROW) != 0;
       float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256) + eg * 2 * kCW;   // [tile parity][kCW]
       // this thread's bias column of a tile (fetched one tile ahead, so its latency hides behind the current tile)
@@ -247,7 +247,7 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         if (elect_one()) {
           const uint32_t sa = smem_base + s * L::kStageBytes;
           const uint64_t bd = umma_desc_sw128(sa + L::kABytes);
-          if (P.dbg & 32) {
+          if (ICAF_DBG(P, 32)) {
           } else if (cblk == 64) {
             const uint64_t ad = umma_desc_sw128(sa);
 #pragma unroll
@@ -300,7 +300,7 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
             if (++s == kStages) { s = 0; ph ^= 1; }
             continue;
           }
-          const bool ldA = !(P.dbg & 8), ldB = !(P.dbg & 16);
+          const bool ldA = !ICAF_DBG(P, 8), ldB = !ICAF_DBG(P, 16);
           mbar_arrive_expect_tx(full_bar(s), (ldB ? L::kBBytes : 0u) + (ldA ? a_bytes : 0u));
           if (ldB) tma_load_2d(sa + L::kABytes, mw, full_bar(s), kb * BK, c.n0);
           if (!ldA) {

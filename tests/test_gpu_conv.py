@@ -60,6 +60,7 @@ CASES = [
     (32, 128, 32, 40, 256, 3, 1, 1, 1),   # CTA-pair kernel, 4-D TMA (16x8 tiles), 320 M tiles = 160 pairs
     (1, 64, 301, 128, 512, 1, 1, 0, 1),   # CTA-pair kernel, odd M-tile count (301): the last pair's peer tile is all padding
     (99, 64, 16, 24, 256, 3, 1, 1, 1),    # CTA-pair kernel, 4-D TMA, 297 M tiles: peer tile past the last image
+    (16, 512, 16, 20, 512, 3, 1, 1, 1),   # yolov5l P5 at batch 16: CTA pairs + halo copies, 16x8 tiles hang over the 20-wide map
 ]
 
 

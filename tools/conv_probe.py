@@ -1,4 +1,5 @@
-"""Per-geometry timing of icaf_conv2d_fwd with the probe switches of the persistent kernel (tools only).
+"""Per-geometry timing of icaf_conv2d_fwd with the probe switches of the persistent kernel (tools only; needs a probe
+build of the library: ICAF_PROBE=1 python -m icafusion_b200.build --force -- the shipped build has no such switches).
     python tools/conv_probe.py [--out gpurun_out/conv_probe.json]
 Every geometry is timed behind an L2 flush with CUDA events (median of 7), for dbg in DBG and forced BN in BNS."""
 import argparse
@@ -37,6 +38,8 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = _lib.lib()
+    if not hasattr(lib, "icaf_debug_set"):
+        sys.exit("conv_probe needs a probe build: ICAF_PROBE=1 python -m icafusion_b200.build --force")
     lib.icaf_debug_set.argtypes = [C.c_int, C.c_int]
     lib.icaf_debug_set.restype = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -5,4 +5,4 @@ timeout 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -x --timeout 400 >
 if [ $rc -ne 0 ]; then exit 0; fi
 timeout 600 python -m pytest tests -q -m gpu -x --timeout 400 --deselect tests/test_gpu_conv.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/pytest_gpu.log
 python bench.py --workload yolov5l_b16 --secondary none --steps 20 --warmup 5 --layer-profile gpurun_out/layers_l_b16.csv > gpurun_out/bench_l_b16.json 2> gpurun_out/bench_l_b16.err; cut -c1-250 gpurun_out/bench_l_b16.json; tail -n 3 gpurun_out/bench_l_b16.err
-ICAF_HALO=0 python bench.py --workload yolov5l_b16 --secondary none --steps 20 --warmup 5 --layer-profile gpurun_out/layers_l_b16_nohalo.csv > gpurun_out/bench_l_b16_nohalo.json 2> gpurun_out/bench_l_b16_nohalo.err; cut -c1-250 gpurun_out/bench_l_b16_nohalo.json
+
