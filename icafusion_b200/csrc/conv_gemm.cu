@@ -504,9 +504,18 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   // (A wave-tail scheme -- peel total % SMs tiles off into a split-K cluster launch -- was measured and dropped: these
   // layers are bound by chip-wide L2->SM bandwidth, so a partly filled last wave just streams the same bytes through
   // fewer, faster CTAs; the second launch only added its fixed cost: 65 -> 87 us on the 320-tile P4 3x3 layer.)
+  static const bool halo_on = []() { const char* e = getenv("ICAF_HALO"); return !(e && e[0] == '0'); }();
+  if (pair_env && halo_on && P.a_mode == A_TMA4D && P.cblk < 64 && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1) {
+    // 16- / 32-channel 3x3 layers (the image stem over the space-to-depth frame): CTA pairs + halo copies, 64-wide tiles
+    const int tx = (g->Wo + 7) / 8, ty = (g->Ho + 15) / 16;
+    const long long pairs = (long long)g->B * tx * ty * ((P.N + 63) / 64) * n_io / 2;
+    if (double(g->Wo) * g->Ho >= 0.6 * (double(tx) * ty * 128.0) && (pair_env == 2 || pairs >= sms / 2)) {
+      P.halo = 2; P.tw = 8; P.th = 16; P.tiles_x = tx; P.tiles_y = ty;
+      return launch_pair<64>(P, w, g, n_io, st);
+    }
+  }
   if (pair_wanted(bn)) {
     // 3x3 / stride 1 layers on 16 x 8 pixel tiles: every activation row is fetched three times instead of nine (conv_pair.cu)
-    static const bool halo_on = []() { const char* e = getenv("ICAF_HALO"); return !(e && e[0] == '0'); }();
     if (halo_on && P.a_mode == A_TMA4D && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && g->Cin % 64 == 0) {
       const int tx = (g->Wo + 7) / 8, ty = (g->Ho + 15) / 16;     // tiles may hang over the right / bottom edge (P5: 16 x 20)
       if (double(g->Wo) * g->Ho >= 0.6 * (double(tx) * ty * 128.0)) {

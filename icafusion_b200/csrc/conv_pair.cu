@@ -21,6 +21,10 @@
 // the plain K-major operand that starts ky atoms (ky * 1024 B) into copy kx -- a 1024-byte aligned descriptor, nothing
 // exotic.  K loop: channel block -> kx (one copy) -> ky (one filter half-tile per tap); two smem rings (copies, filter
 // tiles).  Activation bytes per SM drop 2.7x (9 x 16 KB -> 3 x 18 KB per channel block).
+// Halo mode 2 is the same idea for a 16- / 32-channel map (the image stem over the space-to-depth frame): the whole K
+// extent is one channel block, the three copies (32- / 64-byte rows, matching swizzle) share one ring slot, the filter
+// streams in ordinary 64-wide K blocks and every 16-element K step addresses its tap inside the right copy.  What it buys
+// there is TMA requests, not bytes: 3 x 144 rows per tile instead of 9 x 128 (the stem is bound by the request rate).
 // 576 threads per CTA: warps 0-15 epilogue, warp 16 MMA issuer (leader) + TMEM allocator (both), warp 17 TMA producer.
 #include <cstring>
 
@@ -155,7 +159,11 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   constexpr int kQBBytes = L::kBBytes;
   constexpr int kQCW = L::kCW;
   constexpr int kQBN = BN;
-  const bool halo = P.halo != 0;
+  const int halo = P.halo;                            // 0 tap boxes, 1 x-shifted copies (Cin % 64 == 0), 2 copies of a 16 / 32 channel map
+  const uint32_t cb2 = uint32_t(P.cblk) * 2u;          // halo 2: bytes per pixel row of a copy
+  const uint32_t copy2 = 144u * cb2;                  //         one x-shifted copy, (16+2) x 8 pixels
+  const uint32_t set2 = (3u * copy2 + 1023u) & ~1023u; //        ring slot = the three copies of a tile
+  const int na2 = P.cblk <= 16 ? 4 : 2;
   const uint32_t bar_off = halo ? uint32_t(L::kHaloRing) : uint32_t(kQStages) * kQStageBytes;
   const uint32_t bar_base = smem_base + bar_off;
   // barrier block (8-byte slots): 0-9 full / copy full, 10-19 empty / copy empty, 20-29 filter full, 30-39 filter empty
@@ -287,6 +295,36 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
         mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);      // both CTAs' epilogue groups have drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(buf * kQBN);
+        if (halo == 2) {
+          // small-Cin map (image stem over the space-to-depth frame): one channel block, all three copies in one ring slot;
+          // the filter arrives in ordinary 64-wide K blocks (4 or 2 taps each) and every 16-element K step picks its tap's copy
+          const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
+          mbar_wait(full_bar(ha), hpa);
+          bool first = true;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(bfull_bar(hb), hpb);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t set_base = smem_base + ha * set2;
+              const uint64_t bd = umma_desc_sw128(b_ring + hb * kQBBytes);
+              for (int e = 0; e < BK && kb * BK + e < P.K; e += 16) {
+                const int kabs = kb * BK + e;
+                const int tap = kabs / P.Cin, coff = kabs - tap * P.Cin;
+                const int ky = tap / 3, kx = tap - 3 * ky;
+                const uint64_t ad = umma_desc_kmajor(set_base + kx * copy2 + ky * 8u * cb2 + uint32_t(coff) * 2u, cb2);
+                umma2_f16_ss(tmem_d, ad, bd + uint64_t(2 * (e / 16)), idesc, !first);
+                first = false;
+              }
+              umma2_commit_both(bempty_bar(hb));
+              if (kb == nkb - 1) { umma2_commit_both(empty_bar(ha)); umma2_commit_both(tfull_bar(buf)); }
+            }
+            __syncwarp();
+            first = false;
+            if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
+          }
+          if (++ha == na2) { ha = 0; hpa ^= 1; }
+          continue;
+        }
         if (halo) {
           const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
           bool first = true;
@@ -346,6 +384,21 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
         const PairTile c = pair_tile(P, t, rank, m_pairs, n_tiles, BN);
         const CUtensorMap* mw = c.z ? &maps.w[1] : &maps.w[0];
         const CUtensorMap* ma = c.z ? &maps.a[1] : &maps.a[0];
+        if (halo == 2) {
+          const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
+          mbar_wait(empty_bar(ha), hpa ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(ha), 2u * 3u * copy2);
+          for (int kx = 0; kx < 3; ++kx)
+            tma2_load_4d(smem_base + ha * set2 + kx * copy2, ma, map_to_cta(full_bar(ha), 0), 0, c.ox0 - 1 + kx, c.oy0 - 1, c.tb);
+          if (++ha == na2) { ha = 0; hpa ^= 1; }
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(bempty_bar(hb), hpb ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(bfull_bar(hb), 2u * kQBBytes);
+            tma2_load_2d(b_ring + hb * kQBBytes, mw, map_to_cta(bfull_bar(hb), 0), kb * BK, c.n0 + rank * (kQBN / 2));
+            if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
+          }
+          continue;
+        }
         if (halo) {
           const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
           for (int cbk = 0; cbk < P.Cin / BK; ++cbk) {
@@ -422,8 +475,8 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
     const ConvProblem& pr = P.p[i];
     if (P.a_mode == A_TMA2D)
       rc = encode_tmap_2d(&maps.a[i], pr.x, (uint64_t)P.Cin, (uint64_t)P.M, (uint64_t)pr.x_ld * 2, BK, BM);
-    else if (P.halo)
-      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, 8, 18, 1, 1);   // one x-shifted copy: 8 px x (16+2) rows
+    else if (P.halo)   // one x-shifted copy: 8 px x (16+2) rows of 64 (or all 16 / 32) channels
+      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, P.halo == 2 ? (uint32_t)P.cblk : (uint32_t)BK, 8, 18, 1, 1);
     else
       rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, P.tw * P.stride, P.th * P.stride, P.stride, P.stride);
     if (rc) return rc;
