@@ -12,7 +12,9 @@
 //             (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address).
 //   empty[s]  both: tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11) from the leader's MMA thread.
 //   tfull[b]  both: same multicast commit after the last K block of a tile.
-//   tempty[b] leader only: 16 arrivals = one per epilogue warp of the buffer, both CTAs (the peer's arrive remotely).
+//   tempty[b] leader only: one arrival per epilogue warp of the buffer, both CTAs (the peer's arrive remotely).
+//   TMEM holds four accumulator buffers for BN <= 128 (two for BN = 256), so the cluster-scope hand-shakes of up to four
+//   tiles overlap.
 // Everything else (tile loop, four epilogue groups, bias staging, 256-bit stores) is conv_persist.cu's.
 //
 // Halo mode (P.halo, 3x3 / stride 1 / pad 1 layers, tile = 16 rows x 8 pixels): the nine taps of a 64-channel block read
@@ -42,13 +44,15 @@ template <int BN>                             // BN = tile width = UMMA N (256, 
 struct QSmem {
   static constexpr int kBBytes = (BN / 2) * BK * 2;   // this CTA's half of the filter tile
   static constexpr int kStageBytes = kQABytes + kBBytes;
-  static constexpr int kCW = BN / 2;                  // columns per epilogue group
+  static constexpr int kBufs = BN <= 128 ? 4 : 2;     // accumulator buffers in TMEM
+  static constexpr int kHalves = 4 / kBufs;           // epilogue groups per buffer (four groups in total)
+  static constexpr int kCW = BN / kHalves;            // columns per epilogue group
   static constexpr int kBarBytes = 512;               // barrier block (see the index map in the kernel)
   static constexpr int kTail = kBarBytes + 4 * 2 * kCW * 4 + 1024;
   static constexpr int kStagesFit = (227 * 1024 - kTail) / kStageBytes;
   static constexpr int kStages = kStagesFit > kQMaxStages ? kQMaxStages : kStagesFit;
   static constexpr int kSmem = kStages * kStageBytes + kTail;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTmemCols = kBufs * BN;
   // halo mode (3x3 / stride 1): a ring of activation copies and a ring of per-tap filter half-tiles
   static constexpr int kHaloNA = 4;
   static constexpr int kHaloNBFit = (227 * 1024 - kTail - kHaloNA * kQHaloABytes) / kBBytes;
@@ -158,6 +162,7 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   constexpr int kQStageBytes = L::kStageBytes;
   constexpr int kQBBytes = L::kBBytes;
   constexpr int kQCW = L::kCW;
+  constexpr int kBufs = L::kBufs, kHalves = L::kHalves;
   constexpr int kQBN = BN;
   const int halo = P.halo;                            // 0 tap boxes, 1 x-shifted copies (Cin % 64 == 0), 2 copies of a 16 / 32 channel map
   const uint32_t cb2 = uint32_t(P.cblk) * 2u;          // halo 2: bytes per pixel row of a copy
@@ -167,14 +172,14 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   const uint32_t bar_off = halo ? uint32_t(L::kHaloRing) : uint32_t(kQStages) * kQStageBytes;
   const uint32_t bar_base = smem_base + bar_off;
   // barrier block (8-byte slots): 0-9 full / copy full, 10-19 empty / copy empty, 20-29 filter full, 30-39 filter empty
-  // (halo mode), 40-41 accumulator full, 42-43 accumulator empty, 44 TMEM base address
+  // (halo mode), 40-43 accumulator full, 44-47 accumulator empty, 48 TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (10 + s); };
   auto bfull_bar = [&](int s) { return bar_base + 8u * (20 + s); };
   auto bempty_bar = [&](int s) { return bar_base + 8u * (30 + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (40 + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (42 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * 44;
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (44 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 48;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   pdl_launch_dependents();
@@ -193,9 +198,9 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       mbar_init(bfull_bar(s), 1);
       mbar_init(bempty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kBufs; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 16);
+      mbar_init(tempty_bar(b), 8 * kHalves);      // one arrival per epilogue warp of the buffer, both CTAs
     }
     fence_mbar_init();
   }
@@ -212,13 +217,13 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   cluster_wait();
   tc_fence_after();
   pdl_wait();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * 44);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * 48);
 
   if (warp < kQEpiWarps) {
     // ------------------------------------------------------------------ epilogue groups (both CTAs, own 128 rows)
     const int eg = warp >> 2;
-    const int buf = eg >> 1;
-    const int half = eg & 1;
+    const int buf = eg / kHalves;
+    const int half = eg % kHalves;
     const int gt = tid & 127;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const int ry = a_mode == A_TMA4D ? gt / P.tw : 0;
@@ -235,7 +240,7 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       const int n = q.n0 + half * kQCW + gt;
       return (pb && !row_bias && n < P.N) ? __ldg(pb + n) : 0.f;
     };
-    const int step = 2 * n_clusters;
+    const int step = kBufs * n_clusters;
     int t = cluster_id + buf * n_clusters;
     float bnext = bias_of(t);
     for (int it = 0; t < total_pairs; t += step, ++it) {
@@ -291,8 +296,8 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       uint32_t hpa = 0, hpb = 0;
       int i = 0;
       for (int t = cluster_id; t < total_pairs; t += n_clusters, ++i) {
-        const int buf = i & 1;
-        mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);      // both CTAs' epilogue groups have drained this buffer
+        const int buf = i % kBufs;
+        mbar_wait(tempty_bar(buf), ((i / kBufs) & 1) ^ 1);      // both CTAs' epilogue groups have drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(buf * kQBN);
         if (halo == 2) {

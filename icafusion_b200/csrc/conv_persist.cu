@@ -3,17 +3,17 @@
 // One CTA per SM loops over output tiles (static round-robin).  The three pipelines of conv_gemm.cu are kept but
 // decoupled across tiles so that every unit stays busy:
 //   * the TMA producer runs ahead through the tile sequence, bounded only by the smem ring;
-//   * the MMA warp accumulates tile i into TMEM buffer (i & 1) while
-//   * the two epilogue groups of that buffer -- four warps each, one per half of the tile's columns -- drain the
-//     previous tile of the buffer (bias, SiLU/GELU, residual, fp16 store).  Four groups in total, so two tiles can be
-//     in their epilogue while a third is in the tensor core, and every tile's epilogue is spread over 256 threads:
+//   * the MMA warp accumulates tile i into TMEM buffer (i mod kBufs; four buffers for BN <= 128, two for BN = 256) while
+//   * the epilogue group(s) of that buffer -- four warps each; BN = 256 splits a tile's columns over two groups -- drain the
+//     previous tile of the buffer (bias, SiLU/GELU, residual, fp16 store).  Four groups in total, so up to four tiles
+//     are between MMA and store at once and the buffer hand-shake latency stays off the critical path:
 //     the short-K layers are bound by the latency of that chain, not by a throughput limit (tools/conv_probe.py).
 // Per-tile bookkeeping is kept off that chain: tile coordinates advance as a mixed-radix counter (no divisions), the
 // bias is read straight from global memory (L1-resident across tiles), TMEM loads are double-buffered against the math,
 // rows are written with 256-bit stores (full L2 sectors).
 // 576 threads: warps 0-15 epilogue groups 0-3 (group = 2*buffer + column half), warp 16 MMA issuer + TMEM allocator,
 // warp 17 TMA producer.  Both operands arrive by TMA; A_GATHER layers stay on conv_gemm_tc_kernel.
-// TMEM: 2 x BN fp32 columns.  Shared memory: the whole SM (ring of up to 10 stages).
+// TMEM: kBufs x BN fp32 columns.  Shared memory: the whole SM (ring of up to 10 stages).
 #include <cstring>
 
 #include "conv_common.cuh"
@@ -29,9 +29,12 @@ struct PSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  // [ring] [barriers 256 B] [bias: 4 groups x 2 tiles x BN/2 fp32] ; + 1024 B alignment slack
-  static constexpr int kTailBytes = 256 + 4 * 2 * (BN >= 64 ? BN / 2 : BN) * 4 + 1024;
+  static constexpr int kBufs = BN <= 128 ? 4 : 2;     // accumulator buffers in TMEM (tiles in flight between MMA and epilogue)
+  static constexpr int kHalves = 4 / kBufs;           // epilogue groups per buffer: four groups in total
+  static constexpr int kCW = BN / kHalves;            // columns per group
+  static constexpr int kTmemCols = kBufs * BN;
+  // [ring] [barriers 256 B] [bias: 4 groups x 2 tiles x kCW fp32] ; + 1024 B alignment slack
+  static constexpr int kTailBytes = 256 + 4 * 2 * kCW * 4 + 1024;
   static int total(int stages) { return stages * kStageBytes + kTailBytes; }
 };
 
@@ -115,16 +118,15 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   using L = PSmem<BN>;
-  constexpr int kHalves = BN >= 64 ? 2 : 1;      // epilogue groups per accumulator buffer
-  constexpr int kCW = BN / kHalves;              // columns per group
+  constexpr int kBufs = L::kBufs, kHalves = L::kHalves, kCW = L::kCW;
   const int kStages = P.stages;
   const uint32_t bar_off = uint32_t(kStages) * L::kStageBytes;
   const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kPMaxStages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kPMaxStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kPMaxStages + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kPMaxStages + 4);
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kPMaxStages + 4 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kPMaxStages + 8);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   pdl_launch_dependents();
@@ -140,7 +142,7 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kBufs; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 4 * kHalves);     // one elected arrival per epilogue warp of the buffer
     }
@@ -157,14 +159,14 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
   __syncthreads();
   tc_fence_after();
   pdl_wait();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * kPMaxStages + 4));
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * kPMaxStages + 8));
 
   if (warp < kPEpiWarps) {
     // ------------------------------------------------------------------ epilogue groups
     const int eg = warp >> 2;                      // group
-    const int buf = eg >> 1;                       // accumulator buffer
-    const int half = eg & 1;                       // column half of the tile
-    if (half < kHalves) {
+    const int buf = eg / kHalves;                  // accumulator buffer
+    const int half = eg % kHalves;                 // column half of the tile (BN = 256 only)
+    {
       const int gt = tid & 127;                    // thread within the group == TMEM lane == tile row
       const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
       const int ry = a_mode == A_TMA4D ? gt / P.tw : 0;
@@ -181,7 +183,7 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         return (gt < kCW && pb && !row_bias && q.t < total_tiles && n < P.N) ? __ldg(pb + n) : 0.f;
       };
       TileIter ti;
-      ti.init(P, blockIdx.x + buf * gridDim.x, 2 * gridDim.x, n_tiles, m_tiles);
+      ti.init(P, blockIdx.x + buf * gridDim.x, kBufs * gridDim.x, n_tiles, m_tiles);
       float bnext = bias_of(ti);
       for (int it = 0; ti.t < total_tiles; ++it) {
         const TileCoord c = tile_coord(P, ti, BN);
@@ -237,8 +239,8 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
     uint32_t ph = 0;
     int i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-      const int buf = i & 1;
-      mbar_wait(tempty_bar(buf), ((i >> 1) & 1) ^ 1);      // epilogue groups have drained this buffer (first use: free)
+      const int buf = i % kBufs;
+      mbar_wait(tempty_bar(buf), ((i / kBufs) & 1) ^ 1);      // epilogue groups have drained this buffer (first use: free)
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
       for (int kb = 0; kb < nkb; ++kb) {
