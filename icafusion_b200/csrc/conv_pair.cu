@@ -21,8 +21,8 @@
 // the same (16+2) x (8+2) pixel patch.  Instead of nine shifted TMA boxes, three x-shifted copies of the 18-row patch are
 // loaded (box 64 ch x 8 px x 18 rows at x0-1+kx); a copy is 18 swizzle atoms of 8 pixels x 128 B, so the tap (ky, kx) is
 // the plain K-major operand that starts ky atoms (ky * 1024 B) into copy kx -- a 1024-byte aligned descriptor, nothing
-// exotic.  K loop: channel block -> kx (one copy) -> ky (one filter half-tile per tap); two smem rings (copies, filter
-// tiles).  Activation bytes per SM drop 2.7x (9 x 16 KB -> 3 x 18 KB per channel block).
+// exotic.  K loop: channel block -> kx (one copy + the three filter half-tiles of its ky taps = one hand-over, 12 MMAs);
+// two smem rings (copies, filter tiles).  Activation bytes per SM drop 2.7x (9 x 16 KB -> 3 x 18 KB per channel block).
 // Halo mode 2 is the same idea for a 16- / 32-channel map (the image stem over the space-to-depth frame): the whole K
 // extent is one channel block, the three copies (32- / 64-byte rows, matching swizzle) share one ring slot, the filter
 // streams in ordinary 64-wide K blocks and every 16-element K step addresses its tap inside the right copy.  What it buys
@@ -56,7 +56,8 @@ struct QSmem {
   // halo mode (3x3 / stride 1): a ring of activation copies and a ring of per-tap filter half-tiles
   static constexpr int kHaloNA = 4;
   static constexpr int kHaloNBFit = (227 * 1024 - kTail - kHaloNA * kQHaloABytes) / kBBytes;
-  static constexpr int kHaloNB = kHaloNBFit > kQMaxStages ? kQMaxStages : kHaloNBFit;
+  static constexpr int kHaloNB = kHaloNBFit > kQMaxStages ? kQMaxStages : kHaloNBFit;     // filter half-tiles in the ring
+  static constexpr int kHaloNG = kHaloNB / 3;                                             // ... handed over three at a time
   static constexpr int kHaloRing = kHaloNA * kQHaloABytes + kHaloNB * kBBytes;
   static constexpr int kHaloSmem = kHaloRing + kTail;
 };
@@ -331,28 +332,32 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
           continue;
         }
         if (halo) {
+          // one hand-over per copy: the copy itself plus the three filter half-tiles of its ky taps (12 MMAs per barrier
+          // round trip -- with one tap per round trip the single issuing thread, not the tensor pipe, set the pace)
           const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
           bool first = true;
           for (int cbk = 0; cbk < P.Cin / BK; ++cbk) {
             for (int kx = 0; kx < 3; ++kx) {
               mbar_wait(full_bar(ha), hpa);                  // copy kx of this channel block (both CTAs)
-              for (int ky = 0; ky < 3; ++ky) {
-                mbar_wait(bfull_bar(hb), hpb);               // filter half-tiles of tap (ky, kx)
-                tc_fence_after();
-                if (elect_one()) {
-                  const uint64_t ad = umma_desc_sw128(smem_base + ha * kQHaloABytes + ky * 1024);
-                  const uint64_t bd = umma_desc_sw128(b_ring + hb * kQBBytes);
+              mbar_wait(bfull_bar(hb), hpb);                 // filter half-tiles of taps (0..2, kx)
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t ad0 = umma_desc_sw128(smem_base + ha * kQHaloABytes);
+                const uint64_t bd0 = umma_desc_sw128(b_ring + hb * 3 * kQBBytes);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                   for (int k = 0; k < BK / 16; ++k)
-                    umma2_f16_ss(tmem_d, ad + uint64_t(2 * k), bd + uint64_t(2 * k), idesc, !first || k != 0);
-                  umma2_commit_both(bempty_bar(hb));
-                  if (ky == 2) umma2_commit_both(empty_bar(ha));
-                  if (ky == 2 && kx == 2 && cbk == P.Cin / BK - 1) umma2_commit_both(tfull_bar(buf));
+                    umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (kQBBytes >> 4) + 2 * k), idesc,
+                                 !first || ky != 0 || k != 0);
                 }
-                __syncwarp();
-                first = false;
-                if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
+                umma2_commit_both(bempty_bar(hb));
+                umma2_commit_both(empty_bar(ha));
+                if (kx == 2 && cbk == P.Cin / BK - 1) umma2_commit_both(tfull_bar(buf));
               }
+              __syncwarp();
+              first = false;
+              if (++hb == L::kHaloNG) { hb = 0; hpb ^= 1; }
               if (++ha == L::kHaloNA) { ha = 0; hpa ^= 1; }
             }
           }
@@ -412,13 +417,12 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
               if (rank == 0) mbar_arrive_expect_tx(full_bar(ha), 2u * kQHaloABytes);
               tma2_load_4d(smem_base + ha * kQHaloABytes, ma, map_to_cta(full_bar(ha), 0), cbk * BK, c.ox0 - 1 + kx, c.oy0 - 1, c.tb);
               if (++ha == L::kHaloNA) { ha = 0; hpa ^= 1; }
-              for (int ky = 0; ky < 3; ++ky) {
-                mbar_wait(bempty_bar(hb), hpb ^ 1);
-                if (rank == 0) mbar_arrive_expect_tx(bfull_bar(hb), 2u * kQBBytes);
-                tma2_load_2d(b_ring + hb * kQBBytes, mw, map_to_cta(bfull_bar(hb), 0), (ky * 3 + kx) * P.Cin + cbk * BK,
-                             c.n0 + rank * (kQBN / 2));
-                if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
-              }
+              mbar_wait(bempty_bar(hb), hpb ^ 1);
+              if (rank == 0) mbar_arrive_expect_tx(bfull_bar(hb), 2u * 3u * kQBBytes);
+              const uint32_t lb = map_to_cta(bfull_bar(hb), 0);
+              for (int ky = 0; ky < 3; ++ky)
+                tma2_load_2d(b_ring + (hb * 3 + ky) * kQBBytes, mw, lb, (ky * 3 + kx) * P.Cin + cbk * BK, c.n0 + rank * (kQBN / 2));
+              if (++hb == L::kHaloNG) { hb = 0; hpb ^= 1; }
             }
           }
           continue;

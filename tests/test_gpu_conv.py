@@ -104,16 +104,17 @@ def test_grouped_residual_and_slices(cuda_device):
 
 def test_conv_suite_with_pairs_everywhere(cuda_device):
     """The same conv cases with ICAF_PAIR=all: the CTA-pair kernel (BN 64/128/256, 2-D and 4-D TMA, ragged N, odd tile
-    counts, single-pair grids) replaces every persistent / one-tile launch it can run.  The switch is read once per
-    process, hence the subprocess."""
+    counts, single-pair grids) replaces every persistent / one-tile launch it can run, and the DMFF block tests with it
+    (row bias, GELU, learnable-coefficient residual epilogues).  The switch is read once per process, hence the subprocess."""
     import os
     import subprocess
     import sys
     if os.environ.get("ICAF_PAIR") == "all":
         pytest.skip("already inside the pairs-everywhere run")
     env = dict(os.environ, ICAF_PAIR="all")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k", "matches_oracle or grouped"],
-                       env=env, capture_output=True, text=True, timeout=900)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), os.path.join(here, "test_gpu_dmff.py"), "-q", "-m", "gpu",
+                        "-x", "-k", "matches_oracle or grouped or dmff"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
