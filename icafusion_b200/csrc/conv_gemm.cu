@@ -8,10 +8,15 @@
 //   A_TMA4D  : kxk conv whose 128-row tile is a TH x TW patch of one image and Cin % 64 == 0: one 4-D TMA box
 //              (64 ch, TW*s, TH*s, 1) of the NHWC input per stage at coordinates shifted by the filter tap;
 //              out-of-bounds (= padding) is zero-filled by the TMA unit, the stride is the box traversal stride.
-//   A_GATHER : anything else (image stem with Cin=4, Cin<64, 20-wide P5 maps): producer warps gather 16-byte channel
-//              runs with cp.async (zero-fill), 4 rows x 128 B per warp instruction.
+//              (Cin = 16 / 32: one box per filter tap, 32- / 64-byte swizzle -- persistent and pair kernels only.)
+//   A_GATHER : anything else (Cin = 4 / 8 / odd multiples of 8, Cin < 64 on small grids): producer warps gather 16-byte
+//              channel runs with cp.async (zero-fill), 4 rows x 128 B per warp instruction.
 // The filter tile (BN rows x 64 K) always arrives by 2-D TMA.
-// CTA = one 128 x BN output tile, 192 threads:
+// Three kernels share this contract; icaf_conv2d_fwd picks per layer:
+//   conv_gemm_tc_kernel      (this file)     one tile per CTA, split-K over clusters     -- grids below ~2 tiles per SM
+//   conv_gemm_persist_kernel (conv_persist.cu) one CTA per SM looping over tiles         -- many tiles, short K
+//   conv_gemm_pair_kernel    (conv_pair.cu)  CTA pairs (cta_group::2), halo copies for 3x3 -- wide / deep-K layers
+// conv_gemm_tc_kernel: CTA = one 128 x BN output tile, 192 threads:
 //   warps 0-3 : A_GATHER producers, then the epilogue (thread t owns TMEM lane t = output row t)
 //   warp  4   : TMEM allocator + single-thread tcgen05.mma issuer
 //   warp  5   : TMA producer (one elected thread)
