@@ -495,8 +495,16 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
     if (b == 256) return pairs >= sms / 2 || (pairs >= sms / 4 && nkb_all >= 32);
     return pairs >= sms / 2 && nkb_all >= 8;
   };
+  // 3x3 / stride 1 layers the pair kernel can run with halo copies (conv_pair.cu): once those have removed most of the
+  // activation traffic, BN = 128 pairs beat BN = 256 (probe: 50 vs 52-54 us on M20480 N256 K2304, 54 vs 63 us on the P5 layer:
+  // finer wave balance, four accumulator buffers)
+  static const bool halo_on = []() { const char* e = getenv("ICAF_HALO"); return !(e && e[0] == '0'); }();
+  const bool halo64 = pair_ok && halo_on && P.a_mode == A_TMA4D && P.cblk == 64 && g->kh == 3 && g->kw == 3 && g->stride == 1 &&
+                      g->pad == 1 && g->Cin % 64 == 0 &&
+                      double(g->Wo) * g->Ho >= 0.6 * (double((g->Wo + 7) / 8) * ((g->Ho + 15) / 16) * 128.0);
   int bn = 32;
-  if (P.N >= 256 && (ctas(256) >= 2 * sms || pair_wanted(256))) bn = 256;
+  if (halo64 && P.N >= 128 && pair_wanted(128)) bn = 128;
+  else if (P.N >= 256 && (ctas(256) >= 2 * sms || pair_wanted(256))) bn = 256;
   else if (P.N > 64 && ctas(128) >= sms) bn = 128;
   else if (P.N > 32 && ctas(64) >= sms) bn = 64;
   if (g_dbg_bn) bn = g_dbg_bn;
@@ -509,7 +517,6 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   // (A wave-tail scheme -- peel total % SMs tiles off into a split-K cluster launch -- was measured and dropped: these
   // layers are bound by chip-wide L2->SM bandwidth, so a partly filled last wave just streams the same bytes through
   // fewer, faster CTAs; the second launch only added its fixed cost: 65 -> 87 us on the 320-tile P4 3x3 layer.)
-  static const bool halo_on = []() { const char* e = getenv("ICAF_HALO"); return !(e && e[0] == '0'); }();
   if (pair_env && halo_on && P.a_mode == A_TMA4D && P.cblk < 64 && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1) {
     // 16- / 32-channel 3x3 layers (the image stem over the space-to-depth frame): CTA pairs + halo copies, 64-wide tiles
     const int tx = (g->Wo + 7) / 8, ty = (g->Ho + 15) / 16;
@@ -521,11 +528,8 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   }
   if (pair_wanted(bn)) {
     // 3x3 / stride 1 layers on 16 x 8 pixel tiles: every activation row is fetched three times instead of nine (conv_pair.cu)
-    if (halo_on && P.a_mode == A_TMA4D && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && g->Cin % 64 == 0) {
-      const int tx = (g->Wo + 7) / 8, ty = (g->Ho + 15) / 16;     // tiles may hang over the right / bottom edge (P5: 16 x 20)
-      if (double(g->Wo) * g->Ho >= 0.6 * (double(tx) * ty * 128.0)) {
-        P.halo = 1; P.tw = 8; P.th = 16; P.tiles_x = tx; P.tiles_y = ty;
-      }
+    if (halo64) {   // tiles may hang over the right / bottom edge (P5: 16 x 20)
+      P.halo = 1; P.tw = 8; P.th = 16; P.tiles_x = (g->Wo + 7) / 8; P.tiles_y = (g->Ho + 15) / 16;
     }
     switch (bn) {
       case 256: return launch_pair<256>(P, w, g, n_io, st);

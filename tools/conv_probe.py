@@ -26,6 +26,10 @@ GEOMS = [
     ("3x3_N256_K2304", 16, 32, 40, 256, 256, 3, 1, 1, 2, True),
     ("3x3_N512_K4608", 16, 16, 20, 512, 512, 3, 1, 1, 2, True),
     ("3x3s2_N1024_K4608", 16, 32, 40, 512, 1024, 3, 2, 1, 2, False),
+    ("3x3_N256_K2304_x1", 16, 32, 40, 256, 256, 3, 1, 1, 1, False),
+    ("3x3_N128_K1152_x1", 16, 64, 80, 128, 128, 3, 1, 1, 1, False),
+    ("3x3s2_N256_K1152", 16, 128, 160, 128, 256, 3, 2, 1, 2, False),
+    ("3x3s2_N128_K576", 16, 256, 320, 64, 128, 3, 2, 1, 2, False),
 ]
 DBG = [0, 1, 2, 3, 8, 16, 24, 32, 35]
 

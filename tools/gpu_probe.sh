@@ -1,7 +1,6 @@
 #!/bin/bash
-# Diagnostic session: parity tests, per-geometry probe timings, benches.
+# Probe build (stage switches + forced tile width) -> per-geometry timings; the shipped library is rebuilt afterwards.
 mkdir -p gpurun_out
-python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 5 gpurun_out/pytest_gpu.log
-timeout 600 python tools/conv_probe.py --dbg 0,1,3 --out gpurun_out/conv_probe.json > gpurun_out/conv_probe.log 2>&1; echo "probe rc=$?"
-python bench.py --steps 200 --warmup 20 --layer-profile gpurun_out/layers_s_b1.csv > gpurun_out/bench_s_b1.json 2> gpurun_out/bench_s_b1.err; cut -c1-300 gpurun_out/bench_s_b1.json; tail -n 3 gpurun_out/bench_s_b1.err
-python bench.py --workload yolov5l_b16 --secondary none --steps 20 --warmup 5 --layer-profile gpurun_out/layers_l_b16.csv > gpurun_out/bench_l_b16.json 2> gpurun_out/bench_l_b16.err; cut -c1-300 gpurun_out/bench_l_b16.json; tail -n 3 gpurun_out/bench_l_b16.err
+ICAF_PROBE=1 python -m icafusion_b200.build --force > gpurun_out/probe_build.log 2>&1; tail -n 1 gpurun_out/probe_build.log
+timeout 600 python tools/conv_probe.py --dbg 0 --bns 0,64,128,256 --out gpurun_out/conv_probe_bn.json > gpurun_out/conv_probe_bn.log 2>&1; echo "probe rc=$?"; cat gpurun_out/conv_probe_bn.log | cut -c1-120
+python -m icafusion_b200.build --force > /dev/null 2>&1
