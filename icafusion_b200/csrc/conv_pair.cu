@@ -98,8 +98,12 @@ __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const void* tmap, uin
       ::"r"(dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// Remote arrive on the leader's barrier.  Deliberately the plain form (what CUTLASS' umma_arrive_2x1SM_sm0 emits): the
+// explicit .release.cluster variant compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, i.e. every epilogue warp
+// waited for all of its outstanding global stores once per tile (ncu: 13 % of the stem kernel's stall samples).  The
+// accumulator hand-back needs no memory ordering beyond tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 struct PairTile { int z, mtile, n0, tb, oy0, ox0, m0; };
