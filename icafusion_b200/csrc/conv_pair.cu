@@ -311,25 +311,33 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
           const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
           mbar_wait(full_bar(ha), hpa);
           bool first = true;
+          // (ky, kx, channel offset) of the running 16-element K step, advanced without divisions: this loop is one
+          // thread feeding the tensor pipe, and a runtime "/ Cin" per step made it the slowest stage of the stem
+          uint32_t ky = 0, kx = 0, coff = 0;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(bfull_bar(hb), hpb);
             tc_fence_after();
+            const int nstep = min(BK, P.K - kb * BK) / 16;
             if (elect_one()) {
               const uint32_t set_base = smem_base + ha * set2;
               const uint64_t bd = umma_desc_sw128(b_ring + hb * kQBBytes);
-              for (int e = 0; e < BK && kb * BK + e < P.K; e += 16) {
-                const int kabs = kb * BK + e;
-                const int tap = kabs / P.Cin, coff = kabs - tap * P.Cin;
-                const int ky = tap / 3, kx = tap - 3 * ky;
-                const uint64_t ad = umma_desc_kmajor(set_base + kx * copy2 + ky * 8u * cb2 + uint32_t(coff) * 2u, cb2);
-                umma2_f16_ss(tmem_d, ad, bd + uint64_t(2 * (e / 16)), idesc, !first);
+              uint32_t y = ky, x = kx, c = coff;
+              for (int e = 0; e < nstep; ++e) {
+                const uint64_t ad = umma_desc_kmajor(set_base + x * copy2 + y * 8u * cb2 + c * 2u, cb2);
+                umma2_f16_ss(tmem_d, ad, bd + uint64_t(2 * e), idesc, !first);
                 first = false;
+                c += 16;
+                if (c == uint32_t(P.Cin)) { c = 0; if (++x == 3) { x = 0; ++y; } }
               }
               umma2_commit_both(bempty_bar(hb));
               if (kb == nkb - 1) { umma2_commit_both(empty_bar(ha)); umma2_commit_both(tfull_bar(buf)); }
             }
             __syncwarp();
             first = false;
+            for (int e = 0; e < nstep; ++e) {              // every lane tracks the position (the elected lane may change)
+              coff += 16;
+              if (coff == uint32_t(P.Cin)) { coff = 0; if (++kx == 3) { kx = 0; ++ky; } }
+            }
             if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
           }
           if (++ha == na2) { ha = 0; hpa ^= 1; }
@@ -431,6 +439,7 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
           }
           continue;
         }
+        int ky = 0, kx = 0, ch = 0;                        // filter tap / channel block of the running K block (no divisions)
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * kQStageBytes;
@@ -440,11 +449,9 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
           if (a_mode == A_TMA2D) {
             tma2_load_2d(sa, ma, lfull, kb * BK, c.m0);
           } else {
-            const int k0 = kb * BK;
-            const int tap = k0 / P.Cin;
-            const int ch = k0 - tap * P.Cin;
-            const int ky = tap / P.kw, kx = tap - ky * P.kw;
             tma2_load_4d(sa, ma, lfull, ch, c.ox0 * P.stride - P.pad + kx, c.oy0 * P.stride - P.pad + ky, c.tb);
+            ch += BK;
+            if (ch >= P.Cin) { ch = 0; if (++kx == P.kw) { kx = 0; ++ky; } }
           }
           if (++s == kQStages) { s = 0; ph ^= 1; }
         }

@@ -283,6 +283,7 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         const TileCoord c = tile_coord(P, ti, BN);
         const CUtensorMap* mw = c.z ? &maps.w[1] : &maps.w[0];
         const CUtensorMap* ma = c.z ? &maps.a[1] : &maps.a[0];
+        int ky = 0, kx = 0, ch = 0;                        // tap / channel block of the running K block (64-channel path)
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * L::kStageBytes;
@@ -309,11 +310,11 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
           } else if (a_mode == A_TMA2D) {
             tma_load_2d(sa, ma, full_bar(s), kb * BK, c.m0);
           } else if (a_mode == A_TMA4D) {
-            const int k0 = kb * BK;
-            const int tap = k0 / P.Cin;
-            const int ch = k0 - tap * P.Cin;
-            const int ky = tap / P.kw, kx = tap - ky * P.kw;
             tma_load_4d(sa, ma, full_bar(s), ch, c.ox0 * P.stride - P.pad + kx, c.oy0 * P.stride - P.pad + ky, c.tb);
+          }
+          if (a_mode == A_TMA4D) {                         // advance even when the probe build skipped the load
+            ch += BK;
+            if (ch >= P.Cin) { ch = 0; if (++kx == P.kw) { kx = 0; ++ky; } }
           }
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
