@@ -250,8 +250,10 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
         return None
 
     # ---------------- roofline of the dominant kernel: event-bracketed eager pass --------------------------------
-    # The launches of the profiled step are queued behind a ~3 ms spin kernel so that they execute back to back (an
-    # event pair then sees kernel time + inter-kernel gap, not the Python launch latency).
+    # The launches of the profiled step are queued behind a ~30 ms spin kernel so that they execute back to back (an
+    # event pair then sees kernel time + inter-kernel gap, not the Python launch latency: queueing a yolov5l step takes
+    # the host ~10 ms, longer than the step itself).  Three passes; every launch keeps its fastest time, so a host hiccup
+    # in one pass cannot leak into the figure.
     with torch.no_grad():
         model(eng.rgb, eng.ir)
         torch.cuda.synchronize()
@@ -260,15 +262,19 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
         with ops.profile() as prof:
             for _ in range(reps):
                 flush.zero_()
-                torch.cuda._sleep(int(8e6))
+                torch.cuda._sleep(int(6e7))
                 prof.mark()
                 model(eng.rgb, eng.ir)
                 torch.cuda.synchronize()
         model.__dict__["_icaf_concurrent"] = True
-    summ = prof.summary()
-    if primary and args.layer_profile:           # per-launch table of the last profiled step (geometry, us, TFLOP/s, GB/s)
-        pl = prof.per_launch()
-        pl = pl[-(len(pl) // reps):]
+    allp = prof.per_launch()
+    per = len(allp) // reps
+    pl = [min((allp[r * per + i] for r in range(reps)), key=lambda t: t[2]) for i in range(per)]    # fastest of the passes
+    summ = {}
+    for name, tag, ms, fl, by in pl:
+        d = summ.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["launches"] += reps; d["ms"] += ms * reps; d["flops"] += fl * reps; d["bytes"] += by * reps
+    if primary and args.layer_profile:           # per-launch table of the profiled step (geometry, us, TFLOP/s, GB/s)
         with open(args.layer_profile, "w") as f:
             f.write("kernel,geometry,us,tflops,gbs\n")
             for name, tag, ms, fl, by in pl:
