@@ -33,7 +33,7 @@ struct ConvParams {
   int stages;                             // smem ring depth (runtime: deep rings for small grids, 2 CTAs/SM otherwise)
   int splits;                             // split-K factor = cluster size along x (1 = no cluster); partial sums meet in DSMEM
   int cblk;                               // A_TMA4D: channels per TMA box = min(Cin, 64); < 64 only in the persistent kernel
-  int halo;                               // conv_pair.cu: 3x3/s1 layers stage three x-shifted (th+2)-row copies per channel block
+  int halo;                               // conv_pair.cu: 3x3/s1 layers stage three x-shifted (th+2)-row copies per channel block (0 / 1)
   int dbg;                                // probe builds (-DICAF_PROBE, tools/conv_probe.py): 1 no stores, 2 no activation,
                                           // 8 no A loads, 16 no B loads, 32 no MMA; always 0 in the shipped library
 };

@@ -522,7 +522,7 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
     const int tx = (g->Wo + 7) / 8, ty = (g->Ho + 15) / 16;
     const long long pairs = (long long)g->B * tx * ty * ((P.N + 63) / 64) * n_io / 2;
     if (double(g->Wo) * g->Ho >= 0.6 * (double(tx) * ty * 128.0) && (pair_env == 2 || pairs >= sms / 2)) {
-      P.halo = 2; P.tw = 8; P.th = 16; P.tiles_x = tx; P.tiles_y = ty;
+      P.halo = 1; P.tw = 8; P.th = 16; P.tiles_x = tx; P.tiles_y = ty;
       return launch_pair<64>(P, w, g, n_io, st);
     }
   }

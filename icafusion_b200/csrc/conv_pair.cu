@@ -21,12 +21,13 @@
 // the same (16+2) x (8+2) pixel patch.  Instead of nine shifted TMA boxes, three x-shifted copies of the 18-row patch are
 // loaded (box 64 ch x 8 px x 18 rows at x0-1+kx); a copy is 18 swizzle atoms of 8 pixels x 128 B, so the tap (ky, kx) is
 // the plain K-major operand that starts ky atoms (ky * 1024 B) into copy kx -- a 1024-byte aligned descriptor, nothing
-// exotic.  K loop: channel block -> kx (one copy + the three filter half-tiles of its ky taps = one hand-over, 12 MMAs);
-// two smem rings (copies, filter tiles).  Activation bytes per SM drop 2.7x (9 x 16 KB -> 3 x 18 KB per channel block).
-// Halo mode 2 is the same idea for a 16- / 32-channel map (the image stem over the space-to-depth frame): the whole K
-// extent is one channel block, the three copies (32- / 64-byte rows, matching swizzle) share one ring slot, the filter
-// streams in ordinary 64-wide K blocks and every 16-element K step addresses its tap inside the right copy.  What it buys
-// there is TMA requests, not bytes: 3 x 144 rows per tile instead of 9 x 128 (the stem is bound by the request rate).
+// exotic.  K loop: channel block -> kx; a ring stage holds one copy plus the three filter half-tiles of its ky taps, so
+// one barrier round trip and one commit feed 12 MMAs.  Activation bytes per SM drop 2.7x (9 x 16 KB -> 3 x 18 KB per channel block).
+// 16- / 32-channel maps (the image stem over the space-to-depth frame) take the same path: the TMA box still asks for 64
+// channels and the unit zero-fills the ones the tensor does not have, so the copies keep 128-byte rows and the 128B
+// swizzle; only the K steps that hold real channels are issued, and the filter box of tap t starts at K offset t * Cin.
+// (A first version staged 32- / 64-byte rows with the matching narrow swizzle: every MMA then cost ~200 clk instead of
+// ~40 -- tools/stem_probe.py: 16 channels 277 us, 32 channels 412 us, 64 channels 240 us for the same output.)
 // 576 threads per CTA: warps 0-15 epilogue, warp 16 MMA issuer (leader) + TMEM allocator (both), warp 17 TMA producer.
 #include <cstring>
 
@@ -53,12 +54,11 @@ struct QSmem {
   static constexpr int kStages = kStagesFit > kQMaxStages ? kQMaxStages : kStagesFit;
   static constexpr int kSmem = kStages * kStageBytes + kTail;
   static constexpr int kTmemCols = kBufs * BN;
-  // halo mode (3x3 / stride 1): a ring of activation copies and a ring of per-tap filter half-tiles
-  static constexpr int kHaloNA = 4;
-  static constexpr int kHaloNBFit = (227 * 1024 - kTail - kHaloNA * kQHaloABytes) / kBBytes;
-  static constexpr int kHaloNB = kHaloNBFit > kQMaxStages ? kQMaxStages : kHaloNBFit;     // filter half-tiles in the ring
-  static constexpr int kHaloNG = kHaloNB / 3;                                             // ... handed over three at a time
-  static constexpr int kHaloRing = kHaloNA * kQHaloABytes + kHaloNB * kBBytes;
+  // halo mode (3x3 / stride 1): one ring of stages = [x-shifted activation copy | filter half-tiles of its three ky taps]
+  static constexpr int kHaloStageBytes = kQHaloABytes + 3 * kBBytes;
+  static constexpr int kHaloFit = (227 * 1024 - kTail) / kHaloStageBytes;
+  static constexpr int kHaloStages = kHaloFit > kQMaxStages ? kQMaxStages : kHaloFit;
+  static constexpr int kHaloRing = kHaloStages * kHaloStageBytes;
   static constexpr int kHaloSmem = kHaloRing + kTail;
 };
 
@@ -169,19 +169,15 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   constexpr int kQCW = L::kCW;
   constexpr int kBufs = L::kBufs, kHalves = L::kHalves;
   constexpr int kQBN = BN;
-  const int halo = P.halo;                            // 0 tap boxes, 1 x-shifted copies (Cin % 64 == 0), 2 copies of a 16 / 32 channel map
-  const uint32_t cb2 = uint32_t(P.cblk) * 2u;          // halo 2: bytes per pixel row of a copy
-  const uint32_t copy2 = 144u * cb2;                  //         one x-shifted copy, (16+2) x 8 pixels
-  const uint32_t set2 = (3u * copy2 + 1023u) & ~1023u; //        ring slot = the three copies of a tile
-  const int na2 = P.cblk <= 16 ? 4 : 2;
+  const bool halo = P.halo != 0;                      // x-shifted copies instead of tap boxes (3x3 / stride 1)
+  const int ncb = (P.Cin + BK - 1) / BK;              // halo: 64-channel blocks (1 for the 16- / 32-channel stem maps)
+  const int kst = (P.Cin < BK ? P.Cin : BK) / 16;     // halo: 16-element K steps per tap that hold real channels
   const uint32_t bar_off = halo ? uint32_t(L::kHaloRing) : uint32_t(kQStages) * kQStageBytes;
   const uint32_t bar_base = smem_base + bar_off;
-  // barrier block (8-byte slots): 0-9 full / copy full, 10-19 empty / copy empty, 20-29 filter full, 30-39 filter empty
-  // (halo mode), 40-43 accumulator full, 44-47 accumulator empty, 48 TMEM base address
+  // barrier block (8-byte slots): 0-9 stage full, 10-19 stage empty, 40-43 accumulator full, 44-47 accumulator empty,
+  // 48 TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (10 + s); };
-  auto bfull_bar = [&](int s) { return bar_base + 8u * (20 + s); };
-  auto bempty_bar = [&](int s) { return bar_base + 8u * (30 + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (40 + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (44 + b); };
   const uint32_t tmem_slot = bar_base + 8u * 48;
@@ -200,8 +196,6 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
     for (int s = 0; s < kQMaxStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(bfull_bar(s), 1);
-      mbar_init(bempty_bar(s), 1);
     }
     for (int b = 0; b < kBufs; ++b) {
       mbar_init(tfull_bar(b), 1);
@@ -297,80 +291,45 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       constexpr uint32_t idesc = umma_idesc_f16(2 * BM, kQBN);
       int s = 0;
       uint32_t ph = 0;
-      int ha = 0, hb = 0;                                    // halo mode: copy ring / filter ring positions and phases
-      uint32_t hpa = 0, hpb = 0;
       int i = 0;
       for (int t = cluster_id; t < total_pairs; t += n_clusters, ++i) {
         const int buf = i % kBufs;
         mbar_wait(tempty_bar(buf), ((i / kBufs) & 1) ^ 1);      // both CTAs' epilogue groups have drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(buf * kQBN);
-        if (halo == 2) {
-          // small-Cin map (image stem over the space-to-depth frame): one channel block, all three copies in one ring slot;
-          // the filter arrives in ordinary 64-wide K blocks (4 or 2 taps each) and every 16-element K step picks its tap's copy
-          const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
-          mbar_wait(full_bar(ha), hpa);
-          bool first = true;
-          // (ky, kx, channel offset) of the running 16-element K step, advanced without divisions: this loop is one
-          // thread feeding the tensor pipe, and a runtime "/ Cin" per step made it the slowest stage of the stem
-          uint32_t ky = 0, kx = 0, coff = 0;
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(bfull_bar(hb), hpb);
-            tc_fence_after();
-            const int nstep = min(BK, P.K - kb * BK) / 16;
-            if (elect_one()) {
-              const uint32_t set_base = smem_base + ha * set2;
-              const uint64_t bd = umma_desc_sw128(b_ring + hb * kQBBytes);
-              uint32_t y = ky, x = kx, c = coff;
-              for (int e = 0; e < nstep; ++e) {
-                const uint64_t ad = umma_desc_kmajor(set_base + x * copy2 + y * 8u * cb2 + c * 2u, cb2);
-                umma2_f16_ss(tmem_d, ad, bd + uint64_t(2 * e), idesc, !first);
-                first = false;
-                c += 16;
-                if (c == uint32_t(P.Cin)) { c = 0; if (++x == 3) { x = 0; ++y; } }
-              }
-              umma2_commit_both(bempty_bar(hb));
-              if (kb == nkb - 1) { umma2_commit_both(empty_bar(ha)); umma2_commit_both(tfull_bar(buf)); }
-            }
-            __syncwarp();
-            first = false;
-            for (int e = 0; e < nstep; ++e) {              // every lane tracks the position (the elected lane may change)
-              coff += 16;
-              if (coff == uint32_t(P.Cin)) { coff = 0; if (++kx == 3) { kx = 0; ++ky; } }
-            }
-            if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
-          }
-          if (++ha == na2) { ha = 0; hpa ^= 1; }
-          continue;
-        }
         if (halo) {
-          // one hand-over per copy: the copy itself plus the three filter half-tiles of its ky taps (12 MMAs per barrier
-          // round trip -- with one tap per round trip the single issuing thread, not the tensor pipe, set the pace)
-          const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
+          // one stage = one copy + the filter half-tiles of its three ky taps: a single barrier round trip and a single
+          // commit per 12 MMAs (the issuing thread, not the tensor pipe, sets the pace of these loops)
           bool first = true;
-          for (int cbk = 0; cbk < P.Cin / BK; ++cbk) {
+          for (int cbk = 0; cbk < ncb; ++cbk) {
             for (int kx = 0; kx < 3; ++kx) {
-              mbar_wait(full_bar(ha), hpa);                  // copy kx of this channel block (both CTAs)
-              mbar_wait(bfull_bar(hb), hpb);                 // filter half-tiles of taps (0..2, kx)
+              mbar_wait(full_bar(s), ph);
               tc_fence_after();
               if (elect_one()) {
-                const uint64_t ad0 = umma_desc_sw128(smem_base + ha * kQHaloABytes);
-                const uint64_t bd0 = umma_desc_sw128(b_ring + hb * 3 * kQBBytes);
+                const uint32_t sa = smem_base + s * L::kHaloStageBytes;
+                const uint64_t ad0 = umma_desc_sw128(sa);
+                const uint64_t bd0 = umma_desc_sw128(sa + kQHaloABytes);
+                if (kst == BK / 16) {
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
+                  for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-                  for (int k = 0; k < BK / 16; ++k)
-                    umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (kQBBytes >> 4) + 2 * k), idesc,
-                                 !first || ky != 0 || k != 0);
+                    for (int k = 0; k < BK / 16; ++k)
+                      umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (kQBBytes >> 4) + 2 * k), idesc,
+                                   !first || ky != 0 || k != 0);
+                  }
+                } else {                                   // 16- / 32-channel maps: only the K steps with real channels
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky)
+                    for (int k = 0; k < kst; ++k)
+                      umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (kQBBytes >> 4) + 2 * k), idesc,
+                                   !first || ky != 0 || k != 0);
                 }
-                umma2_commit_both(bempty_bar(hb));
-                umma2_commit_both(empty_bar(ha));
-                if (kx == 2 && cbk == P.Cin / BK - 1) umma2_commit_both(tfull_bar(buf));
+                umma2_commit_both(empty_bar(s));
+                if (kx == 2 && cbk == ncb - 1) umma2_commit_both(tfull_bar(buf));
               }
               __syncwarp();
               first = false;
-              if (++hb == L::kHaloNG) { hb = 0; hpb ^= 1; }
-              if (++ha == L::kHaloNA) { ha = 0; hpa ^= 1; }
+              if (++s == L::kHaloStages) { s = 0; ph ^= 1; }
             }
           }
           continue;
@@ -400,41 +359,21 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       const uint32_t stage_tx = 2u * (uint32_t(kQBBytes) + a_bytes);   // both CTAs' loads complete on the leader's barrier
       int s = 0;
       uint32_t ph = 0;
-      int ha = 0, hb = 0;
-      uint32_t hpa = 0, hpb = 0;
       for (int t = cluster_id; t < total_pairs; t += n_clusters) {
         const PairTile c = pair_tile(P, t, rank, m_pairs, n_tiles, BN);
         const CUtensorMap* mw = c.z ? &maps.w[1] : &maps.w[0];
         const CUtensorMap* ma = c.z ? &maps.a[1] : &maps.a[0];
-        if (halo == 2) {
-          const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
-          mbar_wait(empty_bar(ha), hpa ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(ha), 2u * 3u * copy2);
-          for (int kx = 0; kx < 3; ++kx)
-            tma2_load_4d(smem_base + ha * set2 + kx * copy2, ma, map_to_cta(full_bar(ha), 0), 0, c.ox0 - 1 + kx, c.oy0 - 1, c.tb);
-          if (++ha == na2) { ha = 0; hpa ^= 1; }
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(bempty_bar(hb), hpb ^ 1);
-            if (rank == 0) mbar_arrive_expect_tx(bfull_bar(hb), 2u * kQBBytes);
-            tma2_load_2d(b_ring + hb * kQBBytes, mw, map_to_cta(bfull_bar(hb), 0), kb * BK, c.n0 + rank * (kQBN / 2));
-            if (++hb == L::kHaloNB) { hb = 0; hpb ^= 1; }
-          }
-          continue;
-        }
         if (halo) {
-          const uint32_t b_ring = smem_base + L::kHaloNA * kQHaloABytes;
-          for (int cbk = 0; cbk < P.Cin / BK; ++cbk) {
+          for (int cbk = 0; cbk < ncb; ++cbk) {
             for (int kx = 0; kx < 3; ++kx) {
-              mbar_wait(empty_bar(ha), hpa ^ 1);
-              if (rank == 0) mbar_arrive_expect_tx(full_bar(ha), 2u * kQHaloABytes);
-              tma2_load_4d(smem_base + ha * kQHaloABytes, ma, map_to_cta(full_bar(ha), 0), cbk * BK, c.ox0 - 1 + kx, c.oy0 - 1, c.tb);
-              if (++ha == L::kHaloNA) { ha = 0; hpa ^= 1; }
-              mbar_wait(bempty_bar(hb), hpb ^ 1);
-              if (rank == 0) mbar_arrive_expect_tx(bfull_bar(hb), 2u * 3u * kQBBytes);
-              const uint32_t lb = map_to_cta(bfull_bar(hb), 0);
+              mbar_wait(empty_bar(s), ph ^ 1);
+              const uint32_t sa = smem_base + s * L::kHaloStageBytes;
+              const uint32_t lfull = map_to_cta(full_bar(s), 0);
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * uint32_t(L::kHaloStageBytes));
+              tma2_load_4d(sa, ma, lfull, cbk * BK, c.ox0 - 1 + kx, c.oy0 - 1, c.tb);
               for (int ky = 0; ky < 3; ++ky)
-                tma2_load_2d(b_ring + (hb * 3 + ky) * kQBBytes, mw, lb, (ky * 3 + kx) * P.Cin + cbk * BK, c.n0 + rank * (kQBN / 2));
-              if (++hb == L::kHaloNG) { hb = 0; hpb ^= 1; }
+                tma2_load_2d(sa + kQHaloABytes + ky * kQBBytes, mw, lfull, (ky * 3 + kx) * P.Cin + cbk * BK, c.n0 + rank * (kQBN / 2));
+              if (++s == L::kHaloStages) { s = 0; ph ^= 1; }
             }
           }
           continue;
@@ -495,8 +434,8 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
     const ConvProblem& pr = P.p[i];
     if (P.a_mode == A_TMA2D)
       rc = encode_tmap_2d(&maps.a[i], pr.x, (uint64_t)P.Cin, (uint64_t)P.M, (uint64_t)pr.x_ld * 2, BK, BM);
-    else if (P.halo)   // one x-shifted copy: 8 px x (16+2) rows of 64 (or all 16 / 32) channels
-      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, P.halo == 2 ? (uint32_t)P.cblk : (uint32_t)BK, 8, 18, 1, 1);
+    else if (P.halo)   // one x-shifted copy: 8 px x (16+2) rows x 64 channels (a 16- / 32-channel map is zero-filled up to 64)
+      rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, 8, 18, 1, 1);
     else
       rc = encode_tmap_nhwc(&maps.a[i], pr.x, P.Cin, P.Wi, P.Hi, P.B, pr.x_ld, BK, P.tw * P.stride, P.th * P.stride, P.stride, P.stride);
     if (rc) return rc;
