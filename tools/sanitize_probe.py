@@ -16,7 +16,7 @@ CASES = [
     (2, 64, 32, 40, 128, 3, 1, 1),    # halo copies, BN=128 pairs
     (2, 128, 16, 20, 256, 3, 1, 1),   # halo copies, tiles overhang the 20-wide map
     (2, 64, 32, 40, 128, 3, 2, 1),    # stride 2: tap boxes
-    (8, 16, 64, 80, 32, 3, 1, 1),     # 16-channel map: halo mode 2 (persistent-size grid), N = 32 < BN
+    (8, 16, 64, 80, 32, 3, 1, 1),     # 16-channel map: halo copies of the zero-filled 64-channel view, N = 32 < BN
     (2, 64, 32, 40, 96, 1, 1, 0),     # 1x1, ragged N
     (1, 8, 9, 11, 40, 3, 1, 1),       # gather path (one-tile kernel)
     (4, 64, 64, 80, 64, 1, 1, 0),     # many tiles, short K
