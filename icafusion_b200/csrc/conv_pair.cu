@@ -309,21 +309,16 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
                 const uint32_t sa = smem_base + s * L::kHaloStageBytes;
                 const uint64_t ad0 = umma_desc_sw128(sa);
                 const uint64_t bd0 = umma_desc_sw128(sa + kQHaloABytes);
-                if (kst == BK / 16) {
-#pragma unroll
-                  for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                      umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (kQBBytes >> 4) + 2 * k), idesc,
-                                   !first || ky != 0 || k != 0);
-                  }
-                } else {                                   // 16- / 32-channel maps: only the K steps with real channels
-#pragma unroll
-                  for (int ky = 0; ky < 3; ++ky)
-                    for (int k = 0; k < kst; ++k)
-                      umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (kQBBytes >> 4) + 2 * k), idesc,
-                                   !first || ky != 0 || k != 0);
-                }
+                // kst is 4 (Cin % 64 == 0), 2 or 1 (32- / 16-channel maps): fully unrolled issue sequences, no loop overhead
+                // in the one thread that feeds the tensor pipe
+#define ICAF_ISSUE_TAPS(KST)                                                                                               \
+  _Pragma("unroll") for (int ky = 0; ky < 3; ++ky) {                                                                        \
+    _Pragma("unroll") for (int k = 0; k < (KST); ++k)                                                                       \
+        umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (kQBBytes >> 4) + 2 * k), idesc,  \
+                     !first || ky != 0 || k != 0);                                                                          \
+  }
+                if (kst == 4) { ICAF_ISSUE_TAPS(4) } else if (kst == 2) { ICAF_ISSUE_TAPS(2) } else { ICAF_ISSUE_TAPS(1) }
+#undef ICAF_ISSUE_TAPS
                 umma2_commit_both(empty_bar(s));
                 if (kx == 2 && cbk == ncb - 1) umma2_commit_both(tfull_bar(buf));
               }
