@@ -84,3 +84,30 @@ def test_model_fuse_removes_bn_and_rebinds_forward():
     convs = [x for x in m.modules() if type(x) is Conv]
     assert convs and not any(hasattr(c, "bn") for c in convs) and all(c.conv.bias is not None for c in convs)
     assert not any(".bn." in k for k in m.state_dict())
+
+
+def test_stem_space_to_depth_repack_is_the_same_convolution():
+    """ops.pack_stem_weight: the 6x6 / stride 2 / pad 2 image stem (models/common.py:36-60 with the YAML row
+    [-1, 1, Conv, [c, 6, 2, 2]]) equals a 3x3 / stride 1 / pad 1 convolution over the space-to-depth frame that
+    icaf_pack_image_s2d produces (channel (dy*2+dx)*4 + c).  Pure fp32 torch on the CPU: the identity is exact up to
+    summation order."""
+    import torch.nn.functional as F
+    from icafusion_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(2, 3, 32, 48, generator=g)
+    w = torch.randn(8, 3, 6, 6, generator=g)
+    b = torch.randn(8, generator=g)
+    ref = F.conv2d(img, w, b, stride=2, padding=2)
+    pk = ops.pack_stem_weight(w, b, ops.ACT_NONE, device="cpu")
+    assert (pk.cin, pk.kh, pk.kw, pk.stride, pk.pad) == (16, 3, 3, 1, 1)
+    # unpack the GEMM filter matrix [Cout^32][K^64], K order (ky, kx, c), back to (Cout, 16, 3, 3)
+    ws = pk.w[:8, :144].float().view(8, 3, 3, 16).permute(0, 3, 1, 2)
+    # space-to-depth frame exactly as icaf_pack_image_s2d lays it out: channel (dy*2+dx)*4 + c, c = r,g,b,0
+    B, _, H, W = img.shape
+    x4 = torch.cat([img, img.new_zeros(B, 1, H, W)], 1)
+    s2d = x4.view(B, 4, H // 2, 2, W // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(B, 16, H // 2, W // 2)
+    out = F.conv2d(s2d, ws, b, stride=1, padding=1)
+    assert out.shape == ref.shape
+    # the packed filter is fp16: compare against the fp16-rounded 6x6 filter
+    ref16 = F.conv2d(img, w.half().float(), b, stride=2, padding=2)
+    assert float((out - ref16).abs().max()) < 1e-4
