@@ -59,3 +59,16 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.IcafError):
         _lib.lib()
+
+
+def test_shipped_library_has_no_probe_hooks_and_counts_launches():
+    """The stage switches of tools/conv_probe.py exist only in -DICAF_PROBE builds; the shipped library exports exactly the
+    header's symbols.  The launch tally behind bench.py's `gpu_launches` starts at zero and does not move on rejected calls."""
+    from icafusion_b200 import _lib
+    L = _lib.lib()
+    assert not hasattr(L, "icaf_debug_set")
+    n0 = L.icaf_kernel_launches()
+    g = _lib.ConvGeom(1, 8, 8, 12, 8, 8, 16, 1, 1, 1, 0, 64, 32, 0, 0)      # rejected on the host (Cin = 12)
+    io = (_lib.ConvIO * 1)()
+    assert L.icaf_conv2d_fwd(ctypes.byref(g), io, 1, None) != 0
+    assert L.icaf_kernel_launches() == n0
