@@ -23,6 +23,9 @@
 // the plain K-major operand that starts ky atoms (ky * 1024 B) into copy kx -- a 1024-byte aligned descriptor, nothing
 // exotic.  K loop: channel block -> kx; a ring stage holds one copy plus the three filter half-tiles of its ky taps, so
 // one barrier round trip and one commit feed 12 MMAs.  Activation bytes per SM drop 2.7x (9 x 16 KB -> 3 x 18 KB per channel block).
+// Halo mode 2: when the whole K extent is one channel block and N fits one tile (the stem, the 64 -> 64 channel P2
+// bottlenecks) the nine filter half-tiles are loaded once per problem and stay resident; only activation copies stream.
+// (ncu on the stem: 1.89 GB of TMA traffic for 84 MB of input -- 39 % of it the same 36 KB of filter, reloaded per tile.)
 // 16- / 32-channel maps (the image stem over the space-to-depth frame) take the same path: the TMA box still asks for 64
 // channels and the unit zero-fills the ones the tensor does not have, so the copies keep 128-byte rows and the 128B
 // swizzle; only the K steps that hold real channels are issued, and the filter box of tap t starts at K offset t * Cin.
@@ -60,6 +63,12 @@ struct QSmem {
   static constexpr int kHaloStages = kHaloFit > kQMaxStages ? kQMaxStages : kHaloFit;
   static constexpr int kHaloRing = kHaloStages * kHaloStageBytes;
   static constexpr int kHaloSmem = kHaloRing + kTail;
+  // halo mode 2 (one channel block, one N tile): the nine filter half-tiles stay resident, the ring holds copies only
+  static constexpr int kResBytes = 9 * kBBytes;
+  static constexpr int kResFit = (227 * 1024 - kTail - kResBytes) / kQHaloABytes;
+  static constexpr int kResStages = kResFit > kQMaxStages ? kQMaxStages : (kResFit < 1 ? 1 : kResFit);
+  static constexpr int kResRing = kResBytes + kResStages * kQHaloABytes;
+  static constexpr int kResSmem = kResRing + kTail;
 };
 
 // ---- cta_group::2 PTX (same encodings CUTLASS' SM100_TMA_2SM_LOAD / umma_arrive_multicast_2x1SM use)
@@ -169,15 +178,16 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
   constexpr int kQCW = L::kCW;
   constexpr int kBufs = L::kBufs, kHalves = L::kHalves;
   constexpr int kQBN = BN;
-  const bool halo = P.halo != 0;                      // x-shifted copies instead of tap boxes (3x3 / stride 1)
+  const int halo = P.halo;                            // 1: x-shifted copies instead of tap boxes (3x3 / stride 1); 2: + resident filter
   const int ncb = (P.Cin + BK - 1) / BK;              // halo: 64-channel blocks (1 for the 16- / 32-channel stem maps)
   const int kst = (P.Cin < BK ? P.Cin : BK) / 16;     // halo: 16-element K steps per tap that hold real channels
-  const uint32_t bar_off = halo ? uint32_t(L::kHaloRing) : uint32_t(kQStages) * kQStageBytes;
+  const uint32_t bar_off = halo == 2 ? uint32_t(L::kResRing) : (halo ? uint32_t(L::kHaloRing) : uint32_t(kQStages) * kQStageBytes);
   const uint32_t bar_base = smem_base + bar_off;
-  // barrier block (8-byte slots): 0-9 stage full, 10-19 stage empty, 40-43 accumulator full, 44-47 accumulator empty,
-  // 48 TMEM base address
+  // barrier block (8-byte slots): 0-9 stage full, 10-19 stage empty, 20 / 30 resident filter full / released (halo mode 2),
+  // 40-43 accumulator full, 44-47 accumulator empty, 48 TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (10 + s); };
+  const uint32_t bres_full = bar_base + 8u * 20, bres_empty = bar_base + 8u * 30;
   auto tfull_bar = [&](int b) { return bar_base + 8u * (40 + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (44 + b); };
   const uint32_t tmem_slot = bar_base + 8u * 48;
@@ -197,6 +207,8 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    mbar_init(bres_full, 1);
+    mbar_init(bres_empty, 1);
     for (int b = 0; b < kBufs; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 8 * kHalves);      // one arrival per epilogue warp of the buffer, both CTAs
@@ -291,12 +303,49 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       constexpr uint32_t idesc = umma_idesc_f16(2 * BM, kQBN);
       int s = 0;
       uint32_t ph = 0;
+      int zprev = -1, loads = 0;                             // halo mode 2: problem whose filter is resident, loads so far
       int i = 0;
       for (int t = cluster_id; t < total_pairs; t += n_clusters, ++i) {
         const int buf = i % kBufs;
         mbar_wait(tempty_bar(buf), ((i / kBufs) & 1) ^ 1);      // both CTAs' epilogue groups have drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(buf * kQBN);
+        // kst is 4 (Cin % 64 == 0), 2 or 1 (32- / 16-channel maps): fully unrolled issue sequences, no loop overhead in the
+        // one thread that feeds the tensor pipe.  BKY = distance between the filter tiles of ky and ky + 1 (16-byte units).
+#define ICAF_ISSUE_TAPS(KST, BKY)                                                                                            \
+  _Pragma("unroll") for (int ky = 0; ky < 3; ++ky) {                                                                          \
+    _Pragma("unroll") for (int k = 0; k < (KST); ++k)                                                                         \
+        umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (BKY) + 2 * k), idesc,             \
+                     !first || ky != 0 || k != 0);                                                                            \
+  }
+        if (halo == 2) {
+          // resident filter: all nine half-tiles of this problem's filter sit at the bottom of shared memory (tap t at
+          // t * kQBBytes, t = ky * 3 + kx); a ring stage is just one activation copy
+          const int per_z = m_pairs * n_tiles;
+          const int z = t / per_z;
+          const int zn = t + n_clusters < total_pairs ? (t + n_clusters) / per_z : z;
+          if (z != zprev) { mbar_wait(bres_full, uint32_t(loads & 1)); ++loads; zprev = z; }
+          bool first = true;
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t ad0 = umma_desc_sw128(smem_base + L::kResBytes + s * kQHaloABytes);
+              const uint64_t bd0 = umma_desc_sw128(smem_base + kx * kQBBytes);
+              if (kst == 4) { ICAF_ISSUE_TAPS(4, 3 * (kQBBytes >> 4)) } else if (kst == 2) { ICAF_ISSUE_TAPS(2, 3 * (kQBBytes >> 4)) }
+              else { ICAF_ISSUE_TAPS(1, 3 * (kQBBytes >> 4)) }
+              umma2_commit_both(empty_bar(s));
+              if (kx == 2) {
+                umma2_commit_both(tfull_bar(buf));
+                if (zn != z) umma2_commit_both(bres_empty);   // last tile of this problem: the filter may be replaced
+              }
+            }
+            __syncwarp();
+            first = false;
+            if (++s == L::kResStages) { s = 0; ph ^= 1; }
+          }
+          continue;
+        }
         if (halo) {
           // one stage = one copy + the filter half-tiles of its three ky taps: a single barrier round trip and a single
           // commit per 12 MMAs (the issuing thread, not the tensor pipe, sets the pace of these loops)
@@ -309,16 +358,8 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
                 const uint32_t sa = smem_base + s * L::kHaloStageBytes;
                 const uint64_t ad0 = umma_desc_sw128(sa);
                 const uint64_t bd0 = umma_desc_sw128(sa + kQHaloABytes);
-                // kst is 4 (Cin % 64 == 0), 2 or 1 (32- / 16-channel maps): fully unrolled issue sequences, no loop overhead
-                // in the one thread that feeds the tensor pipe
-#define ICAF_ISSUE_TAPS(KST)                                                                                               \
-  _Pragma("unroll") for (int ky = 0; ky < 3; ++ky) {                                                                        \
-    _Pragma("unroll") for (int k = 0; k < (KST); ++k)                                                                       \
-        umma2_f16_ss(tmem_d, ad0 + uint64_t(ky * (1024 >> 4) + 2 * k), bd0 + uint64_t(ky * (kQBBytes >> 4) + 2 * k), idesc,  \
-                     !first || ky != 0 || k != 0);                                                                          \
-  }
-                if (kst == 4) { ICAF_ISSUE_TAPS(4) } else if (kst == 2) { ICAF_ISSUE_TAPS(2) } else { ICAF_ISSUE_TAPS(1) }
-#undef ICAF_ISSUE_TAPS
+                if (kst == 4) { ICAF_ISSUE_TAPS(4, kQBBytes >> 4) } else if (kst == 2) { ICAF_ISSUE_TAPS(2, kQBBytes >> 4) }
+                else { ICAF_ISSUE_TAPS(1, kQBBytes >> 4) }
                 umma2_commit_both(empty_bar(s));
                 if (kx == 2 && cbk == ncb - 1) umma2_commit_both(tfull_bar(buf));
               }
@@ -329,6 +370,7 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
           }
           continue;
         }
+#undef ICAF_ISSUE_TAPS
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(s), ph);                        // both CTAs' operands of this stage have landed
           tc_fence_after();
@@ -354,10 +396,29 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       const uint32_t stage_tx = 2u * (uint32_t(kQBBytes) + a_bytes);   // both CTAs' loads complete on the leader's barrier
       int s = 0;
       uint32_t ph = 0;
+      int zprev = -1, loads = 0;
       for (int t = cluster_id; t < total_pairs; t += n_clusters) {
         const PairTile c = pair_tile(P, t, rank, m_pairs, n_tiles, BN);
         const CUtensorMap* mw = c.z ? &maps.w[1] : &maps.w[0];
         const CUtensorMap* ma = c.z ? &maps.a[1] : &maps.a[0];
+        if (halo == 2) {
+          if (c.z != zprev) {                                // first tile, or the sequence moved on to the other stream's filter
+            if (loads > 0) mbar_wait(bres_empty, uint32_t((loads - 1) & 1));
+            if (rank == 0) mbar_arrive_expect_tx(bres_full, 2u * uint32_t(L::kResBytes));
+            const uint32_t lb = map_to_cta(bres_full, 0);
+            for (int tap = 0; tap < 9; ++tap)
+              tma2_load_2d(smem_base + tap * kQBBytes, mw, lb, tap * P.Cin, c.n0 + rank * (kQBN / 2));
+            ++loads;
+            zprev = c.z;
+          }
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * kQHaloABytes);
+            tma2_load_4d(smem_base + L::kResBytes + s * kQHaloABytes, ma, map_to_cta(full_bar(s), 0), 0, c.ox0 - 1 + kx, c.oy0 - 1, c.tb);
+            if (++s == L::kResStages) { s = 0; ph ^= 1; }
+          }
+          continue;
+        }
         if (halo) {
           for (int cbk = 0; cbk < ncb; ++cbk) {
             for (int kx = 0; kx < 3; ++kx) {
@@ -411,7 +472,7 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kQSmem > L::kHaloSmem ? kQSmem : L::kHaloSmem);
+                                         227 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute (pair)");
     configured = true;
   }
@@ -439,7 +500,7 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
   const int max_clusters = sm_count_cached() / 2;
   const int waves = (total + max_clusters - 1) / max_clusters;
   const int clusters = (total + waves - 1) / waves;
-  launch_kc(conv_gemm_pair_kernel<BN>, dim3(2 * clusters), dim3(kQThreads), (size_t)(P.halo ? L::kHaloSmem : kQSmem), st, 2u, P, maps, total, m_tiles, m_pairs, n_tiles);
+  launch_kc(conv_gemm_pair_kernel<BN>, dim3(2 * clusters), dim3(kQThreads), (size_t)(P.halo == 2 ? L::kResSmem : (P.halo ? L::kHaloSmem : kQSmem)), st, 2u, P, maps, total, m_tiles, m_pairs, n_tiles);
   return check_launch("conv2d_fwd(pair)");
 }
 
