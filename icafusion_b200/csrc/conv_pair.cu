@@ -480,6 +480,12 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
   const int m_pairs = (m_tiles + 1) / 2;
   const int n_tiles = (P.N + kQBN - 1) / kQBN;
   const int total = m_pairs * n_tiles * n_io;
+  // invariants the kernel's halo paths rely on (the dispatcher in conv_gemm.cu establishes them; fail loudly if it ever does not)
+  if (P.halo && !(g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && P.tw == 8 && P.th == 16 &&
+                  (P.Cin % 64 == 0 || P.Cin == 16 || P.Cin == 32)))
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): halo copies need a 3x3 / stride 1 / pad 1 layer on 16 x 8 tiles");
+  if (P.halo == 2 && !(n_tiles == 1 && P.Cin <= 64))
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): the resident-filter mode needs one channel block and one N tile");
   P.stages = L::kStages;
   P.splits = 1;
   ConvMaps maps;
