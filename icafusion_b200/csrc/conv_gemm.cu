@@ -531,7 +531,12 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   if (pair_wanted(bn)) {
     // 3x3 / stride 1 layers on 16 x 8 pixel tiles: every activation row is fetched three times instead of nine (conv_pair.cu)
     if (halo64) {   // tiles may hang over the right / bottom edge (P5: 16 x 20)
-      P.halo = 1; P.tw = 8;   // (resident filter, halo mode 2, measured slower here: 233 vs 209 us at Cin = 64, N = 64) P.th = 16; P.tiles_x = (g->Wo + 7) / 8; P.tiles_y = (g->Ho + 15) / 16;
+      // (resident filter, halo mode 2, measured slower here: 233 vs 209 us at Cin = 64, N = 64)
+      P.halo = 1;
+      P.tw = 8;
+      P.th = 16;
+      P.tiles_x = (g->Wo + 7) / 8;
+      P.tiles_y = (g->Ho + 15) / 16;
     }
     switch (bn) {
       case 256: return launch_pair<256>(P, w, g, n_io, st);
