@@ -27,6 +27,14 @@ class ConvIO(C.Structure):
                 ("alpha", C.c_void_p), ("beta", C.c_void_p)]
 
 
+class ConvPlan(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("kernel", "bn", "a_mode", "tile_w", "tile_h", "tiles_x", "tiles_y", "cblk", "halo",
+                                       "stages", "splits", "grid_x", "grid_y", "grid_z", "cluster", "smem_bytes",
+                                       "work_items")]
+
+
+KERNEL_TC, KERNEL_PERSIST, KERNEL_PAIR = 0, 1, 2
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 # name -> argtypes; every symbol include/icaf_b200.h declares (tests check the .so exports them all)
 SIGNATURES = {
@@ -35,6 +43,7 @@ SIGNATURES = {
     "icaf_sm_count": [],
     "icaf_kernel_launches": [],
     "icaf_conv2d_fwd": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
+    "icaf_conv2d_plan": [C.POINTER(ConvGeom), _i, _i, _i, C.POINTER(ConvPlan)],
     "icaf_conv2d_fwd_simt": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
     "icaf_pack_image": [_vp, _i, _f, _i, _i, _i, _vp, _vp],
     "icaf_pack_image_s2d": [_vp, _i, _f, _i, _i, _i, _vp, _vp],

@@ -40,7 +40,7 @@ def autopad(k, p=None):
 # layout plumbing
 def to_nhwc(x: torch.Tensor) -> torch.Tensor:
     """Logical (B,C,H,W) -> fp16 (B,H,W,C) contiguous view (zero-copy for channels_last fp16 input)."""
-    if not x.is_cuda:
+    if not ops.on_device(x):
         raise RuntimeError("icafusion_b200 operators run on CUDA tensors only (no CPU fallback)")
     v = x.permute(0, 2, 3, 1)
     if v.dtype != torch.float16 or not v.is_contiguous():
@@ -130,7 +130,7 @@ class Conv(nn.Module):
 
     def forward(self, x):
         if x.shape[1] == 3 and self.conv.in_channels == 3:     # image stem: planar -> packed NHWC4 / space-to-depth
-            if not x.is_cuda:
+            if not ops.on_device(x):
                 raise RuntimeError("icafusion_b200 operators run on CUDA tensors only (no CPU fallback)")
             v = self.stage_image(x)
         else:
@@ -467,10 +467,8 @@ class TransformerFusionBlock(nn.Module):
         self.ir_coefficient = LearnableWeights()
         self.crosstransformer = nn.Sequential(*[CrossTransformerBlock(d_model, d_k, d_v, h, block_exp, attn_pdrop,
                                                                       resid_pdrop) for _ in range(n_layer)])
-        for m in self.crosstransformer.modules():   # reference applies _init_weights before building these; keep
-            if isinstance(m, nn.Linear):             # transformer-style init for a usable default
-                nn.init.normal_(m.weight, std=0.02)
-                nn.init.zeros_(m.bias)
+        # (the reference applies its _init_weights before these exist, common.py:787-790: the attention projections keep
+        #  CrossAttention's std = 0.001 init, the MLPs the nn.Linear default -- same initial state here)
         self.concat = Concat(dimension=1)
         self.conv1x1_out = Conv(c1=d_model * 2, c2=d_model, k=1, s=1, p=0, g=1, act=True)
 

@@ -30,15 +30,21 @@ bool pdl_enabled() {
   }
   return v != 0;
 }
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
 int sm_count_cached() {
-  static int sms = 0;
-  if (sms <= 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        sms <= 0)
-      sms = 148;
+  static int sms[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  if (sms[dev] <= 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
   }
-  return sms;
+  return sms[dev];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -554,12 +554,8 @@ static int fill_attn(const void* qk_vis, const void* qk_ir, const void* vt_vis, 
 template <int D>
 static int launch_attn_pipe(const AttnParams& P, cudaStream_t st) {
   using L = AttnSmemP<D>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(cross_attn_pipe_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    if (e != cudaSuccess) return set_cuda_error(e, "cross_attention: cudaFuncSetAttribute");
-    configured = true;
-  }
+  static bool configured[kMaxDevices] = {false};
+  if (int rc = configure_smem(cross_attn_pipe_kernel<D>, L::kTotal, configured, "cross_attention: cudaFuncSetAttribute")) return rc;
   dim3 grid((P.n_pad + kQT - 1) / kQT, P.B * P.heads, 2);
   launch_k(cross_attn_pipe_kernel<D>, dim3(grid), dim3(160), L::kTotal, st, P);
   return check_launch("cross_attention");
@@ -568,12 +564,8 @@ static int launch_attn_pipe(const AttnParams& P, cudaStream_t st) {
 template <int D>
 static int launch_attn(const AttnParams& P, cudaStream_t st) {
   using L = AttnSmem<D>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(cross_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    if (e != cudaSuccess) return set_cuda_error(e, "cross_attention: cudaFuncSetAttribute");
-    configured = true;
-  }
+  static bool configured[kMaxDevices] = {false};
+  if (int rc = configure_smem(cross_attn_tc_kernel<D>, L::kTotal, configured, "cross_attention: cudaFuncSetAttribute")) return rc;
   dim3 grid((P.n_pad + kQT - 1) / kQT, P.B * P.heads, 2);
   launch_k(cross_attn_tc_kernel<D>, dim3(grid), dim3(160), L::kTotal, st, P);
   return check_launch("cross_attention");

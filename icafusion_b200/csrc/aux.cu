@@ -392,10 +392,14 @@ __global__ void detect_decode_kernel(const DetectParams P) {
 }
 
 __global__ void prefetch_l2_kernel(const char* __restrict__ p, size_t bytes) {
-  pdl_launch_dependents();          // no pdl_wait: the region holds parameters, no kernel writes it
+  pdl_launch_dependents();
+  // The region holds parameters (no kernel writes it), so the prefetches need not wait for the previous kernel ...
   size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 128;
   const size_t stride = size_t(gridDim.x) * blockDim.x * 128;
   for (; i < bytes; i += stride) prefetch_l2(p + i);
+  // ... but this grid must not COMPLETE before its predecessor does: the next kernel's griddepcontrol.wait only covers
+  // the grid launched right before it, so an early-finishing prefetch would let a consumer overtake its producer.
+  pdl_wait();
 }
 
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -518,6 +522,8 @@ extern "C" int icaf_detect_decode(const void* p, int64_t p_ld, void* x_out, void
                                   int na, int no, int total_rows, int row_off, float stride, const float* anchors_host,
                                   void* stream) {
   if (!p || !x_out || !z || !logits || !anchors_host || na < 1 || na > 8 || no < 6) return set_error(ICAF_ERR_BAD_ARG, "detect_decode: bad argument");
+  if (B < 1 || ny < 1 || nx < 1 || p_ld < (int64_t)na * no || row_off < 0 || (long long)row_off + (long long)na * ny * nx > total_rows)
+    return set_error(ICAF_ERR_BAD_ARG, "detect_decode: rows [row_off, row_off + na*ny*nx) must lie inside [0, total_rows) and p_ld >= na*no");
   DetectParams P;
   P.p = (const __half*)p; P.p_ld = p_ld; P.x_out = (__half*)x_out; P.z = (__half*)z; P.logits = (__half*)logits;
   P.B = B; P.ny = ny; P.nx = nx; P.na = na; P.no = no; P.total_rows = total_rows; P.row_off = row_off; P.stride = stride;

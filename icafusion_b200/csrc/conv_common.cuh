@@ -176,12 +176,29 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&acc)[16], const flo
   }
 }
 
-// persistent kernel (conv_persist.cu)
+// Host-side launch plan: everything the dispatcher decides before it touches CUDA.  icaf_conv2d_plan (host only, no
+// device needed) exposes it so that a CPU test can walk every layer geometry through the dispatcher's invariants.
+struct ConvPlan {
+  int kernel;                     // ICAF_KERNEL_TC / _PERSIST / _PAIR
+  int bn;                         // output-channel tile width
+  unsigned grid_x, grid_y, grid_z, cluster;
+  int smem;                       // dynamic shared memory per CTA (bytes)
+  int total, m_tiles, m_pairs, n_tiles;
+  int sms;                        // SM count the plan was made for
+};
+
+// Each kernel family: plan_* fills the launch shape (and P.stages / P.splits) and checks the kernel's invariants without
+// any CUDA call; launch_* encodes the TMA descriptors and launches exactly that plan.
+// persistent kernel (conv_persist.cu), BN = 32, 64, 128, 256
 template <int BN>
-int launch_persist(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
+int plan_persist(ConvParams& P, int n_io, ConvPlan& pl);
+template <int BN>
+int launch_persist(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
 
 // CTA-pair kernel (conv_pair.cu): 256 x BN tiles over two SMs, tcgen05.mma.cta_group::2 (BN = 64, 128, 256)
 template <int BN>
-int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
+int plan_pair(ConvParams& P, const icaf_conv_geom* g, int n_io, ConvPlan& pl);
+template <int BN>
+int launch_pair(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
 
 }  // namespace icaf

@@ -346,8 +346,9 @@ static int g_dbg = 0, g_dbg_bn = 0;       // probe builds only: see icaf_debug_s
 #else
 constexpr int g_dbg = 0, g_dbg_bn = 0;
 #endif
-static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, ConvParams& P, const __half* (&w)[2]) {
-  if (!g || !io || n_io < 1 || n_io > 2) return set_error(ICAF_ERR_BAD_ARG, "conv2d: need 1 or 2 problems");
+// Geometry half of the argument check (host only): everything the planner needs, no pointers.
+static int fill_geom(const icaf_conv_geom* g, int n_io, ConvParams& P) {
+  if (!g || n_io < 1 || n_io > 2) return set_error(ICAF_ERR_BAD_ARG, "conv2d: need 1 or 2 problems");
   if (!(g->Cin == 4 || g->Cin % 8 == 0)) return set_error(ICAF_ERR_UNSUPPORTED, "conv2d: Cin must be 4 or a multiple of 8");
   if (g->Cin == 4 && (g->Wi % 2 || g->stride % 2 || g->pad % 2 || g->kw % 2))
     return set_error(ICAF_ERR_UNSUPPORTED, "conv2d: packed-image (Cin=4) path needs even Wi, stride, pad, kw");
@@ -362,6 +363,13 @@ static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io
   P.B = g->B; P.Hi = g->Hi; P.Wi = g->Wi; P.Cin = g->Cin; P.Ho = g->Ho; P.Wo = g->Wo;
   P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad = g->pad; P.act = g->act; P.epi = g->epi;
   P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.stages = 2; P.splits = 1; P.cblk = 64; P.halo = 0; P.dbg = g_dbg;
+  memset(P.p, 0, sizeof(P.p));
+  return ICAF_OK;
+}
+
+static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, ConvParams& P, const __half* (&w)[2]) {
+  if (!io) return set_error(ICAF_ERR_BAD_ARG, "conv2d: null io");
+  if (int rc = fill_geom(g, n_io, P)) return rc;
   for (int i = 0; i < 2; ++i) {
     const icaf_conv_io& s = io[i < n_io ? i : 0];
     bool need_res = g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES);
@@ -404,21 +412,18 @@ static void plan_a_mode(const icaf_conv_geom* g, ConvParams& P) {
 }
 
 template <int BN>
-static int launch_tc(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+static int plan_tc(ConvParams& P, int n_io, ConvPlan& pl) {
   using L = SmemLayout<BN>;
   constexpr int kSmemCap = 227 * 1024;
-  static bool configured = false;   // idempotent attribute; benign race
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute");
-    configured = true;
-  }
   const int mt = P.a_mode == A_TMA4D ? P.B * P.tiles_x * P.tiles_y : (P.M + BM - 1) / BM;
-  dim3 grid(mt, (P.N + BN - 1) / BN, n_io);
+  if (P.a_mode == A_TMA4D && !(P.tw >= 1 && P.th >= 1 && P.tw * P.th <= BM && P.tiles_x * P.tw >= P.Wo && P.tiles_y * P.th >= P.Ho &&
+                               P.cblk == 64 && P.Cin % 64 == 0))
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d(tc): 4-D tiles must cover the map with at most 128 pixels each, 64-channel blocks");
+  unsigned gx = unsigned(mt), gy = unsigned((P.N + BN - 1) / BN), gz = unsigned(n_io);
   // Ring depth: a grid that fits in one wave gets the whole SM (deep ring: the K loop is latency-bound at small M);
   // otherwise two CTAs share an SM so that one CTA's epilogue overlaps the other's main loop.
-  const long long ctas = (long long)grid.x * grid.y * grid.z;
-  const int budget = (ctas <= sm_count_cached() || BN > 128) ? kSmemCap : (kSmemCap / 2 - 1024);
+  const long long ctas = (long long)gx * gy * gz;
+  const int budget = (ctas <= pl.sms || BN > 128) ? kSmemCap : (kSmemCap / 2 - 1024);
   int stages = (budget - L::kTailBytes) / L::kStageBytes;
   const int nkb = P.k_pad / BK;
   if (stages > nkb) stages = nkb;
@@ -426,8 +431,8 @@ static int launch_tc(ConvParams& P, const __half* const (&w)[2], const icaf_conv
   if (stages < 2) stages = 2;
   // Split-K: a grid that leaves most SMs idle on a deep K loop is spread over clusters of `splits` CTAs per tile.
   int splits = 1;
-  if (ctas * 2 <= sm_count_cached() && nkb >= 8) {
-    splits = int(sm_count_cached() / ctas);
+  if (ctas * 2 <= pl.sms && nkb >= 8) {
+    splits = int(pl.sms / ctas);
     if (splits > 8) splits = 8;                    // portable cluster size
     if (splits > nkb / 4) splits = nkb / 4;        // >= 4 K blocks per CTA
     const int per_split = BM * (BN + 4) * 4;       // staged fp32 partial tile in the leader's ring
@@ -438,10 +443,23 @@ static int launch_tc(ConvParams& P, const __half* const (&w)[2], const icaf_conv
     const int per = (nkb + splits - 1) / splits;
     if (stages > per) stages = per < 2 ? 2 : per;
     while ((splits - 1) * (BM * (BN + 4) * 4) > stages * L::kStageBytes) ++stages;   // keep room for the partial tiles
-    grid.x *= splits;
+    gx *= splits;
   }
+  if (stages > kMaxStages || L::total(stages) > kSmemCap)
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d(tc): shared-memory plan exceeds the ring / 227 KB");
   P.stages = stages;
   P.splits = splits;
+  pl.kernel = ICAF_KERNEL_TC; pl.bn = BN;
+  pl.grid_x = gx; pl.grid_y = gy; pl.grid_z = gz; pl.cluster = unsigned(splits);
+  pl.smem = L::total(stages);
+  pl.total = int(ctas); pl.m_tiles = mt; pl.m_pairs = 0; pl.n_tiles = int(gy);
+  return ICAF_OK;
+}
+
+template <int BN>
+static int launch_tc(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+  static bool configured[kMaxDevices] = {false};
+  if (int rc = configure_smem(conv_gemm_tc_kernel<BN>, 227 * 1024, configured, "conv2d: cudaFuncSetAttribute")) return rc;
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < n_io; ++i) {
@@ -456,36 +474,32 @@ static int launch_tc(ConvParams& P, const __half* const (&w)[2], const icaf_conv
     if (rc) return rc;
   }
   if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
-  launch_kc(conv_gemm_tc_kernel<BN>, grid, dim3(kThreads), (size_t)L::total(stages), st, (unsigned)splits, P, maps);
+  launch_kc(conv_gemm_tc_kernel<BN>, dim3(pl.grid_x, pl.grid_y, pl.grid_z), dim3(kThreads), (size_t)pl.smem, st, pl.cluster, P, maps);
   return check_launch("conv2d_fwd");
 }
 
-}  // namespace icaf
+// ---------------------------------------------------------------------------------------------------
+// The dispatcher, host only: staging mode, tile shapes, kernel family and tile width for one layer geometry.  No CUDA call.
+// pair_mode: -1 = the ICAF_PAIR environment switch (default 1), 0 = never CTA pairs, 1 = heuristic, 2 = pairs wherever they can run.
+static int env_pair_mode() {
+  static const int v = []() { const char* e = getenv("ICAF_PAIR"); return !e ? 1 : (e[0] == '0' ? 0 : (e[0] == 'a' ? 2 : 1)); }();
+  return v;
+}
 
-using namespace icaf;
-
-#ifdef ICAF_PROBE
-// Probe builds only (not part of the ABI, absent from the shipped library): kernel-stage switches + forced tile width.
-extern "C" void icaf_debug_set(int dbg, int bn) { g_dbg = dbg; g_dbg_bn = bn; }
-#endif
-
-extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream) {
-  ConvParams P;
-  const __half* w[2];
-  int rc = fill_params(g, io, n_io, P, w);
-  if (rc) return rc;
+static int plan_conv(const icaf_conv_geom* g, int n_io, int sms, int pair_mode, ConvParams& P, ConvPlan& pl) {
+  memset(&pl, 0, sizeof(pl));
+  pl.sms = sms;
+  if (sms < 1) return set_error(ICAF_ERR_BAD_ARG, "conv2d: SM count must be positive");
   plan_a_mode(g, P);
-  cudaStream_t st = (cudaStream_t)stream;
   // Tile width: the widest BN that still yields at least ~one CTA per SM (two waves for the 1-CTA/SM BN=256); small
   // problems take BN=32 so that more SMs share the K loop.
   const long long mt = P.a_mode == A_TMA4D ? (long long)P.B * P.tiles_x * P.tiles_y : (P.M + BM - 1) / BM;
-  const int sms = sm_count_cached();
   auto ctas = [&](int bn) { return mt * ((P.N + bn - 1) / bn) * n_io; };
   // CTA pairs (conv_pair.cu): two SMs share one 256 x BN tile and each loads only half of the filter tile.  Measured
   // (yolov5l batch 16, profiles/): always a win at BN = 256 once a wave of clusters is full (or half full with a deep K
   // loop); at BN = 128 / 64 only for the deep-K (3x3) layers -- the short-K 1x1 layers are HBM / epilogue bound and lose
   // to the pair's extra synchronisation.  ICAF_PAIR=0 disables it, ICAF_PAIR=all forces it wherever it can run (tests).
-  static const int pair_env = []() { const char* e = getenv("ICAF_PAIR"); return !e ? 1 : (e[0] == '0' ? 0 : (e[0] == 'a' ? 2 : 1)); }();
+  const int pair_env = pair_mode < 0 ? env_pair_mode() : pair_mode;
   const bool pair_ok = pair_env && (P.a_mode == A_TMA2D || (P.a_mode == A_TMA4D && P.cblk == 64));
   const int nkb_all = P.k_pad / BK;
   auto pair_wanted = [&](int b) {
@@ -511,7 +525,7 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
   if (g_dbg_bn) bn = g_dbg_bn;
   // Many tiles per SM: the persistent kernel overlaps main loop and epilogue across tiles (conv_persist.cu).
   static const bool persist_on = []() { const char* e = getenv("ICAF_PERSISTENT"); return !(e && e[0] == '0'); }();
-  bool persistent = persist_on && ctas(bn) >= 2 * sms && P.a_mode != A_GATHER;   // both operands by TMA
+  const bool persistent = persist_on && ctas(bn) >= 2 * sms && P.a_mode != A_GATHER;   // both operands by TMA
   if (P.a_mode == A_TMA4D && P.cblk < 64 && !persistent) {      // small-Cin TMA staging exists in the persistent kernel only
     P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.cblk = 64;
   }
@@ -524,11 +538,14 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
     const long long pairs = (long long)g->B * tx * ty * ((P.N + 63) / 64) * n_io / 2;
     if (double(g->Wo) * g->Ho >= 0.6 * (double(tx) * ty * 128.0) && (pair_env == 2 || pairs >= sms / 2)) {
       P.halo = (bres_on && P.N <= 64) ? 2 : 1;           // 2: the filter (one 64-wide N tile, one channel block) stays resident
-      P.tw = 8; P.th = 16; P.tiles_x = tx; P.tiles_y = ty;
-      return launch_pair<64>(P, w, g, n_io, st);
+      P.tw = 8;
+      P.th = 16;
+      P.tiles_x = tx;
+      P.tiles_y = ty;
+      return plan_pair<64>(P, g, n_io, pl);
     }
   }
-  if (pair_wanted(bn)) {
+  if (pair_wanted(bn) && P.a_mode != A_GATHER) {
     // 3x3 / stride 1 layers on 16 x 8 pixel tiles: every activation row is fetched three times instead of nine (conv_pair.cu)
     if (halo64) {   // tiles may hang over the right / bottom edge (P5: 16 x 20)
       // (resident filter, halo mode 2, measured slower here: 233 vs 209 us at Cin = 64, N = 64)
@@ -539,24 +556,75 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
       P.tiles_y = (g->Ho + 15) / 16;
     }
     switch (bn) {
-      case 256: return launch_pair<256>(P, w, g, n_io, st);
-      case 128: return launch_pair<128>(P, w, g, n_io, st);
-      default: return launch_pair<64>(P, w, g, n_io, st);
+      case 256: return plan_pair<256>(P, g, n_io, pl);
+      case 128: return plan_pair<128>(P, g, n_io, pl);
+      default: return plan_pair<64>(P, g, n_io, pl);
     }
   }
   if (persistent) {
     switch (bn) {
-      case 256: return launch_persist<256>(P, w, g, n_io, st);
-      case 128: return launch_persist<128>(P, w, g, n_io, st);
-      case 64: return launch_persist<64>(P, w, g, n_io, st);
-      default: return launch_persist<32>(P, w, g, n_io, st);
+      case 256: return plan_persist<256>(P, n_io, pl);
+      case 128: return plan_persist<128>(P, n_io, pl);
+      case 64: return plan_persist<64>(P, n_io, pl);
+      default: return plan_persist<32>(P, n_io, pl);
     }
   }
   switch (bn) {
-    case 256: return launch_tc<256>(P, w, g, n_io, st);
-    case 128: return launch_tc<128>(P, w, g, n_io, st);
-    case 64: return launch_tc<64>(P, w, g, n_io, st);
-    default: return launch_tc<32>(P, w, g, n_io, st);
+    case 256: return plan_tc<256>(P, n_io, pl);
+    case 128: return plan_tc<128>(P, n_io, pl);
+    case 64: return plan_tc<64>(P, n_io, pl);
+    default: return plan_tc<32>(P, n_io, pl);
+  }
+}
+
+}  // namespace icaf
+
+using namespace icaf;
+
+#ifdef ICAF_PROBE
+// Probe builds only (not part of the ABI, absent from the shipped library): kernel-stage switches + forced tile width.
+extern "C" void icaf_debug_set(int dbg, int bn) { g_dbg = dbg; g_dbg_bn = bn; }
+#endif
+
+extern "C" int icaf_conv2d_plan(const icaf_conv_geom* g, int n_io, int sm_count, int pair_mode, icaf_conv_plan* out) {
+  if (!out) return set_error(ICAF_ERR_BAD_ARG, "conv2d_plan: null output");
+  ConvParams P;
+  int rc = fill_geom(g, n_io, P);
+  if (rc) return rc;
+  ConvPlan pl;
+  rc = plan_conv(g, n_io, sm_count, pair_mode, P, pl);
+  if (rc) return rc;
+  out->kernel = pl.kernel; out->bn = pl.bn; out->a_mode = P.a_mode;
+  out->tile_w = P.tw; out->tile_h = P.th; out->tiles_x = P.tiles_x; out->tiles_y = P.tiles_y;
+  out->cblk = P.cblk; out->halo = P.halo; out->stages = P.stages; out->splits = P.splits;
+  out->grid_x = int(pl.grid_x); out->grid_y = int(pl.grid_y); out->grid_z = int(pl.grid_z); out->cluster = int(pl.cluster);
+  out->smem_bytes = pl.smem; out->work_items = pl.total;
+  return ICAF_OK;
+}
+
+extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream) {
+  ConvParams P;
+  const __half* w[2];
+  int rc = fill_params(g, io, n_io, P, w);
+  if (rc) return rc;
+  ConvPlan pl;
+  rc = plan_conv(g, n_io, sm_count_cached(), -1, P, pl);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int key = pl.kernel * 1000 + pl.bn;
+  switch (key) {
+    case ICAF_KERNEL_PAIR * 1000 + 256: return launch_pair<256>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_PAIR * 1000 + 128: return launch_pair<128>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_PAIR * 1000 + 64: return launch_pair<64>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_PERSIST * 1000 + 256: return launch_persist<256>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_PERSIST * 1000 + 128: return launch_persist<128>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_PERSIST * 1000 + 64: return launch_persist<64>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_PERSIST * 1000 + 32: return launch_persist<32>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_TC * 1000 + 256: return launch_tc<256>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_TC * 1000 + 128: return launch_tc<128>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_TC * 1000 + 64: return launch_tc<64>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_TC * 1000 + 32: return launch_tc<32>(P, pl, w, g, n_io, st);
+    default: return set_error(ICAF_ERR_BAD_ARG, "conv2d: the planner produced an unknown kernel / tile width");
   }
 }
 

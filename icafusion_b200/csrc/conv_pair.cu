@@ -465,33 +465,45 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
 }
 
 template <int BN>
-int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+int plan_pair(ConvParams& P, const icaf_conv_geom* g, int n_io, ConvPlan& pl) {
   using L = QSmem<BN>;
-  constexpr int kQBN = BN;
-  constexpr int kQSmem = L::kSmem;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute (pair)");
-    configured = true;
-  }
+  if (!(P.a_mode == A_TMA2D || P.a_mode == A_TMA4D)) return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): both operands must arrive by TMA");
   const int m_tiles = P.a_mode == A_TMA4D ? P.B * P.tiles_x * P.tiles_y : (P.M + BM - 1) / BM;
   const int m_pairs = (m_tiles + 1) / 2;
-  const int n_tiles = (P.N + kQBN - 1) / kQBN;
+  const int n_tiles = (P.N + BN - 1) / BN;
   const int total = m_pairs * n_tiles * n_io;
-  // invariants the kernel's halo paths rely on (the dispatcher in conv_gemm.cu establishes them; fail loudly if it ever does not)
-  if (P.halo && !(g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && P.tw == 8 && P.th == 16 &&
+  // invariants the kernel's paths rely on (the dispatcher in conv_gemm.cu establishes them; fail loudly if it ever does not)
+  if (P.a_mode == A_TMA4D && !(P.tw >= 1 && P.th >= 1 && P.tw * P.th <= BM && P.tiles_x * P.tw >= P.Wo && P.tiles_y * P.th >= P.Ho))
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): 4-D tiles must cover the map with at most 128 pixels each");
+  if (P.halo && !(P.a_mode == A_TMA4D && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && P.tw == 8 && P.th == 16 &&
                   (P.Cin % 64 == 0 || P.Cin == 16 || P.Cin == 32)))
     return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): halo copies need a 3x3 / stride 1 / pad 1 layer on 16 x 8 tiles");
+  if (!P.halo && P.a_mode == A_TMA4D && P.cblk != 64)
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): tap boxes need 64-channel blocks");
   if (P.halo == 2 && !(n_tiles == 1 && P.Cin <= 64))
     return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): the resident-filter mode needs one channel block and one N tile");
   P.stages = L::kStages;
   P.splits = 1;
+  const int max_clusters = pl.sms / 2;
+  if (max_clusters < 1) return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): needs at least two SMs");
+  const int waves = (total + max_clusters - 1) / max_clusters;
+  const int clusters = (total + waves - 1) / waves;
+  pl.kernel = ICAF_KERNEL_PAIR; pl.bn = BN;
+  pl.grid_x = unsigned(2 * clusters); pl.grid_y = pl.grid_z = 1; pl.cluster = 2;
+  pl.smem = P.halo == 2 ? L::kResSmem : (P.halo ? L::kHaloSmem : L::kSmem);
+  if (pl.smem > 227 * 1024) return set_error(ICAF_ERR_BAD_ARG, "conv2d(pair): shared-memory plan exceeds 227 KB");
+  pl.total = total; pl.m_tiles = m_tiles; pl.m_pairs = m_pairs; pl.n_tiles = n_tiles;
+  return ICAF_OK;
+}
+
+template <int BN>
+int launch_pair(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+  static bool configured[kMaxDevices] = {false};
+  if (int rc = configure_smem(conv_gemm_pair_kernel<BN>, 227 * 1024, configured, "conv2d: cudaFuncSetAttribute (pair)")) return rc;
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < n_io; ++i) {
-    int rc = encode_tmap_2d(&maps.w[i], w[i], (uint64_t)P.k_pad, (uint64_t)g->w_rows, (uint64_t)P.k_pad * 2, BK, kQBN / 2);
+    int rc = encode_tmap_2d(&maps.w[i], w[i], (uint64_t)P.k_pad, (uint64_t)g->w_rows, (uint64_t)P.k_pad * 2, BK, BN / 2);
     if (rc) return rc;
     const ConvProblem& pr = P.p[i];
     if (P.a_mode == A_TMA2D)
@@ -503,15 +515,16 @@ int launch_pair(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom
     if (rc) return rc;
   }
   if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
-  const int max_clusters = sm_count_cached() / 2;
-  const int waves = (total + max_clusters - 1) / max_clusters;
-  const int clusters = (total + waves - 1) / waves;
-  launch_kc(conv_gemm_pair_kernel<BN>, dim3(2 * clusters), dim3(kQThreads), (size_t)(P.halo == 2 ? L::kResSmem : (P.halo ? L::kHaloSmem : kQSmem)), st, 2u, P, maps, total, m_tiles, m_pairs, n_tiles);
+  launch_kc(conv_gemm_pair_kernel<BN>, dim3(pl.grid_x), dim3(kQThreads), (size_t)pl.smem, st, 2u, P, maps, pl.total, pl.m_tiles, pl.m_pairs, pl.n_tiles);
   return check_launch("conv2d_fwd(pair)");
 }
 
-template int launch_pair<64>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
-template int launch_pair<128>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
-template int launch_pair<256>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
+#define ICAF_INST(BN)                                                                                              \
+  template int plan_pair<BN>(ConvParams&, const icaf_conv_geom*, int, ConvPlan&);                                  \
+  template int launch_pair<BN>(const ConvParams&, const ConvPlan&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
+ICAF_INST(64)
+ICAF_INST(128)
+ICAF_INST(256)
+#undef ICAF_INST
 
 }  // namespace icaf

@@ -331,22 +331,34 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
 }
 
 template <int BN>
-int launch_persist(ConvParams& P, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+int plan_persist(ConvParams& P, int n_io, ConvPlan& pl) {
   using L = PSmem<BN>;
   constexpr int kSmemCap = 227 * 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv2d: cudaFuncSetAttribute (persistent)");
-    configured = true;
-  }
+  if (P.a_mode == A_GATHER) return set_error(ICAF_ERR_BAD_ARG, "conv2d(persistent): both operands must arrive by TMA");
   const int m_tiles = P.a_mode == A_TMA4D ? P.B * P.tiles_x * P.tiles_y : (P.M + BM - 1) / BM;
   const int n_tiles = (P.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * n_io;
+  if (P.a_mode == A_TMA4D && !(P.tw >= 1 && P.th >= 1 && P.tw * P.th <= BM && P.tiles_x * P.tw >= P.Wo && P.tiles_y * P.th >= P.Ho &&
+                               (P.cblk == 64 || P.cblk == 32 || P.cblk == 16) && P.Cin % P.cblk == 0))
+    return set_error(ICAF_ERR_BAD_ARG, "conv2d(persistent): 4-D tiles must cover the map with at most 128 pixels each");
   int stages = (kSmemCap - L::kTailBytes) / L::kStageBytes;
   if (stages > kPMaxStages) stages = kPMaxStages;
+  if (stages < 2) return set_error(ICAF_ERR_BAD_ARG, "conv2d(persistent): ring shallower than two stages");
   P.stages = stages;
   P.splits = 1;
+  // balanced static schedule: every CTA gets ceil(total/waves) or one fewer tiles
+  const int waves = (total + pl.sms - 1) / pl.sms;
+  pl.kernel = ICAF_KERNEL_PERSIST; pl.bn = BN;
+  pl.grid_x = unsigned((total + waves - 1) / waves); pl.grid_y = pl.grid_z = 1; pl.cluster = 1;
+  pl.smem = L::total(stages);
+  pl.total = total; pl.m_tiles = m_tiles; pl.m_pairs = 0; pl.n_tiles = n_tiles;
+  return ICAF_OK;
+}
+
+template <int BN>
+int launch_persist(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+  static bool configured[kMaxDevices] = {false};
+  if (int rc = configure_smem(conv_gemm_persist_kernel<BN>, 227 * 1024, configured, "conv2d: cudaFuncSetAttribute (persistent)")) return rc;
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < n_io; ++i) {
@@ -361,17 +373,17 @@ int launch_persist(ConvParams& P, const __half* const (&w)[2], const icaf_conv_g
     if (rc) return rc;
   }
   if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
-  const int sms = sm_count_cached();
-  // balanced static schedule: every CTA gets ceil(total/waves) or one fewer tiles
-  const int waves = (total + sms - 1) / sms;
-  const int grid = (total + waves - 1) / waves;
-  launch_k(conv_gemm_persist_kernel<BN>, dim3(grid), dim3(kPThreads), (size_t)L::total(stages), st, P, maps, total, m_tiles, n_tiles);
+  launch_k(conv_gemm_persist_kernel<BN>, dim3(pl.grid_x), dim3(kPThreads), (size_t)pl.smem, st, P, maps, pl.total, pl.m_tiles, pl.n_tiles);
   return check_launch("conv2d_fwd(persistent)");
 }
 
-template int launch_persist<32>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
-template int launch_persist<64>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
-template int launch_persist<128>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
-template int launch_persist<256>(ConvParams&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
+#define ICAF_INST(BN)                                                                                              \
+  template int plan_persist<BN>(ConvParams&, int, ConvPlan&);                                                      \
+  template int launch_persist<BN>(const ConvParams&, const ConvPlan&, const __half* const (&)[2], const icaf_conv_geom*, int, cudaStream_t);
+ICAF_INST(32)
+ICAF_INST(64)
+ICAF_INST(128)
+ICAF_INST(256)
+#undef ICAF_INST
 
 }  // namespace icaf

@@ -13,7 +13,8 @@ namespace icaf {
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
 int check_launch(const char* where);   // cudaGetLastError after a launch; never synchronises
-int sm_count_cached();
+int sm_count_cached();   // SM count of the CURRENT device (cached per device ordinal)
+int current_device();    // cudaGetDevice; -1 on error
 bool pdl_enabled();        // programmatic dependent launch on every kernel (env ICAF_PDL, default on)
 
 // Launch with the programmatic-stream-serialization attribute when PDL is enabled (every kernel of this library
@@ -45,6 +46,20 @@ inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   return launch_kc(kernel, grid, block, smem, st, 1u, static_cast<Args&&>(args)...);
+}
+
+// Opt a kernel into > 48 KB of dynamic shared memory once per device (the attribute is per device and per function):
+// `done` is the caller's static per-device flag array.
+constexpr int kMaxDevices = 64;
+template <typename K>
+inline int configure_smem(K kernel, int bytes, bool (&done)[kMaxDevices], const char* where) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return set_error(ICAF_ERR_CUDA, "no current CUDA device (or ordinal >= 64)");
+  if (done[dev]) return ICAF_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_cuda_error(e, where);
+  done[dev] = true;      // idempotent attribute; a race between two threads only sets it twice
+  return ICAF_OK;
 }
 
 // TMA descriptors (host side). fp16 tensors, 128-byte swizzle, zero fill out of bounds.

@@ -60,6 +60,35 @@ class profile:
         return out
 
 
+_DRY = None            # when a list: no kernel is launched; every C-ABI call is recorded as (name, args, work)
+
+
+class dry_run:
+    """Context manager: walk the product path without a GPU.  Tensors live on the ``meta`` device (shapes and strides
+    only), packed filters stay where the module is (CPU), and every C-ABI call is recorded instead of launched:
+    ``records`` = [(entry point, ctypes args, work dict)].  Convolution records keep their ``ConvGeom`` so a test can feed
+    the exact geometries of a model to ``icaf_conv2d_plan`` (tests/test_abi_cpu.py)."""
+
+    def __enter__(self):
+        global _DRY
+        self.records = []
+        _DRY = self.records
+        return self
+
+    def __exit__(self, *a):
+        global _DRY
+        _DRY = None
+
+
+def dry_running() -> bool:
+    return _DRY is not None
+
+
+def on_device(t: torch.Tensor) -> bool:
+    """True for CUDA tensors (and for anything while a dry run is recording: meta activations, CPU-resident filters)."""
+    return t.is_cuda or _DRY is not None
+
+
 _WEIGHT_TRACE = None   # when a list: (container, key) of every weight tensor a forward consumes
 
 
@@ -121,6 +150,9 @@ def _stream() -> C.c_void_p:
 
 def _call(name: str, fn, args, work=None):
     """Invoke one C-ABI kernel launcher on the current stream (optionally event-bracketed)."""
+    if _DRY is not None:
+        _DRY.append((name, args, work or {}))
+        return
     if _PROFILE is not None:
         if _PROFILE.last is None:
             _PROFILE.mark()
@@ -136,7 +168,7 @@ def _call(name: str, fn, args, work=None):
 
 def _check_view(t: torch.Tensor, what: str) -> int:
     """Validate an fp16 NHWC view and return its pixel pitch (elements)."""
-    if t.dtype != torch.float16 or not t.is_cuda or t.dim() != 4:
+    if t.dtype != torch.float16 or not on_device(t) or t.dim() != 4:
         raise ValueError(f"{what}: expected a CUDA fp16 (B,H,W,C) tensor, got {t.dtype} {tuple(t.shape)} on {t.device}")
     B, H, W, Cc = t.shape
     ld = t.stride(2) if W > 1 else (t.stride(1) if H > 1 else (t.stride(0) if B > 1 else Cc))
@@ -191,8 +223,14 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], act: int = A
     return pack_conv_weight(weight.detach()[:, :, None, None], bias, 1, 0, act, device)
 
 
+def _addr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return 0 if t.device.type == "meta" else t.data_ptr()
+
+
 def _ptr(t: Optional[torch.Tensor]):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    return C.c_void_p(_addr(t) or 0)
 
 
 def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Optional[Sequence[torch.Tensor]] = None,
@@ -223,22 +261,23 @@ def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Option
             raise ValueError("conv2d: grouped problems must share one geometry")
         if tuple(outs[i].shape) != (B, Ho, Wo, p0.cout):
             raise ValueError(f"conv2d: output shape {tuple(outs[i].shape)} != {(B, Ho, Wo, p0.cout)}")
-        ios[i].x, ios[i].x_ld = xs[i].data_ptr(), _check_view(xs[i], "conv2d input")
-        ios[i].w = pk.w.data_ptr()
-        ios[i].bias = pk.bias.data_ptr() if pk.bias is not None else None
-        ios[i].y, ios[i].y_ld = outs[i].data_ptr(), _check_view(outs[i], "conv2d output")
+        ios[i].x, ios[i].x_ld = _addr(xs[i]), _check_view(xs[i], "conv2d input")
+        ios[i].w = _addr(pk.w)
+        ios[i].bias = _addr(pk.bias)
+        ios[i].y, ios[i].y_ld = _addr(outs[i]), _check_view(outs[i], "conv2d output")
         if res is not None:
             if tuple(res[i].shape) != (B, Ho, Wo, p0.cout):
                 raise ValueError("conv2d: residual shape mismatch")
-            ios[i].res, ios[i].res_ld = res[i].data_ptr(), _check_view(res[i], "conv2d residual")
+            ios[i].res, ios[i].res_ld = _addr(res[i]), _check_view(res[i], "conv2d residual")
         if scaled is not None:
-            ios[i].alpha, ios[i].beta = scaled[i][0].data_ptr(), scaled[i][1].data_ptr()
+            ios[i].alpha, ios[i].beta = _addr(scaled[i][0]), _addr(scaled[i][1])
     fn = _lib.lib().icaf_conv2d_fwd_simt if simt else _lib.lib().icaf_conv2d_fwd
     M = B * Ho * Wo
     kk = p0.kh * p0.kw * p0.cin
     work = {"tag": f"M{M} N{p0.cout} K{kk} k{p0.kh}s{p0.stride} x{n}" + (" +res" if res is not None else ""),
             "flops": 2.0 * M * p0.cout * kk * n,
             "bytes": 2.0 * n * (B * Hi * Wi * p0.cin + M * p0.cout * (2 if res is not None else 1) + p0.cout * kk)}
+    work["geom"], work["n_io"] = g, n
     _call("icaf_conv2d_fwd_simt" if simt else "icaf_conv2d_fwd", fn, (C.byref(g), ios, n), work)
     return list(outs)
 
@@ -267,7 +306,7 @@ def pack_stem_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], act: in
 
 def pack_image(img: torch.Tensor, scale: float = 1.0, s2d: bool = False) -> torch.Tensor:
     """(B,3,H,W) fp16 / fp32 / uint8 planar image -> (B,H,W,4) fp16, or with `s2d` -> (B,H/2,W/2,16) space-to-depth."""
-    if img.dim() != 4 or img.shape[1] != 3 or not img.is_cuda:
+    if img.dim() != 4 or img.shape[1] != 3 or not on_device(img):
         raise ValueError(f"pack_image: expected a CUDA (B,3,H,W) tensor, got {tuple(img.shape)}")
     code = {torch.float16: 0, torch.float32: 1, torch.uint8: 2}.get(img.dtype)
     if code is None:
@@ -297,6 +336,8 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     B, H, W, Cc = x.shape
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, Cc, dtype=torch.float16, device=x.device)
+    elif tuple(out.shape) != (B, 2 * H, 2 * W, Cc):
+        raise ValueError(f"upsample2x: output shape {tuple(out.shape)} != {(B, 2 * H, 2 * W, Cc)}")
     _call("icaf_upsample2x", _lib.lib().icaf_upsample2x, (_ptr(x), _check_view(x, "upsample x"), _ptr(out), _check_view(out, "upsample out"),
                                                         B, H, W, Cc), {"bytes": 10.0 * x.numel()})
     return out
@@ -304,7 +345,8 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
 
 def copy_channels(x: torch.Tensor, out: torch.Tensor) -> None:
     B, H, W, Cc = x.shape
-    assert tuple(out.shape) == tuple(x.shape)
+    if tuple(out.shape) != tuple(x.shape):
+        raise ValueError(f"copy_channels: output shape {tuple(out.shape)} != {tuple(x.shape)}")
     _call("icaf_copy_channels", _lib.lib().icaf_copy_channels, (_ptr(x), _check_view(x, "copy x"), _ptr(out), _check_view(out, "copy out"),
                                                               B * H * W, Cc), {"bytes": 4.0 * x.numel()})
 
@@ -352,7 +394,12 @@ def dmff_upsample_cat(tok_vis, tok_ir, x_vis, x_ir, nh: int, nw: int, mode: int 
     B, H, W, Cc = x_vis.shape
     out = torch.empty(B, H, W, 2 * Cc, dtype=torch.float16, device=x_vis.device)
     ld = _check_view(x_vis, "dmff x_vis")
-    assert _check_view(x_ir, "dmff x_ir") == ld and tok_vis.is_contiguous() and tok_ir.is_contiguous()
+    if tuple(x_ir.shape) != tuple(x_vis.shape) or _check_view(x_ir, "dmff x_ir") != ld:
+        raise ValueError("dmff_upsample_cat: the two feature maps must share shape and pitch")
+    n_pad = tok_vis.shape[1]
+    if tuple(tok_vis.shape) != (B, n_pad, Cc) or tuple(tok_ir.shape) != (B, n_pad, Cc) or n_pad < nh * nw or \
+            not (tok_vis.is_contiguous() and tok_ir.is_contiguous()):
+        raise ValueError(f"dmff_upsample_cat: token tensors must be contiguous (B, >= {nh * nw}, {Cc})")
     _call("icaf_dmff_upsample_cat", _lib.lib().icaf_dmff_upsample_cat,
           (_ptr(tok_vis), _ptr(tok_ir), tok_vis.shape[1], _ptr(x_vis), _ptr(x_ir), ld, _ptr(out), 2 * Cc, B, H, W, Cc, nh, nw, mode),
           {"bytes": 2.0 * (2 * x_vis.numel() + out.numel() + 2 * tok_vis.numel())})
@@ -362,7 +409,10 @@ def dmff_upsample_cat(tok_vis, tok_ir, x_vis, x_ir, nh: int, nw: int, mode: int 
 def detect_decode(p: torch.Tensor, na: int, no: int, z: torch.Tensor, logits: torch.Tensor, row_off: int, stride: float,
                   anchors_px: Sequence[float]) -> torch.Tensor:
     """p: (B,ny,nx,>=na*no) conv output. Fills rows [row_off, row_off+na*ny*nx) of z/logits; returns x (B,na,ny,nx,no)."""
-    B, ny, nx, _ = p.shape
+    B, ny, nx, pc = p.shape
+    if pc < na * no or z.shape[0] != B or logits.shape[:2] != z.shape[:2] or z.shape[2] != no or logits.shape[2] != no - 5 or \
+            row_off < 0 or row_off + na * ny * nx > z.shape[1]:
+        raise ValueError(f"detect_decode: level ({ny}x{nx}, {na} anchors) at row {row_off} does not fit z {tuple(z.shape)}")
     x_out = torch.empty(B, na, ny, nx, no, dtype=torch.float16, device=p.device)
     anch = (C.c_float * (2 * na))(*[float(a) for a in anchors_px])
     _call("icaf_detect_decode", _lib.lib().icaf_detect_decode,

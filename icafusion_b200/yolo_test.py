@@ -72,10 +72,13 @@ class Detect(nn.Module):
         """One detection level: 1x1 conv (yolo_test.py:49) + decode (:50-63) into rows [off, off+na*ny*nx) of z/logits."""
         if self.training:
             raise NotImplementedError("Detect: training-mode forward is not built yet in icafusion_b200")
-        anchor_px = self.__dict__.get("_icaf_anchor_px")
-        if anchor_px is None:                      # host copy of anchor_grid (pixels); constant after build
-            anchor_px = self.anchor_grid.detach().float().cpu().view(self.nl, -1).tolist()
-            self.__dict__["_icaf_anchor_px"] = anchor_px
+        ag = self.anchor_grid
+        key = (ag.data_ptr(), ag._version, ag.device)
+        cache = self.__dict__.get("_icaf_anchor_px")
+        if cache is None or cache[0] != key:       # host copy of anchor_grid (pixels); re-read when the buffer changes
+            cache = (key, ag.detach().float().cpu().view(self.nl, -1).tolist())
+            self.__dict__["_icaf_anchor_px"] = cache
+        anchor_px = cache[1]
         p = ops.conv2d([v], [self._packed(i)])[0]
         return ops.detect_decode(p, self.na, self.no, z, logits, off, float(self.stride[i]), anchor_px[i])
 
@@ -90,6 +93,15 @@ class Detect(nn.Module):
         for i in range(self.nl):
             x[i] = xs[i]                 # the reference overwrites its input list in place (yolo_test.py:49-51)
         return z, logits, x
+
+
+def check_anchor_order(m: "Detect") -> None:
+    """Anchor areas must grow with the stride; flip the levels if the YAML lists them the other way round
+    (reference: utils/autoanchor.py:12-20, called from Model.__init__, yolo_test.py:106)."""
+    a = m.anchor_grid.prod(-1).view(-1)
+    if (a[-1] - a[0]).sign() != (m.stride[-1] - m.stride[0]).sign():
+        m.anchors[:] = m.anchors.flip(0)
+        m.anchor_grid[:] = m.anchor_grid.flip(0)
 
 
 def fuse_conv_and_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
@@ -173,6 +185,7 @@ class Model(nn.Module):
         if isinstance(m, Detect):
             m.stride = torch.Tensor([8.0, 16.0, 32.0])              # yolo_test.py:104 (hard-coded in the reference)
             m.anchors /= m.stride.view(-1, 1, 1)
+            check_anchor_order(m)
             self.stride = m.stride
         for mod in self.modules():                                    # utils/torch_utils.py:144-154
             if type(mod) is nn.BatchNorm2d:
@@ -239,6 +252,13 @@ class Model(nn.Module):
     def forward(self, x, x2, augment=False, profile=False):
         if augment:
             raise NotImplementedError("augmented (multi-scale / flip) inference is outside the hot path built here")
+        if tuple(x.shape) != tuple(x2.shape):
+            raise ValueError(f"RGB and IR batches must share one shape, got {tuple(x.shape)} and {tuple(x2.shape)}")
+        smax = int(self.stride.max()) if hasattr(self, "stride") else 32
+        if x.dim() != 4 or x.shape[2] % smax or x.shape[3] % smax:
+            # the reference fails at torch.cat for such inputs (models/common.py:321); here the concat buffers are planned
+            # from the stride pyramid, so reject up front
+            raise ValueError(f"image height and width must be multiples of the maximum stride {smax}, got {tuple(x.shape)}")
         return self.forward_once(x, x2, profile)
 
     def forward_once(self, x, x2, profile=False):
@@ -267,7 +287,7 @@ class Model(nn.Module):
         """Image staging for the stem layer `stem` (a Conv taking the 3-channel image)."""
         if img.dim() != 4 or img.shape[1] != 3:
             raise ValueError(f"expected (B,3,H,W) images, got {tuple(img.shape)}")
-        if not img.is_cuda:
+        if not ops.on_device(img):
             raise RuntimeError("icafusion_b200 runs on CUDA tensors only (no CPU fallback)")
         if isinstance(stem, Conv) and stem.conv.in_channels == 3:
             return stem.stage_image(img)
@@ -289,10 +309,11 @@ class Model(nn.Module):
         layers = list(self.model)
         y: List = [None] * len(layers)
         dev = rgb.device
-        main = torch.cuda.current_stream(dev)
+        dry = ops.dry_running()                   # shape-only walk on meta tensors (no streams, nothing launched)
+        main = None if dry else torch.cuda.current_stream(dev)
         forked = {}                               # layer index -> side stream its result is being produced on
         n_side = [0]
-        concurrent = self.__dict__.get("_icaf_concurrent", True)
+        concurrent = self.__dict__.get("_icaf_concurrent", True) and not dry
 
         def fork():
             st = self._side_streams(dev, n_side[0] + 1)[n_side[0]]

@@ -79,6 +79,28 @@ typedef struct {
 
 int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream);
 
+/* The dispatcher's decision for one layer geometry, computed on the HOST only (no device, no stream, no pointers):
+ * which kernel family runs it, with which tile shapes, grid and shared memory.  icaf_conv2d_fwd launches exactly the
+ * plan this returns for (geometry, n_io, SM count of the current device, ICAF_PAIR switch); the same invariant checks
+ * run in both, so a GPU-less test can walk every layer of a model through the dispatcher (tests/test_abi_cpu.py).
+ * pair_mode: -1 = environment default (ICAF_PAIR), 0 = never CTA pairs, 1 = heuristic, 2 = pairs wherever possible. */
+#define ICAF_KERNEL_TC 0      /* one 128 x BN tile per CTA, split-K clusters   (conv_gemm.cu)    */
+#define ICAF_KERNEL_PERSIST 1 /* one CTA per SM looping over tiles              (conv_persist.cu) */
+#define ICAF_KERNEL_PAIR 2    /* CTA pairs, tcgen05 cta_group::2, halo copies   (conv_pair.cu)    */
+typedef struct {
+  int kernel;                            /* ICAF_KERNEL_*                                                     */
+  int bn;                                /* output-channel tile width (32/64/128/256)                         */
+  int a_mode;                            /* activation staging: 0 cp.async gather, 1 2-D TMA, 2 4-D TMA       */
+  int tile_w, tile_h, tiles_x, tiles_y;  /* 4-D TMA: output-pixel tile and tiles per image                    */
+  int cblk;                              /* channels per TMA box                                              */
+  int halo;                              /* pair kernel: 0 tap boxes, 1 x-shifted halo copies, 2 + resident filter */
+  int stages, splits;                    /* smem ring depth; split-K factor (= cluster size of the tc kernel) */
+  int grid_x, grid_y, grid_z, cluster;   /* launch shape                                                      */
+  int smem_bytes;                        /* dynamic shared memory per CTA                                     */
+  int work_items;                        /* tiles (tc/persist) or tile pairs (pair) the grid iterates over    */
+} icaf_conv_plan;
+int icaf_conv2d_plan(const icaf_conv_geom* g, int n_io, int sm_count, int pair_mode, icaf_conv_plan* out);
+
 /* Test-only CUDA-core reference of the same contract (slow, obviously-correct); used by tests to
  * localise tensor-core bugs on the device.  Not called by the product path. */
 int icaf_conv2d_fwd_simt(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream);

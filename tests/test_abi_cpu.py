@@ -72,3 +72,100 @@ def test_shipped_library_has_no_probe_hooks_and_counts_launches():
     io = (_lib.ConvIO * 1)()
     assert L.icaf_conv2d_fwd(ctypes.byref(g), io, 1, None) != 0
     assert L.icaf_kernel_launches() == n0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Host-only walk of the conv dispatcher over every layer geometry the detectors issue (no GPU): the product path is run
+# in dry mode (meta tensors, nothing launched), every recorded icaf_conv2d_fwd geometry goes through icaf_conv2d_plan --
+# the same planner + invariant checks icaf_conv2d_fwd runs before it launches.
+def _dry_geometries(size: str, B: int, H: int = 512, W: int = 640):
+    from icafusion_b200 import Model, ops
+    m = Model(f"yolov5{size}_Transfusion_kaist").eval().fuse().half()
+    rgb = torch.empty(B, 3, H, W, dtype=torch.uint8, device="meta")
+    with torch.no_grad(), ops.dry_run() as dr:
+        z, logits, xs = m(rgb, rgb)
+    assert z.shape[0] == B and z.shape[2] == 6
+    seen, out = set(), []
+    for name, args, work in dr.records:
+        if name != "icaf_conv2d_fwd":
+            continue
+        g, n = work["geom"], work["n_io"]
+        key = tuple(getattr(g, f) for f, _ in g._fields_) + (n,)
+        if key not in seen:
+            seen.add(key)
+            out.append((g, n, work["tag"]))
+    return out, len(dr.records)
+
+
+def _check_plan(g, n, pl, sms, tag):
+    from icafusion_b200 import _lib
+    where = f"{tag}: kernel {pl.kernel} bn {pl.bn} a_mode {pl.a_mode} halo {pl.halo}"
+    assert pl.kernel in (_lib.KERNEL_TC, _lib.KERNEL_PERSIST, _lib.KERNEL_PAIR) and pl.bn in (32, 64, 128, 256), where
+    assert 0 < pl.smem_bytes <= 227 * 1024, where
+    assert pl.grid_x >= 1 and pl.grid_y >= 1 and pl.grid_z >= 1 and pl.stages >= 1, where
+    ctas = pl.grid_x * pl.grid_y * pl.grid_z
+    if pl.a_mode == 2:       # 4-D TMA tiles cover the output map with <= 128 pixels per tile
+        assert 1 <= pl.tile_w * pl.tile_h <= 128, where
+        assert pl.tiles_x * pl.tile_w >= g.Wo and pl.tiles_y * pl.tile_h >= g.Ho, where
+        assert (pl.tiles_x - 1) * pl.tile_w < g.Wo and (pl.tiles_y - 1) * pl.tile_h < g.Ho, where
+        assert pl.cblk in (16, 32, 64) and g.Cin % pl.cblk == 0, where
+    if pl.halo:
+        assert pl.kernel == _lib.KERNEL_PAIR and pl.a_mode == 2 and (g.kh, g.kw, g.stride, g.pad) == (3, 3, 1, 1), where
+        assert (pl.tile_w, pl.tile_h) == (8, 16), where
+        assert (pl.tiles_x, pl.tiles_y) == ((g.Wo + 7) // 8, (g.Ho + 15) // 16), where
+    if pl.halo == 2:
+        assert g.Cin <= 64 and g.Cout <= pl.bn, where
+    if pl.kernel == _lib.KERNEL_PAIR:
+        assert pl.cluster == 2 and pl.grid_x % 2 == 0 and pl.grid_x <= sms and pl.a_mode in (1, 2), where
+        assert pl.grid_x // 2 <= pl.work_items, where
+    elif pl.kernel == _lib.KERNEL_PERSIST:
+        assert pl.cluster == 1 and pl.grid_x <= sms and pl.a_mode in (1, 2) and pl.grid_x <= pl.work_items, where
+    else:
+        assert pl.cluster == pl.splits and 1 <= pl.splits <= 8 and pl.grid_x % pl.splits == 0, where
+        if pl.a_mode == 2:
+            assert pl.cblk == 64, where
+        assert ctas == pl.work_items * pl.splits, where
+
+
+@pytest.mark.parametrize("size,B", [("s", 1), ("s", 16), ("l", 1), ("l", 16)])
+def test_dispatcher_plans_every_layer_geometry(size, B):
+    from icafusion_b200 import _lib
+    L = _lib.lib()
+    geoms, n_calls = _dry_geometries(size, B)
+    assert len(geoms) >= 25 and n_calls >= 60
+    kernels = set()
+    for g, n, tag in geoms:
+        for sms in (148, 132):
+            for pair_mode in (0, 1, 2):
+                pl = _lib.ConvPlan()
+                rc = L.icaf_conv2d_plan(ctypes.byref(g), n, sms, pair_mode, ctypes.byref(pl))
+                assert rc == 0, f"{tag} (sms {sms}, pair mode {pair_mode}): {L.icaf_last_error().decode()}"
+                _check_plan(g, n, pl, sms, tag)
+                if pair_mode == 0:
+                    assert pl.kernel != _lib.KERNEL_PAIR
+                if sms == 148 and pair_mode == 1:
+                    kernels.add((pl.kernel, pl.halo))
+    if (size, B) == ("l", 16):     # the compute-bound config exercises all three kernel families and both halo modes
+        assert {(0, 0), (1, 0), (2, 0), (2, 1), (2, 2)} <= kernels, kernels
+
+
+def test_dispatcher_plan_matches_small_and_odd_geometries():
+    """The GPU parity cases of tests/test_gpu_conv.py (ragged N, odd maps, strides, split-K shapes) plan cleanly too."""
+    from icafusion_b200 import _lib
+    L = _lib.lib()
+    cases = [(1, 8, 8, 64, 96, 1, 1, 0), (2, 20, 16, 64, 64, 3, 1, 1), (1, 16, 20, 512, 512, 3, 1, 1), (8, 64, 80, 64, 64, 3, 1, 1),
+             (1, 33, 47, 64, 128, 3, 2, 1), (16, 128, 160, 64, 64, 3, 1, 1), (1, 10, 10, 1024, 4096, 1, 1, 0),
+             (16, 256, 320, 16, 64, 3, 1, 1), (1, 256, 320, 16, 32, 3, 1, 1), (3, 17, 19, 24, 40, 3, 1, 1)]
+    for B, Hi, Wi, Cin, Cout, k, s, p in cases:
+        Ho, Wo = (Hi + 2 * p - k) // s + 1, (Wi + 2 * p - k) // s + 1
+        kp = (k * k * Cin + 63) // 64 * 64
+        g = _lib.ConvGeom(B, Hi, Wi, Cin, Ho, Wo, Cout, k, k, s, p, kp, (Cout + 31) // 32 * 32, 1, 0)
+        for n in (1, 2):
+            for pair_mode in (0, 1, 2):
+                pl = _lib.ConvPlan()
+                rc = L.icaf_conv2d_plan(ctypes.byref(g), n, 148, pair_mode, ctypes.byref(pl))
+                assert rc == 0, L.icaf_last_error().decode()
+                _check_plan(g, n, pl, 148, f"B{B} {Hi}x{Wi} {Cin}->{Cout} k{k}s{s}")
+    bad = _lib.ConvGeom(1, 8, 8, 12, 8, 8, 16, 1, 1, 1, 0, 64, 32, 0, 0)
+    assert L.icaf_conv2d_plan(ctypes.byref(bad), 1, 148, -1, ctypes.byref(_lib.ConvPlan())) == 2
+    assert L.icaf_conv2d_plan(ctypes.byref(g), 1, 0, -1, ctypes.byref(_lib.ConvPlan())) == 1
