@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 Workloads (BASELINE.json `configs`):
-    yolov5s_b1   (default)  configs[1]: yolov5s_ICAFusion, 640x512 synthetic RGB+IR, batch 1 per GPU, inference
-    yolov5l_b16             configs[2]: yolov5l_ICAFusion, batch 16 per GPU
+    yolov5l_b16  (default)  configs[2]: yolov5l_ICAFusion, 640x512 synthetic RGB+IR, batch 16 per GPU, inference -- the largest
+                            single-GPU configuration; the headline line at every N
+    yolov5s_b1              configs[1]: yolov5s_ICAFusion, batch 1 per GPU (latency-bound regime; reported under `secondary` at N=1)
 A "step" = one forward of the whole two-stream detector (stage images -> two CSPDarknet streams -> 3 DMFF blocks ->
 PANet head -> Detect decode) over one batch.  N>1: one process per GPU (torchrun), the batch dimension is sharded --
 every rank runs its own pairs, there is no collective on the inference path ("weak" scaling).
@@ -14,9 +15,13 @@ every rank runs its own pairs, there is no collective on the inference path ("we
            between steps, max over ranks.
 `e2e`    : pairs/s through the reference-facing call with HOST (pinned, uint8) frames: H2D + forward + D2H of the
            decoded predictions inside the timed region.
-`roofline`: the tcgen05 implicit-GEMM conv kernel (all Conv/Linear launches of one step): algorithmic FLOPs / event time.
+`roofline`: the tcgen05 implicit-GEMM conv kernels (every Conv / Linear / Detect GEMM of a step): algorithmic FLOPs of those
+           launches / the time they take INSIDE the timed step = ms_per_step x their share of the step's kernel time (the
+           share from a CUDA-event pass over one step on the launching stream; profiles/ holds the ncu launch list of the
+           same step for comparison), against the SUSTAINED tensor peak of MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the oracle (fp32 PyTorch-CPU restatement of the reference forward; the reference
-           itself is Python and cannot travel to the GPU box) timed on this host's cores.
+           itself is Python and cannot travel to the GPU box) timed on this host's cores at a FIXED intra-op thread count
+           (32, or fewer if the host has fewer usable cores) so the two arms share one denominator.
 """
 from __future__ import annotations
 
@@ -47,9 +52,10 @@ def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return p["bf16_tflops"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst)"
+        return {"tensor": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "tensor_burst": p["bf16_tflops"], "hbm": p["hbm_gbs"],
+                "src": "measured (MEASURED_PEAKS.json: bf16_tflops_sustained -- the kernels run inside a multi-ms step; hbm_gbs)"}
     except Exception:  # noqa: BLE001
-        return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return {"tensor": 1590.0, "tensor_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
@@ -106,10 +112,13 @@ def _usable_cpus() -> int:
     return n
 
 
-def cpu_reference_throughput(wl, budget_s=20.0, max_pairs=64):
-    """The reference's CPU path (oracle port: same torch CPU ops, fp32, fused BN) on the host cores; bounded sample.
-    PyTorch's intra-op pool does not scale to 100+ threads on these small convolutions (47 s/pair at 128 threads on the
-    GPU box vs 0.3 s at 8), so the thread count is picked by a short sweep and reported as `cores`."""
+CPU_THREADS = 32        # fixed intra-op thread count of the CPU arm: the fastest setting round 1's sweeps found on the GPU box (PyTorch's
+                        # pool stops scaling on these convolutions beyond it: 47 s/pair at 128 threads); both arms use it -> one denominator
+
+
+def cpu_reference_throughput(wl, budget_s=20.0, max_pairs=64, warm=1):
+    """The reference's CPU path (oracle port: same torch CPU ops, fp32, fused BN) on the host cores; bounded sample:
+    batch-1 forwards of the workload's model until `max_pairs` pairs or `budget_s` seconds, median forward time."""
     import torch
     from oracle import icaf_oracle as O
     from oracle import synth
@@ -117,30 +126,21 @@ def cpu_reference_throughput(wl, budget_s=20.0, max_pairs=64):
     B = 1                                   # the CPU sample runs batch 1 (latency-optimal on CPU)
     rgb, ir = synth.synth_images(B, wl["H"], wl["W"], 0)
     usable = _usable_cpus()
-    t_start = time.perf_counter()
-    best = None
+    nt = max(1, min(CPU_THREADS, usable))
+    torch.set_num_threads(nt)
     with torch.no_grad():
-        for nt in [t for t in (8, 16, 32, 64, 128, 256) if t <= usable] or [usable]:
-            torch.set_num_threads(nt)
-            O.model_forward(sd, cfg, rgb, ir)                     # warm-up at this thread count
-            t = time.perf_counter()
+        for _ in range(max(1, warm)):
             O.model_forward(sd, cfg, rgb, ir)
-            dt = time.perf_counter() - t
-            if best is None or dt < best[1]:
-                best = (nt, dt)
-            if dt > 1.15 * best[1] or time.perf_counter() - t_start > 0.4 * budget_s:
-                break            # past the scaling knee: more threads only add contention
-        torch.set_num_threads(best[0])
         t0, n, times = time.perf_counter(), 0, []
-        while n < max_pairs and (time.perf_counter() - t0) < 0.6 * budget_s:
+        while n < max_pairs and (time.perf_counter() - t0) < budget_s:
             t = time.perf_counter()
             O.model_forward(sd, cfg, rgb, ir)
             times.append(time.perf_counter() - t)
             n += B
     per = sorted(times)[len(times) // 2]
-    return {"value": round(B / per, 3), "unit": "pairs/s", "cores": best[0], "kind": "port",
+    return {"value": round(B / per, 3), "unit": "pairs/s", "cores": nt, "kind": "port",
             "sample": f"{n} pairs of {wl['desc'].split(',')[0]} at batch 1, fp32, median of {len(times)} forwards "
-                      f"({sum(times):.1f} s of CPU work) at the fastest intra-op thread count of a sweep up to {usable} usable cores; "
+                      f"({sum(times):.1f} s of CPU work) on {nt} intra-op threads (fixed; {usable} usable cores); "
                       "oracle/icaf_oracle.py (PyTorch-CPU restatement of the reference forward)",
             "cpu_model": _cpu_model(), "host_cpus": os.cpu_count()}
 
@@ -161,7 +161,8 @@ def run_reference(args, wl):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    cb = cpu_reference_throughput(wl, budget_s=min(120.0, 4.0 * (steps + args.warmup)), max_pairs=steps + args.warmup)
+    # one "step" of this arm = one pair of the workload (a bounded sample of its batch); W warm-up pairs, K timed pairs, capped at 90 s
+    cb = cpu_reference_throughput(wl, budget_s=90.0, max_pairs=steps, warm=max(1, min(args.warmup, 3)))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": round(1000.0 / cb["value"], 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -279,7 +280,7 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
             f.write("kernel,geometry,us,tflops,gbs\n")
             for name, tag, ms, fl, by in pl:
                 f.write(f"{name},{tag},{ms * 1e3:.2f},{fl / (ms * 1e-3) / 1e12 if ms > 0 else 0:.2f},{by / (ms * 1e-3) / 1e9 if ms > 0 else 0:.1f}\n")
-    conv = summ.get("icaf_conv2d_fwd", {"ms": 1.0, "flops": 0.0, "launches": 1})
+    conv = summ.get("icaf_conv2d_fwd", {"ms": 1.0, "flops": 0.0, "launches": 1, "bytes": 0.0})
     traffic, traffic_src = None, None      # DRAM bytes per conv launch from the committed ncu capture of the same step
     try:
         import glob
@@ -290,16 +291,30 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
         traffic_src = os.path.relpath(cands[-1], ROOT) + " (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the conv launches of one step)"
     except Exception:  # noqa: BLE001
         pass
-    tf_peak, hbm_peak, peak_src = _peaks()
-    ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+    pk = _peaks()
+    # The conv kernels' time INSIDE the timed step: the graph-replayed step time x their share of the step's kernel time
+    # (event pass: every launch bracketed on its stream; the share cancels the constant per-launch event overhead, which
+    # the absolute event times carry).  By construction launches x avg_launch_us <= ms_per_step.
     total_ms = sum(v["ms"] for v in summ.values())
+    share = conv["ms"] / total_ms if total_ms > 0 else 0.0
+    step_ms = dev_ms / K
+    conv_launches = conv["launches"] // reps
+    conv_ms_in_step = step_ms * share
+    conv_flops_step = conv["flops"] / reps
+    ach = conv_flops_step / (conv_ms_in_step * 1e-3) / 1e12 if conv_ms_in_step > 0 else 0.0
     roofline = {"kernel": "icaf_conv2d_fwd = conv_gemm_{tc,persist,pair}_kernel (every Conv/Linear/Detect GEMM of a step)", "bound": "tensor",
-                "achieved": round(ach, 3), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 5), "traffic": traffic, "traffic_source": traffic_src,
+                "achieved": round(ach, 3), "peak": pk["tensor"], "unit": "TFLOP/s", "frac": round(ach / pk["tensor"], 5),
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_flops_per_launch": round(conv_flops_step / max(1, conv_launches)),
                 "algorithmic_bytes_per_launch": round(conv.get("bytes", 0.0) / max(1, conv["launches"])),
-                "peak_source": peak_src, "launches_per_step": conv["launches"] // reps,
-                "avg_launch_us": round(1e3 * conv["ms"] / max(1, conv["launches"]), 2),
-                "share_of_step_kernel_time": round(conv["ms"] / total_ms, 3),
-                "per_kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(summ.items())}}
+                "peak_source": pk["src"], "frac_of_burst_peak": round(ach / pk["tensor_burst"], 5),
+                "launches_per_step": conv_launches,
+                "avg_launch_us": round(1e3 * conv_ms_in_step / max(1, conv_launches), 2),
+                "share_of_step_kernel_time": round(share, 4),
+                "time_basis": "ms_per_step (CUDA-graph replay, timed region) x share_of_step_kernel_time (CUDA-event pass over the same step, "
+                              "one stream); launches_per_step x avg_launch_us <= ms_per_step",
+                "event_pass_us_per_launch": round(1e3 * conv["ms"] / max(1, conv["launches"]), 2),
+                "per_kernel_ms_per_step_event_pass": {k: round(v["ms"] / reps, 4) for k, v in sorted(summ.items())}}
     flops_pair = sum(v["flops"] for v in summ.values()) / reps / B     # algorithmic 2*M*N*K (+ 8*N^2*C attention) of one step
     pairs = world * B * K
     out = {"value": round(pairs / (dev_ms * 1e-3), 2), "ms_per_step": round(dev_ms / K, 4), "steps": K, "warmup": Wm,
@@ -311,6 +326,10 @@ def _measure(args, wl, K, Wm, dev, world, rank, local, primary=True):
            "gpu_launches": eng.launches_per_step * K,
            "model_tflops": round(flops_pair * pairs / (dev_ms * 1e-3) / 1e12, 3),
            "wall_s_timed_region": round(t_wall, 4), "clocks": clocks, "roofline": roofline}
+    # whole-step bound: sum over launches of max(F_i / tensor peak, bytes_i / HBM peak) vs the timed step
+    bound_ms = sum(max(fl / (pk["tensor"] * 1e12), by / (pk["hbm"] * 1e9)) for _, _, _, fl, by in pl) * 1e3
+    out["step_roofline"] = {"bound_ms": round(bound_ms, 4), "achieved_ms": round(step_ms, 4), "frac": round(bound_ms / step_ms, 4),
+                            "note": "sum over the step's launches of max(flops/tensor_peak, algorithmic_bytes/hbm_peak), no cross-layer fusion assumed"}
     if primary:
         out["e2e"] = {"value": round(pairs / (e2e_ms * 1e-3), 2), "unit": "pairs/s",
                       "h2d_bytes_per_step": int(rgb_pin.numel() + ir_pin.numel()), "d2h_bytes_per_step": int(eng.z.numel() * 2),
@@ -356,43 +375,60 @@ def run_ours(args, wl):
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     K, Wm = args.steps, max(3, args.warmup)
-    m = _measure(args, wl, K, Wm, dev, world, rank, local, primary=True)
-    sec_name = args.secondary
-    if sec_name == "auto":
-        sec_name = "yolov5l_b16" if (args.workload == "yolov5s_b1" and world == 1) else "none"
-    sec = None
-    if sec_name != "none" and world == 1:
-        sec = _measure(args, WORKLOADS[sec_name], max(5, min(K, 20)), 3, dev, world, rank, local, primary=False)
-    if rank == 0:
-        cb = cpu_reference_throughput(wl, budget_s=20.0)
-        dm = dmff_block_metrics(dev) if world == 1 else None
-        line = {"metric": METRIC, "value": m["value"], "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16", "data": "synthetic", "config": m["config"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"],
-                "model_tflops": m["model_tflops"], "wall_s_timed_region": m["wall_s_timed_region"], "clocks": m["clocks"],
-                "roofline": m["roofline"], "cpu_baseline": cb}
-        if dm is not None:
-            line["dmff_block"] = dm
-        if sec is not None:
-            line["secondary"] = {"note": "same detector path at BASELINE configs[2] (compute-bound regime of the same kernels)",
-                                 "metric": METRIC, "unit": "pairs/s", **{k: sec[k] for k in
-                                 ("value", "ms_per_step", "steps", "warmup", "config", "model_tflops", "roofline")}}
-        print(json.dumps(line))
+    m = _measure(args, wl, K, Wm, dev, world, rank, local, primary=True)      # the same workload at every N
     if world > 1:
+        # every rank is done with the GPU work once this barrier returns; rank 0 alone goes on to the CPU baseline and the
+        # single-GPU extras, so no rank spins in NCCL while it does
         dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return
+    notes = []
+    sec_name = args.secondary
+    if sec_name == "auto":
+        sec_name = "yolov5s_b1" if (args.workload == "yolov5l_b16" and world == 1) else "none"
+    sec = dm = cb = None
+    if sec_name != "none" and world == 1:
+        try:
+            sec = _measure(args, WORKLOADS[sec_name], 200 if WORKLOADS[sec_name]["batch"] == 1 else max(5, min(K, 20)), 5, dev, 1, 0, local,
+                           primary=False)
+        except Exception as e:  # noqa: BLE001  (an extra leg must never cost the headline line)
+            notes.append(f"secondary workload {sec_name} failed: {type(e).__name__}: {e}")
+    if world == 1:
+        try:
+            dm = dmff_block_metrics(dev)
+        except Exception as e:  # noqa: BLE001
+            notes.append(f"dmff_block leg failed: {type(e).__name__}: {e}")
+    try:
+        cb = cpu_reference_throughput(wl, budget_s=20.0)
+    except Exception as e:  # noqa: BLE001
+        notes.append(f"cpu_baseline leg failed: {type(e).__name__}: {e}")
+    line = {"metric": METRIC, "value": m["value"], "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic", "config": m["config"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"],
+            "model_tflops": m["model_tflops"], "wall_s_timed_region": m["wall_s_timed_region"], "clocks": m["clocks"],
+            "roofline": m["roofline"], "step_roofline": m["step_roofline"], "cpu_baseline": cb}
+    if dm is not None:
+        line["dmff_block"] = dm
+    if sec is not None:
+        line["secondary"] = {"note": "same detector path at BASELINE configs[1] (batch 1: the launch/latency-bound regime of the same kernels)",
+                             "metric": METRIC, "unit": "pairs/s", **{k: sec[k] for k in
+                             ("value", "ms_per_step", "steps", "warmup", "config", "model_tflops", "roofline", "step_roofline", "gpu_launches")}}
+    if notes:
+        line["notes"] = notes
+    print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="yolov5s_b1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="yolov5l_b16", choices=sorted(WORKLOADS))
     ap.add_argument("--layer-profile", default=None, help="write a per-launch CSV (event-timed eager pass) to this path")
     ap.add_argument("--secondary", default="auto", help="also measure this workload (device-resident value + roofline) and report it "
-                    "under 'secondary'; 'auto' = yolov5l_b16 when the primary is yolov5s_b1 on 1 GPU; 'none' disables")
+                    "under 'secondary'; 'auto' = yolov5s_b1 when the primary is yolov5l_b16 on 1 GPU; 'none' disables")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -7,7 +7,8 @@ import torch
 from helpers import err
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-3   # P is rounded to fp16 before the PV MMA (as in the reference's fp16 path) + fp16 output
+TOL = 1e-3   # the north-star tolerance: P is rounded to fp16 before the PV MMA (as in the reference's fp16 path) + fp16 output;
+             # observed 4e-4 .. 9e-4 (printed per case)
 
 
 def _oracle(qk_q, qk_k, vt, B, N, n_pad, C, h):
@@ -35,7 +36,9 @@ def test_cross_attention(cuda_device, B, N, C):
     torch.cuda.synchronize()
     r_v = _oracle(qk_i, qk_v, vt_v, B, N, n_pad, C, h)      # RGB output: IR queries on RGB keys/values (common.py:670,682)
     r_i = _oracle(qk_v, qk_i, vt_i, B, N, n_pad, C, h)
-    assert err(s_v[:, :N], r_v) < TOL and err(s_i[:, :N], r_i) < TOL, "CUDA-core reference disagrees with the oracle"
-    assert err(o_v[:, :N], r_v) < TOL and err(o_i[:, :N], r_i) < TOL
+    es, eo = max(err(s_v[:, :N], r_v), err(s_i[:, :N], r_i)), max(err(o_v[:, :N], r_v), err(o_i[:, :N], r_i))
+    print(f"\n[attention B{B} N{N} C{C} d{C // h}] tcgen05 {eo:.2e}  cuda-core {es:.2e}  (tol {TOL:.0e})")
+    assert es < TOL, "CUDA-core reference disagrees with the oracle"
+    assert eo < TOL
     if n_pad > N:
         assert float(o_v[:, N:].abs().max()) == 0 and float(o_i[:, N:].abs().max()) == 0    # pad rows stay finite (zero)

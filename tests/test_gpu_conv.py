@@ -47,7 +47,7 @@ CASES = [
     (2, 128, 16, 20, 128, 3, 2, 1, 1),    # stride 2 onto an 8x10 map: 10-wide tiles
     (1, 512, 16, 20, 512, 3, 1, 1, 1),    # P5 of yolov5l at batch 1: 72 K blocks over an 8-CTA cluster (DSMEM split-K reduction)
     (1, 2048, 1, 104, 512, 1, 1, 0, 0),   # MLP fc2 shape (rows as pixels): K=2048, split-K over clusters, 2-D TMA
-    (8, 64, 64, 80, 64, 3, 1, 1, 1),      # 320 tiles -> persistent kernel, 4-D TMA, BN=64
+    (8, 64, 64, 80, 64, 3, 1, 1, 1),      # 3x3/s1 on 64 channels, 640 tiles of 16x8: CTA-pair kernel with halo copies, BN=64
     (8, 3, 128, 160, 32, 6, 2, 2, 1),     # 320 tiles, cp.async gather (6x6 image stem on the packed NHWC4 image), BN=32
     (4, 128, 64, 80, 256, 3, 2, 1, 1),    # persistent, 4-D TMA stride 2, BN=128, 18 K blocks per tile
     (3, 64, 100, 84, 96, 1, 1, 0, 2),     # persistent, 2-D TMA, ragged M (25200 rows) and N (96), GELU
@@ -75,8 +75,10 @@ def test_conv_matches_oracle(cuda_device, case):
     y_simt = ops.conv2d([xv], [pk], simt=True)[0]
     torch.cuda.synchronize()
     ref = _ref(x, w, b, s, p, act)
-    assert err(nchw(y_simt), ref) < TOL, "CUDA-core reference kernel disagrees with the oracle"
-    assert err(nchw(y), ref) < TOL
+    e_simt, e_tc = err(nchw(y_simt), ref), err(nchw(y), ref)
+    print(f"\n[conv {case}] tcgen05 {e_tc:.2e}  cuda-core {e_simt:.2e}")
+    assert e_simt < TOL, "CUDA-core reference kernel disagrees with the oracle"
+    assert e_tc < TOL
     assert err(y, y_simt) < TOL
 
 

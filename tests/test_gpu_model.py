@@ -114,3 +114,35 @@ def test_letterboxed_640x640_vs_oracle(cuda_device):
     e = err(z, zr)
     print(f"\n[yolov5s 640x640] z {e:.2e}")
     assert tuple(z.shape) == (1, 25200, 6) and e < TOL_MODEL
+
+
+def test_bench_shape_yolov5l_b16_through_graph(cuda_device):
+    """The benchmark's own configuration (BASELINE configs[2]: yolov5l, batch 16, 512x640, uint8 frames through
+    GraphedDetector): pairs 0 and 15 against the fp32 CPU oracle, and every pair against the same model run eagerly at
+    batch 1 (batch independence; equal up to the fp32 summation order the batch-dependent tile plans choose)."""
+    from icafusion_b200 import Model
+    from icafusion_b200.cfg import load_cfg
+    from icafusion_b200.engine import GraphedDetector
+    cfg = load_cfg("yolov5l_Transfusion_kaist")
+    model = Model(cfg).eval()
+    sd = load_synth(model, 0)
+    model = model.fuse().half().to(cuda_device)
+    B = 16
+    rgb, ir = synth.synth_images(B, 512, 640, 0)
+    rgb_u8, ir_u8 = (rgb * 255).to(torch.uint8), (ir * 255).to(torch.uint8)
+    eng = GraphedDetector(model, B, 512, 640, in_dtype=torch.uint8, device=cuda_device)
+    z = eng.infer_to_host(rgb_u8.pin_memory(), ir_u8.pin_memory()).clone()
+    assert tuple(z.shape) == (B, 20160, 6) and torch.isfinite(z.float()).all()
+    with torch.no_grad():
+        for j in (0, 15):
+            a, b = rgb_u8[j:j + 1].float() / 255.0, ir_u8[j:j + 1].float() / 255.0
+            zr = O.model_forward(O.fold_bn(sd), cfg, a, b)[0]
+            e = err(z[j:j + 1], zr)
+            print(f"\n[yolov5l b16 graph, pair {j}] z vs fp32 oracle {e:.2e}")
+            assert e < TOL_MODEL
+        worst = 0.0
+        for j in range(B):
+            z1 = model(rgb_u8[j:j + 1].to(cuda_device), ir_u8[j:j + 1].to(cuda_device))[0]
+            worst = max(worst, err(z[j:j + 1], z1))
+        print(f"[yolov5l b16 graph] worst pair vs the eager batch-1 forward {worst:.2e}")
+        assert worst < 1.5e-3
