@@ -56,6 +56,9 @@ SIGNATURES = {
     "icaf_cross_attention": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "icaf_cross_attention_simt": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "icaf_dmff_upsample_cat": [_vp, _vp, _i, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "icaf_nms_workspace_bytes": [_i, _i],
+    "icaf_nms": [_vp, _i, _i, _i, _f, _f, _i, C.c_uint64, _i, _vp, _vp, _vp, C.c_size_t, _vp],
+    "icaf_axpby": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "icaf_detect_decode": [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.POINTER(C.c_float), _vp],
 }
 
@@ -77,7 +80,8 @@ def lib() -> C.CDLL:
         for name, argtypes in SIGNATURES.items():
             fn = getattr(L, name)            # AttributeError here = header/.so drift
             fn.argtypes = argtypes
-            fn.restype = C.c_char_p if name == "icaf_last_error" else (C.c_longlong if name == "icaf_kernel_launches" else C.c_int)
+            fn.restype = {"icaf_last_error": C.c_char_p, "icaf_kernel_launches": C.c_longlong,
+                          "icaf_nms_workspace_bytes": C.c_size_t}.get(name, C.c_int)
         _lib = L
     return _lib
 

@@ -59,6 +59,12 @@ def _require_eval(m: nn.Module):
                                   "(call .eval()); there is no PyTorch fallback")
 
 
+def _dev_half(t: torch.Tensor) -> torch.Tensor:
+    if not ops.on_device(t):
+        raise RuntimeError("icafusion_b200 operators run on CUDA tensors only (no CPU fallback)")
+    return t if t.dtype == torch.float16 else t.to(torch.float16)
+
+
 def _versions(*ts) -> tuple:
     return tuple((t.data_ptr(), t._version, t.device) if t is not None else None for t in ts)
 
@@ -276,7 +282,8 @@ class LearnableCoefficient(nn.Module):
         self.bias = nn.Parameter(torch.FloatTensor([1.0]), requires_grad=True)
 
     def forward(self, x):
-        raise NotImplementedError("LearnableCoefficient is applied inside the fused CrossTransformerBlock epilogues")
+        """Stand-alone call (inside CrossTransformerBlock the gain rides in the GEMM epilogues): x * bias."""
+        return ops.axpby(_dev_half(x), self.bias.detach().float()).view(x.shape)
 
 
 class LearnableWeights(nn.Module):
@@ -288,7 +295,8 @@ class LearnableWeights(nn.Module):
         self.w2 = nn.Parameter(torch.tensor([0.5]), requires_grad=True)
 
     def forward(self, x1, x2):
-        raise NotImplementedError("LearnableWeights is applied inside the fused DMFF token-pooling kernel")
+        """Stand-alone call (inside the DMFF block the mix rides in the token-pooling kernel): x1*w1 + x2*w2."""
+        return ops.axpby(_dev_half(x1), self.w1.detach().float(), _dev_half(x2), self.w2.detach().float()).view(x1.shape)
 
 
 class AdaptivePool2d(nn.Module):
@@ -310,7 +318,19 @@ class AdaptivePool2d(nn.Module):
         return H, W
 
     def forward(self, x):
-        raise NotImplementedError("AdaptivePool2d runs fused inside TransformerFusionBlock")
+        """Stand-alone call: (B,C,H,W) -> (B,C,output_h,output_w) with the reference's stride / kernel rule (common.py:874-888);
+        runs the same pooling kernel as the fused block with the mix pinned to this module's pool type."""
+        v = to_nhwc(x)
+        B, H, W, C = v.shape
+        nh, nw = self.out_size(H, W)
+        if (nh, nw) == (H, W):
+            return x
+        if self.pool_type not in ("avg", "max"):
+            raise NotImplementedError(f"AdaptivePool2d: pool_type {self.pool_type!r}")
+        mix = torch.tensor([1.0, 0.0, 1.0, 0.0] if self.pool_type == "avg" else [0.0, 1.0, 0.0, 1.0], device=v.device)
+        pos = torch.zeros(nh * nw, C, dtype=torch.float16, device=v.device)
+        tok, _ = ops.dmff_pool_tokens(v, v, pos, pos, mix, nh, nw)
+        return tok[:, :nh * nw].reshape(B, nh, nw, C).permute(0, 3, 1, 2)
 
 
 class CrossAttention(nn.Module):
@@ -341,8 +361,73 @@ class CrossAttention(nn.Module):
                 nn.init.normal_(m.weight, std=0.001)
                 nn.init.constant_(m.bias, 0)
 
+    # -- packed parameters ---------------------------------------------------------------------
+    def packed(self):
+        live = [self.que_proj_vis, self.key_proj_vis, self.val_proj_vis, self.que_proj_ir, self.key_proj_ir, self.val_proj_ir,
+                self.out_proj_vis, self.out_proj_ir, self.LN1, self.LN2]
+        key = _versions(*[p for m in live for p in (m.weight, m.bias)])
+        cache = self.__dict__.get("_icaf_pack")
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        if self.d_model % 64:
+            raise NotImplementedError("CrossAttention: d_model must be a multiple of 64")
+        f32 = lambda t: t.detach().float().contiguous()   # noqa: E731
+        P = {}
+        for mod, q, k, v, o in (("vis", self.que_proj_vis, self.key_proj_vis, self.val_proj_vis, self.out_proj_vis),
+                                ("ir", self.que_proj_ir, self.key_proj_ir, self.val_proj_ir, self.out_proj_ir)):
+            P[f"qk_{mod}"] = ops.pack_linear(torch.cat([q.weight, k.weight], 0), torch.cat([q.bias, k.bias], 0))
+            P[f"wv_{mod}"] = v.weight.detach().to(torch.float16).contiguous()     # A operand of the swap-AB V^T linear
+            P[f"bv_{mod}"] = f32(v.bias)
+            P[f"out_{mod}"] = ops.pack_linear(o.weight, o.bias)
+        for name, ln in (("ln_vis", self.LN1), ("ln_ir", self.LN2)):
+            P[name] = (f32(ln.weight), f32(ln.bias), ln.eps)
+        self.__dict__["_icaf_pack"] = (key, P)
+        return P
+
+    def attend(self, r2: torch.Tensor, i2: torch.Tensor, B: int, N: int, n_pad: int):
+        """LN -> fused [Q|K] / V^T projections -> flash cross-attention for both directions (common.py:660-682).
+        r2, i2: fp16 (B*n_pad, C) token matrices.  Returns the merged-head attention outputs (B*n_pad, C) x 2 and the packs."""
+        P = self.packed()
+        rows, C = r2.shape
+        # LN1(rgb), LN2(ir)                                        common.py:660,665
+        rn, inn = ops.layernorm(r2, P["ln_vis"][0], P["ln_vis"][1], i2, P["ln_ir"][0], P["ln_ir"][1], P["ln_vis"][2])
+        # fused [Q|K] projections, both modalities in one launch   common.py:661-662,666-667
+        qk_v, qk_i = ops.linear([rn, inn], [P["qk_vis"], P["qk_ir"]])
+        # V^T = Wv . LN(x)^T (swap-AB: the token matrix is the "filter")   common.py:663,668
+        tok_as_w = [PackedConv(t, None, C, rows, 1, 1, 1, 0, ACT_NONE, is_weight=False) for t in (rn, inn)]
+        ops.note_weight(P, "wv_vis")
+        ops.note_weight(P, "wv_ir")
+        for t, b in zip(tok_as_w, (P["bv_vis"], P["bv_ir"])):
+            t.bias = b
+        vt_v, vt_i = ops.linear([P["wv_vis"], P["wv_ir"]], tok_as_w, bias_row=True)
+        # flash cross-attention, both directions                   common.py:670-684
+        a_v, a_i = ops.cross_attention(qk_v, qk_i, vt_v, vt_i, B, N, n_pad, C, self.h)
+        return a_v.view(rows, C), a_i.view(rows, C), P
+
     def forward(self, x, attention_mask=None, attention_weights=None):
-        raise NotImplementedError("CrossAttention runs fused inside CrossTransformerBlock")
+        """Stand-alone call: x = [rgb_tokens, ir_tokens] (B, N, C) -> [out_vis, out_ir] (common.py:641-687).  Inside
+        CrossTransformerBlock the output projection additionally carries the coefficient pair in its epilogue."""
+        _require_eval(self)
+        if attention_mask is not None or attention_weights is not None:
+            raise NotImplementedError("CrossAttention: attention_mask / attention_weights are unused by the reference forward")
+        r, i = x
+        B, N, C = r.shape
+        r, i, n_pad = _pad_tokens(r, N), _pad_tokens(i, N), ops.round_up(N, 8)
+        a_v, a_i, P = self.attend(r.view(B * n_pad, C), i.view(B * n_pad, C), B, N, n_pad)
+        o_v, o_i = ops.linear([a_v, a_i], [P["out_vis"], P["out_ir"]])                     # common.py:683,685
+        return [o_v.view(B, n_pad, C)[:, :N], o_i.view(B, n_pad, C)[:, :N]]
+
+
+def _pad_tokens(t: torch.Tensor, N: int) -> torch.Tensor:
+    """(B, N, C) tokens -> contiguous fp16 (B, round_up(N, 8), C), pad rows zero."""
+    t = _dev_half(t)
+    B, _, C = t.shape
+    n_pad = ops.round_up(N, 8)
+    if n_pad == N:
+        return t.contiguous()
+    out = t.new_zeros(B, n_pad, C)
+    out[:, :N] = t
+    return out
 
 
 def _mlp(d_model, block_exp, resid_pdrop):
@@ -370,31 +455,18 @@ class CrossTransformerBlock(nn.Module):
 
     # -- packed parameters ---------------------------------------------------------------------
     def packed(self):
-        ca = self.crossatt
-        live = [ca.que_proj_vis, ca.key_proj_vis, ca.val_proj_vis, ca.que_proj_ir, ca.key_proj_ir, ca.val_proj_ir,
-                ca.out_proj_vis, ca.out_proj_ir, self.mlp_vis[0], self.mlp_vis[2], self.mlp_ir[0], self.mlp_ir[2],
-                ca.LN1, ca.LN2, self.LN2]
+        live = [self.mlp_vis[0], self.mlp_vis[2], self.mlp_ir[0], self.mlp_ir[2], self.LN2]
         ts = [p for m in live for p in (m.weight, m.bias)] + [getattr(self, f"coefficient{j}").bias for j in range(1, 9)]
         key = _versions(*ts)
         cache = self.__dict__.get("_icaf_pack")
         if cache is not None and cache[0] == key:
             return cache[1]
-        d = ca.d_model
-        if d % 64:
-            raise NotImplementedError("CrossTransformerBlock: d_model must be a multiple of 64")
         f32 = lambda t: t.detach().float().contiguous()   # noqa: E731
         P = {}
-        for mod, q, k, v, o in (("vis", ca.que_proj_vis, ca.key_proj_vis, ca.val_proj_vis, ca.out_proj_vis),
-                                ("ir", ca.que_proj_ir, ca.key_proj_ir, ca.val_proj_ir, ca.out_proj_ir)):
-            P[f"qk_{mod}"] = ops.pack_linear(torch.cat([q.weight, k.weight], 0), torch.cat([q.bias, k.bias], 0))
-            P[f"wv_{mod}"] = v.weight.detach().to(torch.float16).contiguous()     # A operand of the swap-AB V^T linear
-            P[f"bv_{mod}"] = f32(v.bias)
-            P[f"out_{mod}"] = ops.pack_linear(o.weight, o.bias)
         for mod, mlp in (("vis", self.mlp_vis), ("ir", self.mlp_ir)):
             P[f"fc1_{mod}"] = ops.pack_linear(mlp[0].weight, mlp[0].bias, ACT_GELU)
             P[f"fc2_{mod}"] = ops.pack_linear(mlp[2].weight, mlp[2].bias)
-        for name, ln in (("ln_vis", ca.LN1), ("ln_ir", ca.LN2), ("ln2", self.LN2)):
-            P[name] = (f32(ln.weight), f32(ln.bias), ln.eps)
+        P["ln2"] = (f32(self.LN2.weight), f32(self.LN2.bias), self.LN2.eps)
         P["coef"] = torch.cat([getattr(self, f"coefficient{j}").bias.detach().float().reshape(1) for j in range(1, 9)])
         self.__dict__["_icaf_pack"] = (key, P)
         return P
@@ -405,27 +477,13 @@ class CrossTransformerBlock(nn.Module):
         P = self.packed()
         B, n_pad, C = r.shape
         rows = B * n_pad
-        h = self.crossatt.h
         c = P["coef"]
         co = lambda a, b: (c[a - 1:a], c[b - 1:b])   # noqa: E731  (alpha, beta) device scalars
         r2, i2 = r.view(rows, C), i.view(rows, C)
         for _ in range(self.loops):
-            # LN1(rgb), LN2(ir)                                        common.py:660,665
-            rn, inn = ops.layernorm(r2, P["ln_vis"][0], P["ln_vis"][1], i2, P["ln_ir"][0], P["ln_ir"][1], P["ln_vis"][2])
-            # fused [Q|K] projections, both modalities in one launch   common.py:661-662,666-667
-            qk_v, qk_i = ops.linear([rn, inn], [P["qk_vis"], P["qk_ir"]])
-            # V^T = Wv . LN(x)^T (swap-AB: the token matrix is the "filter")   common.py:663,668
-            tok_as_w = [PackedConv(t, None, C, rows, 1, 1, 1, 0, ACT_NONE, is_weight=False) for t in (rn, inn)]
-            ops.note_weight(P, "wv_vis")
-            ops.note_weight(P, "wv_ir")
-            for t, b in zip(tok_as_w, (P["bv_vis"], P["bv_ir"])):
-                t.bias = b
-            vt_v, vt_i = ops.linear([P["wv_vis"], P["wv_ir"]], tok_as_w, bias_row=True)
-            # flash cross-attention, both directions                   common.py:670-684
-            a_v, a_i = ops.cross_attention(qk_v, qk_i, vt_v, vt_i, B, N, n_pad, C, h)
+            a_v, a_i, A = self.crossatt.attend(r2, i2, B, N, n_pad)                         # common.py:745 (660-682)
             # out_proj + coefficient pair: ra = c1*r + c2*o_r          common.py:683,685,747-748
-            ra, ia = ops.linear([a_v.view(rows, C), a_i.view(rows, C)], [P["out_vis"], P["out_ir"]],
-                                res=[r2, i2], scaled=[co(1, 2), co(3, 4)])
+            ra, ia = ops.linear([a_v, a_i], [A["out_vis"], A["out_ir"]], res=[r2, i2], scaled=[co(1, 2), co(3, 4)])
             # MLPs on LN2 (same LN2 for both)                          common.py:749-750
             rl, il = ops.layernorm(ra, P["ln2"][0], P["ln2"][1], ia, P["ln2"][0], P["ln2"][1], P["ln2"][2])
             hr, hi = ops.linear([rl, il], [P["fc1_vis"], P["fc1_ir"]])
@@ -435,17 +493,8 @@ class CrossTransformerBlock(nn.Module):
     def forward(self, x):
         """x = [rgb_tokens, ir_tokens], each (B, N, C) like the reference (common.py:737-759)."""
         r, i = x
-        B, N, C = r.shape
-        n_pad = ops.round_up(N, 8)
-
-        def pad(t):
-            t = t.to(torch.float16)
-            if n_pad == N:
-                return t.contiguous()
-            out = t.new_zeros(B, n_pad, C)
-            out[:, :N] = t
-            return out
-        r, i = self.run(pad(r), pad(i), N)
+        N = r.shape[1]
+        r, i = self.run(_pad_tokens(r, N), _pad_tokens(i, N), N)
         return [r[:, :N], i[:, :N]]
 
 

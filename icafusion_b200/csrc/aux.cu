@@ -391,6 +391,158 @@ __global__ void detect_decode_kernel(const DetectParams P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// out = a * x (+ b * y): LearnableCoefficient / LearnableWeights called stand-alone (common.py:569-587)
+__global__ void axpby_kernel(const __half* __restrict__ x, const __half* __restrict__ y, const float* __restrict__ a,
+                             const float* __restrict__ b, __half* __restrict__ out, long long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float av = __ldg(a), bv = y ? __ldg(b) : 0.f;
+  float fx[8], fy[8];
+  unpack8(ldg16(x + i * 8), fx);
+  if (y) {
+    unpack8(ldg16(y + i * 8), fy);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) fx[e] = av * fx[e] + bv * fy[e];
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) fx[e] = av * fx[e];
+  }
+  *reinterpret_cast<uint4*>(out + i * 8) = pack8(fx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched non-maximum suppression on the decoded predictions (reference: utils/general.py:518-607, best-class branch +
+// torchvision.ops.nms).  One block per image, three phases, no host round trip:
+//   1. candidates: obj > conf_thres and conf = obj * max_k cls_k > conf_thres (fp32 from the fp16 predictions), class filter;
+//      key = (conf bits << 32) | ~row  -> descending key order = descending confidence, ties in row order (= stable sort)
+//   2. rank sort: rank[i] = #{j : key_j > key_i} (keys are unique), order[rank] = row
+//   3. greedy suppression in confidence order, 16 candidates per round (one per warp against the kept list, then warp 0
+//      resolves the round in order); stops after max_det kept boxes.  IoU arithmetic mirrors torchvision's kernel in fp32
+//      (no FMA contraction), boxes offset by cls * 4096 unless agnostic (general.py:590-592).
+constexpr int kNmsThreads = 512;
+constexpr int kNmsMaxDet = 1024;
+struct NmsParams {
+  const __half* z;
+  int B, R, no, agnostic, max_det, max_nms;
+  float conf_thres, iou_thres;
+  unsigned long long class_mask;
+  float* det; int* count;
+  unsigned long long* keys; int* order;
+};
+struct NmsBox { float x1, y1, x2, y2, conf, cls; };
+__device__ __forceinline__ NmsBox nms_box(const __half* __restrict__ r, int no) {
+  NmsBox b;
+  const float cx = __half2float(r[0]), cy = __half2float(r[1]), w = __half2float(r[2]), h = __half2float(r[3]);
+  const float obj = __half2float(r[4]);
+  float best = __fmul_rn(__half2float(r[5]), obj);
+  int bj = 0;
+  for (int k = 1; k < no - 5; ++k) {
+    const float c = __fmul_rn(__half2float(r[5 + k]), obj);
+    if (c > best) { best = c; bj = k; }
+  }
+  const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);       // xywh2xyxy, general.py:332-339
+  b.x1 = __fsub_rn(cx, hw); b.y1 = __fsub_rn(cy, hh); b.x2 = __fadd_rn(cx, hw); b.y2 = __fadd_rn(cy, hh);
+  b.conf = best; b.cls = float(bj);
+  return b;
+}
+__device__ __forceinline__ bool nms_iou_gt(const float4& a, const float4& b, float thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z), top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
+}
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ unsigned long long skeys[kNmsThreads];
+  __shared__ float4 kept[kNmsMaxDet];        // offset boxes of the kept detections
+  __shared__ float4 round_box[16];
+  __shared__ int round_sup[16];
+  __shared__ int s_n, s_kept;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __half* z = P.z + (size_t)b * P.R * P.no;
+  unsigned long long* keys = P.keys + (size_t)b * P.R;
+  int* order = P.order + (size_t)b * P.R;
+  if (tid == 0) { s_n = 0; s_kept = 0; }
+  __syncthreads();
+  // ---- phase 1: candidates
+  for (int r = tid; r < P.R; r += kNmsThreads) {
+    const __half* row = z + (size_t)r * P.no;
+    if (!(__half2float(row[4]) > P.conf_thres)) continue;
+    const NmsBox bx = nms_box(row, P.no);
+    if (!(bx.conf > P.conf_thres)) continue;
+    if (P.class_mask && !((P.class_mask >> int(bx.cls)) & 1ull)) continue;
+    const int slot = atomicAdd(&s_n, 1);
+    keys[slot] = ((unsigned long long)__float_as_uint(bx.conf) << 32) | (unsigned long long)(~(unsigned)r);
+  }
+  __syncthreads();
+  const int n = s_n;
+  // ---- phase 2: rank sort (descending key)
+  for (int base = 0; base < n; base += kNmsThreads) {
+    const int i = base + tid;
+    const unsigned long long ki = i < n ? keys[i] : 0ull;
+    int rank = 0;
+    for (int t0 = 0; t0 < n; t0 += kNmsThreads) {
+      __syncthreads();
+      skeys[tid] = t0 + tid < n ? keys[t0 + tid] : 0ull;
+      __syncthreads();
+      const int m = min(kNmsThreads, n - t0);
+      for (int j = 0; j < m; ++j) rank += skeys[j] > ki;
+    }
+    if (i < n) order[rank] = int(~(unsigned)(ki & 0xffffffffull));
+  }
+  __syncthreads();
+  // ---- phase 3: greedy suppression, 16 candidates per round
+  const int n_eff = min(n, P.max_nms);
+  float* det = P.det + (size_t)b * P.max_det * 6;
+  for (int c0 = 0; c0 < n_eff; c0 += 16) {
+    const int nk = s_kept;
+    if (nk >= P.max_det) break;
+    const int c = c0 + warp;
+    NmsBox bx;
+    float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < n_eff) {
+      bx = nms_box(z + (size_t)order[c] * P.no, P.no);
+      const float off = P.agnostic ? 0.f : __fmul_rn(bx.cls, 4096.f);
+      ob = make_float4(__fadd_rn(bx.x1, off), __fadd_rn(bx.y1, off), __fadd_rn(bx.x2, off), __fadd_rn(bx.y2, off));
+      bool sup = false;
+      for (int k = lane; k < nk; k += 32) sup |= nms_iou_gt(kept[k], ob, P.iou_thres);
+      sup = __any_sync(0xffffffffu, sup);
+      if (lane == 0) { round_sup[warp] = sup; round_box[warp] = ob; }
+    } else if (lane == 0) {
+      round_sup[warp] = 1;
+    }
+    __syncthreads();
+    if (warp == 0) {                       // resolve the round in confidence order against the boxes it adds itself
+      int nk2 = nk;
+      const int first_new = nk;
+      for (int w = 0; w < 16 && nk2 < P.max_det; ++w) {
+        if (round_sup[w]) continue;        // uniform across the warp (shared memory)
+        const float4 cb = round_box[w];
+        bool sup = false;
+        if (first_new + lane < nk2) sup = nms_iou_gt(kept[first_new + lane], cb, P.iou_thres);
+        if (__any_sync(0xffffffffu, sup)) continue;
+        if (lane == 0) {
+          kept[nk2] = cb;
+          const NmsBox kb = nms_box(z + (size_t)order[c0 + w] * P.no, P.no);
+          float* d = det + (size_t)nk2 * 6;
+          d[0] = kb.x1; d[1] = kb.y1; d[2] = kb.x2; d[3] = kb.y2; d[4] = kb.conf; d[5] = kb.cls;
+        }
+        __syncwarp();
+        ++nk2;
+      }
+      if (lane == 0) s_kept = nk2;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) P.count[b] = s_kept;
+}
+
 __global__ void prefetch_l2_kernel(const char* __restrict__ p, size_t bytes) {
   pdl_launch_dependents();
   // The region holds parameters (no kernel writes it), so the prefetches need not wait for the previous kernel ...
@@ -531,4 +683,33 @@ extern "C" int icaf_detect_decode(const void* p, int64_t p_ld, void* x_out, void
   long long total = (long long)B * na * ny * nx;
   launch_k(detect_decode_kernel, dim3(blocks_for(total, 128)), dim3(128), 0, (cudaStream_t)stream, P);
   return check_launch("detect_decode");
+}
+
+extern "C" int icaf_axpby(const void* x, const void* y, const float* a, const float* b, void* out, int64_t n, void* stream) {
+  if (!x || !a || !out || (y && !b) || n < 0 || n % 8) return set_error(ICAF_ERR_BAD_ARG, "axpby: null pointer or element count not a multiple of 8");
+  if (n == 0) return ICAF_OK;
+  launch_k(axpby_kernel, dim3(blocks_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, (const __half*)y, a, b, (__half*)out,
+           (long long)(n / 8));
+  return check_launch("axpby");
+}
+
+extern "C" size_t icaf_nms_workspace_bytes(int B, int R) {
+  if (B < 1 || R < 1) return 0;
+  return (size_t)B * R * (sizeof(unsigned long long) + sizeof(int));
+}
+
+extern "C" int icaf_nms(const void* z, int B, int R, int no, float conf_thres, float iou_thres, int agnostic, uint64_t class_mask,
+                        int max_det, float* det, int* count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!z || !det || !count || !workspace) return set_error(ICAF_ERR_BAD_ARG, "nms: null pointer");
+  if (B < 1 || R < 1 || no < 6 || max_det < 1 || max_det > kNmsMaxDet) return set_error(ICAF_ERR_BAD_ARG, "nms: bad shape (max_det <= 1024)");
+  if (class_mask && no - 5 > 64) return set_error(ICAF_ERR_UNSUPPORTED, "nms: the class filter covers at most 64 classes");
+  if (workspace_bytes < icaf_nms_workspace_bytes(B, R) || (reinterpret_cast<uintptr_t>(workspace) & 7))
+    return set_error(ICAF_ERR_BAD_ARG, "nms: workspace too small (icaf_nms_workspace_bytes) or not 8-byte aligned");
+  NmsParams P;
+  P.z = (const __half*)z; P.B = B; P.R = R; P.no = no; P.agnostic = agnostic; P.max_det = max_det; P.max_nms = 30000;   // general.py:531
+  P.conf_thres = conf_thres; P.iou_thres = iou_thres; P.class_mask = class_mask; P.det = det; P.count = count;
+  P.keys = (unsigned long long*)workspace;
+  P.order = (int*)((char*)workspace + (size_t)B * R * sizeof(unsigned long long));
+  launch_k(nms_kernel, dim3(B), dim3(kNmsThreads), 0, (cudaStream_t)stream, P);
+  return check_launch("nms");
 }

@@ -13,13 +13,16 @@ from typing import Iterable, Iterator, Optional, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .yolo_test import Model
 
 
 class GraphedDetector:
     def __init__(self, model: Model, batch: int, height: int, width: int, in_dtype: torch.dtype = torch.float16,
-                 device: Optional[torch.device] = None, warmup: int = 2):
+                 device: Optional[torch.device] = None, warmup: int = 2, nms: Optional[dict] = None):
+        """`nms`: keyword arguments of :func:`icafusion_b200.ops.nms` (e.g. ``dict(conf_thres=0.25, iou_thres=0.45)``); when
+        given, the batched device NMS (utils/general.py:518-607) is captured behind the forward and ``infer_detections``
+        returns its fixed-capacity result -- the whole detect_twostream.py:84-86 step without a host round trip in between."""
         if model.training:
             raise ValueError("GraphedDetector needs model.eval()")
         self.model = model
@@ -38,13 +41,25 @@ class GraphedDetector:
                 self.model.consolidate_weights(self.rgb, self.ir)     # one contiguous filter arena -> per-step L2 prefetch
                 self.model(self.rgb, self.ir)
             self.stream.synchronize()
+            self.det = self.count = None
+            if nms is not None:                         # static NMS buffers live outside the graph's private pool
+                z0 = self.model(self.rgb, self.ir)[0]
+                self.det, self.count = ops.nms(z0, **nms)
+                need = int(_lib.lib().icaf_nms_workspace_bytes(z0.shape[0], z0.shape[1]))
+                self._nms_ws = torch.empty((need + 7) // 8, dtype=torch.int64, device=self.device)
+                self.stream.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self.z, self.logits, self.xs = self.model(self.rgb, self.ir)
+                if nms is not None:
+                    ops.nms(self.z, det=self.det, count=self.count, workspace=self._nms_ws, **nms)
             self.launches_per_step = ops.launch_count() - n0
         self.stream.synchronize()
         self._z_host = torch.empty(self.z.shape, dtype=self.z.dtype, pin_memory=True)
+        if nms is not None:
+            self._det_host = torch.empty(self.det.shape, dtype=self.det.dtype, pin_memory=True)
+            self._count_host = torch.empty(self.count.shape, dtype=self.count.dtype, pin_memory=True)
 
     # -- device-resident path ------------------------------------------------------------------
     def replay(self):
@@ -68,6 +83,18 @@ class GraphedDetector:
         self._z_host.copy_(self.z, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._z_host
+
+
+    def infer_detections(self, rgb_host: torch.Tensor, ir_host: torch.Tensor):
+        """End-to-end step with the captured NMS: H2D, forward, NMS, D2H of the (B, max_det, 6) detections and their counts.
+        Returns (det_host fp32, count_host int32), valid until the next call."""
+        if self.det is None:
+            raise RuntimeError("GraphedDetector was built without nms=...")
+        self(rgb_host, ir_host)
+        self._det_host.copy_(self.det, non_blocking=True)
+        self._count_host.copy_(self.count, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._det_host, self._count_host
 
 
 class PipelinedDetector:

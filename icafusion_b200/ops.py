@@ -419,3 +419,53 @@ def detect_decode(p: torch.Tensor, na: int, no: int, z: torch.Tensor, logits: to
           (_ptr(p), _check_view(p, "detect p"), _ptr(x_out), _ptr(z), _ptr(logits), B, ny, nx, na, no, z.shape[1], row_off, float(stride), anch),
           {"bytes": 2.0 * (p.numel() + 2.2 * x_out.numel())})
     return x_out
+
+
+def axpby(x: torch.Tensor, a: torch.Tensor, y: Optional[torch.Tensor] = None, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = a*x (+ b*y): fp16 tensors of one shape, `a` / `b` one-element fp32 device tensors (LearnableCoefficient /
+    LearnableWeights called stand-alone, common.py:569-587)."""
+    if x.dtype != torch.float16 or not on_device(x):
+        raise ValueError("axpby: expected a CUDA fp16 tensor")
+    x = x.contiguous()
+    n = x.numel()
+    if n % 8:
+        raise ValueError("axpby: element count must be a multiple of 8")
+    if y is not None:
+        if y.shape != x.shape or y.dtype != torch.float16:
+            raise ValueError("axpby: x and y must share shape and dtype")
+        y = y.contiguous()
+    out = torch.empty_like(x)
+    _call("icaf_axpby", _lib.lib().icaf_axpby, (_ptr(x), _ptr(y), _ptr(a), _ptr(b), _ptr(out), n),
+          {"bytes": 2.0 * n * (3 if y is not None else 2)})
+    return out
+
+
+def nms(z: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45, agnostic: bool = False,
+        classes: Optional[Sequence[int]] = None, max_det: int = 300, det: Optional[torch.Tensor] = None,
+        count: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """Batched NMS on the device (utils/general.py:518-607, best-class branch).  z: fp16 (B, R, nc+5) decoded predictions.
+    Returns (det fp32 (B, max_det, 6) rows [x1,y1,x2,y2,conf,cls] in confidence order, count int32 (B,)); no host sync."""
+    if z.dim() != 3 or z.dtype != torch.float16 or not on_device(z) or not z.is_contiguous():
+        raise ValueError(f"nms: expected a contiguous CUDA fp16 (B, R, nc+5) tensor, got {z.dtype} {tuple(z.shape)}")
+    B, R, no = z.shape
+    mask = 0
+    if classes is not None:
+        for c in classes:
+            if not 0 <= int(c) < min(no - 5, 64):
+                raise ValueError(f"nms: class {c} outside [0, {min(no - 5, 64)})")
+            mask |= 1 << int(c)
+        if mask == 0:
+            raise ValueError("nms: empty class filter")
+    if det is None:
+        det = torch.zeros(B, max_det, 6, dtype=torch.float32, device=z.device)
+    if count is None:
+        count = torch.zeros(B, dtype=torch.int32, device=z.device)
+    need = int(_lib.lib().icaf_nms_workspace_bytes(B, R))
+    if workspace is None:
+        workspace = torch.empty((need + 7) // 8, dtype=torch.int64, device=z.device)
+    if tuple(det.shape) != (B, max_det, 6) or det.dtype != torch.float32 or tuple(count.shape) != (B,) or count.dtype != torch.int32:
+        raise ValueError("nms: det must be fp32 (B, max_det, 6) and count int32 (B,)")
+    _call("icaf_nms", _lib.lib().icaf_nms,
+          (_ptr(z), B, R, no, float(conf_thres), float(iou_thres), int(bool(agnostic)), C.c_uint64(mask), int(max_det), _ptr(det), _ptr(count),
+           _ptr(workspace), C.c_size_t(workspace.numel() * workspace.element_size())), {"bytes": 2.0 * z.numel()})
+    return det, count

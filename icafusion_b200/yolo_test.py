@@ -243,7 +243,7 @@ class Model(nn.Module):
             return m.cv2.conv.out_channels
         if isinstance(m, TransformerFusionBlock):
             return m.n_embd
-        if isinstance(m, Upsample):
+        if isinstance(m, nn.Upsample):
             return ch[m.i - 1] if m.f == -1 else ch[m.f]
         if isinstance(m, Concat):
             return sum(ch[m.i - 1 if j == -1 else j] for j in m.f)
@@ -273,7 +273,9 @@ class Model(nn.Module):
             return C3.run([m], [v], o)[0]
         if isinstance(m, SPPF):
             return SPPF.run([m], [v], o)[0]
-        if isinstance(m, Upsample):
+        if isinstance(m, nn.Upsample):             # ours, or torch's own class inside an unpickled reference checkpoint
+            if m.mode != "nearest" or m.scale_factor is None or float(m.scale_factor) != 2.0:
+                raise NotImplementedError("Upsample: only nearest x2 is supported")
             return ops.upsample2x(v, out)
         if isinstance(m, Concat):
             return Concat.run(v)
@@ -306,6 +308,9 @@ class Model(nn.Module):
         """Layer walk with branch-level concurrency: the RGB/IR streams run as grouped launches on the current stream;
         a DMFF block is forked onto a side stream as soon as both of its inputs exist (P3 and P4 fusion overlap the rest of
         the backbone), Detect levels are forked as soon as their head output exists; consumers join before they read."""
+        if "_ir_start" not in self.__dict__:       # an unpickled checkpoint (models/experimental.py:118) never ran __init__
+            self._plan_streams()
+            self._plan_concats()
         layers = list(self.model)
         y: List = [None] * len(layers)
         dev = rgb.device
@@ -408,7 +413,7 @@ class Model(nn.Module):
                 if m.i in self._concat_dst and not isinstance(m, (Concat, Detect)):
                     ref = x[0] if isinstance(x, (list, tuple)) else x
                     B, H, W = ref.shape[0], ref.shape[1], ref.shape[2]
-                    if isinstance(m, Upsample):
+                    if isinstance(m, nn.Upsample):
                         H, W = 2 * H, 2 * W
                     elif isinstance(m, Conv):
                         k, s_, p = m.conv.kernel_size[0], m.conv.stride[0], m.conv.padding[0]

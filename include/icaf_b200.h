@@ -173,6 +173,23 @@ int icaf_dmff_upsample_cat(const void* tok_vis, const void* tok_ir, int n_pad, c
 int icaf_detect_decode(const void* p, int64_t p_ld, void* x_out, void* z, void* logits, int B, int ny, int nx, int na,
                        int no, int total_rows, int row_off, float stride, const float* anchors_host, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Batched non-maximum suppression on the decoded predictions, fully on the device.
+ * Replaces utils/general.py:518-607 non_max_suppression (best-class branch: conf = obj * max cls, both > conf_thres,
+ * class-offset boxes unless `agnostic`, torchvision.ops.nms greedy suppression at iou_thres, max_nms = 30000 candidates,
+ * first max_det kept).  z: fp16 (B, R, no) as icaf_detect_decode writes it; arithmetic in fp32 like the reference on
+ * z.float().  class_mask: bit k set = keep class k (0 = all classes; at most 64 classes with a mask).
+ * det: fp32 (B, max_det, 6) rows [x1, y1, x2, y2, conf, cls] in confidence order; count: int32 (B) rows valid per image.
+ * workspace: icaf_nms_workspace_bytes(B, R) bytes of device memory, 8-byte aligned (caller owned).
+ * ------------------------------------------------------------------------------------------- */
+size_t icaf_nms_workspace_bytes(int B, int R);
+int icaf_nms(const void* z, int B, int R, int no, float conf_thres, float iou_thres, int agnostic, uint64_t class_mask,
+             int max_det, float* det, int* count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out = a[0] * x (+ b[0] * y when y != NULL) over n fp16 elements (n % 8 == 0, 16-byte aligned); a, b device fp32 scalars.
+ * LearnableCoefficient.forward / LearnableWeights.forward called stand-alone (models/common.py:569-587). */
+int icaf_axpby(const void* x, const void* y, const float* a, const float* b, void* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

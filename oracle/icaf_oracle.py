@@ -295,6 +295,73 @@ def fold_bn(sd: SD, bn_eps=BN_EPS_MODEL) -> SD:
 
 
 # ----------------------------------------------------------------------------------------
+# post-processing (utils/general.py)
+# ----------------------------------------------------------------------------------------
+def greedy_nms(boxes, scores, iou_thres: float):
+    """torchvision.ops.nms restated (the reference calls it at utils/general.py:592; torchvision is a third-party
+    dependency, unpinned in requirements.txt:10, 0.26 in this image -- csrc/ops/cpu/nms_kernel.cpp): stable sort by
+    descending score, keep a box unless a kept higher-scored box overlaps it with IoU > iou_thres.  fp32 arithmetic in
+    the kernel's order.  Returns kept indices in score order."""
+    import numpy as np
+    b = boxes.detach().cpu().numpy().astype(np.float32)
+    sc = scores.detach().cpu().numpy().astype(np.float32)
+    order = np.argsort(-sc, kind="stable")
+    x1, y1, x2, y2 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    areas = ((x2 - x1) * (y2 - y1)).astype(np.float32)
+    suppressed = np.zeros(len(sc), dtype=bool)
+    keep = []
+    for _i in range(len(order)):
+        i = order[_i]
+        if suppressed[i]:
+            continue
+        keep.append(int(i))
+        rest = order[_i + 1:]
+        xx1 = np.maximum(x1[i], x1[rest]); yy1 = np.maximum(y1[i], y1[rest])
+        xx2 = np.minimum(x2[i], x2[rest]); yy2 = np.minimum(y2[i], y2[rest])
+        w = np.maximum(np.float32(0), (xx2 - xx1).astype(np.float32))
+        h = np.maximum(np.float32(0), (yy2 - yy1).astype(np.float32))
+        inter = (w * h).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ovr = inter / ((areas[i] + areas[rest]).astype(np.float32) - inter).astype(np.float32)
+        suppressed[rest[ovr > np.float32(iou_thres)]] = True
+    return torch.as_tensor(keep, dtype=torch.long)
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, max_det=300):
+    """utils/general.py:518-607, best-class branch (multi_label is off whenever nc == 1, :533): per image
+    x = x[obj > conf]; cls *= obj; box = xywh2xyxy; conf, j = cls.max(1); keep conf > conf_thres; optional class filter;
+    top max_nms = 30000 by confidence; boxes + cls * 4096 unless agnostic; NMS; first max_det = 300."""
+    max_wh, max_nms = 4096, 30000
+    out = []
+    pred = prediction.float()
+    for x in pred:
+        x = x[x[:, 4] > conf_thres].clone()
+        if not x.shape[0]:
+            out.append(torch.zeros((0, 6)))
+            continue
+        x[:, 5:] *= x[:, 4:5]
+        box = x[:, :4].clone()
+        box[:, 0] = x[:, 0] - x[:, 2] / 2
+        box[:, 1] = x[:, 1] - x[:, 3] / 2
+        box[:, 2] = x[:, 0] + x[:, 2] / 2
+        box[:, 3] = x[:, 1] + x[:, 3] / 2
+        conf, j = x[:, 5:].max(1, keepdim=True)
+        x = torch.cat((box, conf, j.float()), 1)[conf.view(-1) > conf_thres]
+        if classes is not None:
+            x = x[(x[:, 5:6] == torch.tensor(classes, dtype=x.dtype)).any(1)]
+        n = x.shape[0]
+        if not n:
+            out.append(torch.zeros((0, 6)))
+            continue
+        if n > max_nms:
+            x = x[x[:, 4].argsort(descending=True)[:max_nms]]
+        c = x[:, 5:6] * (0 if agnostic else max_wh)
+        i = greedy_nms(x[:, :4] + c, x[:, 4], iou_thres)[:max_det]
+        out.append(x[i])
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # Work accounting (SURVEY.md section 8d) -- used by bench.py to turn time into GFLOP/s
 # ----------------------------------------------------------------------------------------
 def dmff_flops(B, C, H, W, N, loops=1):

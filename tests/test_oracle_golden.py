@@ -56,3 +56,26 @@ def test_flop_accounting_matches_survey():
     l = O.model_conv_flops(load_cfg("yolov5l_Transfusion_kaist"), 512, 640) / 1e9
     assert abs(s - 24.61) < 0.02 and abs(l - 155.82) < 0.05, (s, l)
     assert abs(O.dmff_flops(1, 256, 64, 80, 400) / 1e9 - 2.928) < 0.01
+
+
+def test_nms_oracle_matches_reference_golden():
+    """oracle.non_max_suppression (incl. its restated greedy NMS) reproduces the REAL reference's output rows exactly
+    (tests/golden/nms_cases.npz from oracle/gen_golden_nms.py), and the greedy NMS equals torchvision's on random boxes."""
+    m, d = load_golden("nms_cases")
+    pred = torch.from_numpy(d["pred"])
+    for st in m["settings"]:
+        out = O.non_max_suppression(pred, st["conf"], st["iou"], classes=st["classes"], agnostic=st["agnostic"])
+        for b, o in enumerate(out):
+            want = d[f"{st['name']}_{b}"]
+            assert o.shape[0] == st["counts"][b] == want.shape[0]
+            assert np.array_equal(o.numpy(), want), (st["name"], b)
+    try:
+        import torchvision
+    except Exception:  # noqa: BLE001
+        return
+    g = torch.Generator().manual_seed(0)
+    xy = torch.rand(3000, 2, generator=g) * 600
+    wh = torch.rand(3000, 2, generator=g) * 120 + 2
+    boxes, scores = torch.cat([xy, xy + wh], 1), (torch.rand(3000, generator=g) * 64).round() / 64     # many score ties
+    for thr in (0.3, 0.45, 0.6):
+        assert torch.equal(O.greedy_nms(boxes, scores, thr), torchvision.ops.nms(boxes, scores, thr))
