@@ -81,8 +81,10 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
   cuuint64_t strides[1] = {row_pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  // staged rows are box_inner*2 bytes wide; the swizzle span equals the row (32 / 64 / 128 B)
+  const CUtensorMapSwizzle swz = box_inner >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(inner * 2, row_pitch_bytes),
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2_promotion(inner * 2, row_pitch_bytes),
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[160];

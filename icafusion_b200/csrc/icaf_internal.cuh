@@ -63,7 +63,7 @@ inline int configure_smem(K kernel, int bytes, bool (&done)[kMaxDevices], const 
 }
 
 // TMA descriptors (host side). fp16 tensors, 128-byte swizzle, zero fill out of bounds.
-// 2D: [rows][inner] with a row pitch in bytes; box = box_rows x box_inner (box_inner*2 <= 128 B).
+// 2D: [rows][inner] with a row pitch in bytes; box = box_rows x box_inner (box_inner = 64 / 32 / 16 halfs -> 128B / 64B / 32B swizzle).
 int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
                    uint32_t box_inner, uint32_t box_rows);
 // 4D NHWC activation view (C, W, H, B) with pixel pitch `ld` elements; box = (box_c, box_w, box_h, 1) *input* elements,
