@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libicaf_b200.so")
 
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
-EPI_BIAS_ROW, EPI_ADD_RES, EPI_SCALED_RES = 1, 2, 4
+EPI_BIAS_ROW, EPI_ADD_RES, EPI_SCALED_RES, EPI_LN_FOLD, EPI_EMIT_STATS = 1, 2, 4, 8, 16
 
 
 class ConvGeom(C.Structure):
@@ -24,7 +24,9 @@ class ConvGeom(C.Structure):
 class ConvIO(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_ld", C.c_int64), ("w", C.c_void_p), ("bias", C.c_void_p),
                 ("res", C.c_void_p), ("res_ld", C.c_int64), ("y", C.c_void_p), ("y_ld", C.c_int64),
-                ("alpha", C.c_void_p), ("beta", C.c_void_p)]
+                ("alpha", C.c_void_p), ("beta", C.c_void_p),
+                ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_parts", C.c_int), ("ln_eps", C.c_float),
+                ("stats_out", C.c_void_p)]
 
 
 class ConvPlan(C.Structure):
@@ -51,7 +53,8 @@ SIGNATURES = {
     "icaf_upsample2x": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp],
     "icaf_copy_channels": [_vp, _i64, _vp, _i64, _i64, _i, _vp],
     "icaf_prefetch_l2": [_vp, C.c_size_t, _vp],
-    "icaf_dmff_pool_tokens": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "icaf_dmff_pool_tokens": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "icaf_row_stats": [_vp, _vp, _vp, _vp, _i64, _i, _vp],
     "icaf_layernorm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp],
     "icaf_cross_attention": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "icaf_cross_attention_simt": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -371,38 +371,28 @@ class CrossAttention(nn.Module):
             return cache[1]
         if self.d_model % 64:
             raise NotImplementedError("CrossAttention: d_model must be a multiple of 64")
-        f32 = lambda t: t.detach().float().contiguous()   # noqa: E731
         P = {}
-        for mod, q, k, v, o in (("vis", self.que_proj_vis, self.key_proj_vis, self.val_proj_vis, self.out_proj_vis),
-                                ("ir", self.que_proj_ir, self.key_proj_ir, self.val_proj_ir, self.out_proj_ir)):
-            P[f"qk_{mod}"] = ops.pack_linear(torch.cat([q.weight, k.weight], 0), torch.cat([q.bias, k.bias], 0))
-            P[f"wv_{mod}"] = v.weight.detach().to(torch.float16).contiguous()     # A operand of the swap-AB V^T linear
-            P[f"bv_{mod}"] = f32(v.bias)
+        # one [Q|K|V] projection per modality with its LayerNorm folded in (LN1 -> rgb, LN2 -> ir: common.py:660,665)
+        for mod, q, k, v, o, ln in (("vis", self.que_proj_vis, self.key_proj_vis, self.val_proj_vis, self.out_proj_vis, self.LN1),
+                                    ("ir", self.que_proj_ir, self.key_proj_ir, self.val_proj_ir, self.out_proj_ir, self.LN2)):
+            P[f"qkv_{mod}"] = ops.pack_linear_ln(torch.cat([q.weight, k.weight, v.weight], 0), torch.cat([q.bias, k.bias, v.bias], 0),
+                                                 ln.weight, ln.bias, ln.eps)
             P[f"out_{mod}"] = ops.pack_linear(o.weight, o.bias)
-        for name, ln in (("ln_vis", self.LN1), ("ln_ir", self.LN2)):
-            P[name] = (f32(ln.weight), f32(ln.bias), ln.eps)
         self.__dict__["_icaf_pack"] = (key, P)
         return P
 
-    def attend(self, r2: torch.Tensor, i2: torch.Tensor, B: int, N: int, n_pad: int):
-        """LN -> fused [Q|K] / V^T projections -> flash cross-attention for both directions (common.py:660-682).
-        r2, i2: fp16 (B*n_pad, C) token matrices.  Returns the merged-head attention outputs (B*n_pad, C) x 2 and the packs."""
+    def attend(self, r2: torch.Tensor, i2: torch.Tensor, B: int, N: int, n_pad: int, stats=None):
+        """[LN ->] fused Q|K|V projection -> flash cross-attention for both directions (common.py:660-682).
+        r2, i2: fp16 (B*n_pad, C) token matrices; `stats`: their row statistics (fp32 (rows, parts, 2) x 2) if a producer
+        already emitted them.  LayerNorm never runs as a kernel: it is folded into the projection GEMM's epilogue.
+        Returns the merged-head attention outputs (B*n_pad, C) x 2 and the packs."""
         P = self.packed()
         rows, C = r2.shape
-        # LN1(rgb), LN2(ir)                                        common.py:660,665
-        rn, inn = ops.layernorm(r2, P["ln_vis"][0], P["ln_vis"][1], i2, P["ln_ir"][0], P["ln_ir"][1], P["ln_vis"][2])
-        # fused [Q|K] projections, both modalities in one launch   common.py:661-662,666-667
-        qk_v, qk_i = ops.linear([rn, inn], [P["qk_vis"], P["qk_ir"]])
-        # V^T = Wv . LN(x)^T (swap-AB: the token matrix is the "filter")   common.py:663,668
-        tok_as_w = [PackedConv(t, None, C, rows, 1, 1, 1, 0, ACT_NONE, is_weight=False) for t in (rn, inn)]
-        ops.note_weight(P, "wv_vis")
-        ops.note_weight(P, "wv_ir")
-        for t, b in zip(tok_as_w, (P["bv_vis"], P["bv_ir"])):
-            t.bias = b
-        vt_v, vt_i = ops.linear([P["wv_vis"], P["wv_ir"]], tok_as_w, bias_row=True)
-        # flash cross-attention, both directions                   common.py:670-684
-        a_v, a_i = ops.cross_attention(qk_v, qk_i, vt_v, vt_i, B, N, n_pad, C, self.h)
-        return a_v.view(rows, C), a_i.view(rows, C), P
+        if stats is None:
+            stats = ops.row_stats(r2, i2)
+        qkv_v, qkv_i = ops.linear([r2, i2], [P["qkv_vis"], P["qkv_ir"]], ln_stats=list(stats))   # common.py:660-668
+        a_v, a_i = ops.cross_attention(qkv_v.view(B, n_pad, 3 * C), qkv_i.view(B, n_pad, 3 * C), None, None, B, N, n_pad, C, self.h)
+        return a_v.view(rows, C), a_i.view(rows, C), P                                             # common.py:670-684
 
     def forward(self, x, attention_mask=None, attention_weights=None):
         """Stand-alone call: x = [rgb_tokens, ir_tokens] (B, N, C) -> [out_vis, out_ir] (common.py:641-687).  Inside
@@ -461,18 +451,18 @@ class CrossTransformerBlock(nn.Module):
         cache = self.__dict__.get("_icaf_pack")
         if cache is not None and cache[0] == key:
             return cache[1]
-        f32 = lambda t: t.detach().float().contiguous()   # noqa: E731
         P = {}
-        for mod, mlp in (("vis", self.mlp_vis), ("ir", self.mlp_ir)):
-            P[f"fc1_{mod}"] = ops.pack_linear(mlp[0].weight, mlp[0].bias, ACT_GELU)
+        for mod, mlp in (("vis", self.mlp_vis), ("ir", self.mlp_ir)):      # the SAME LN2 in front of both MLPs (common.py:749-750)
+            P[f"fc1_{mod}"] = ops.pack_linear_ln(mlp[0].weight, mlp[0].bias, self.LN2.weight, self.LN2.bias, self.LN2.eps, ACT_GELU)
             P[f"fc2_{mod}"] = ops.pack_linear(mlp[2].weight, mlp[2].bias)
-        P["ln2"] = (f32(self.LN2.weight), f32(self.LN2.bias), self.LN2.eps)
         P["coef"] = torch.cat([getattr(self, f"coefficient{j}").bias.detach().float().reshape(1) for j in range(1, 9)])
         self.__dict__["_icaf_pack"] = (key, P)
         return P
 
-    def run(self, r: torch.Tensor, i: torch.Tensor, N: int):
-        """r, i: fp16 (B, Npad, C) token streams (pad rows finite).  Returns the updated streams."""
+    def run(self, r: torch.Tensor, i: torch.Tensor, N: int, stats=None):
+        """r, i: fp16 (B, Npad, C) token streams (pad rows finite); `stats`: their row statistics when the producer emitted
+        them (the token-pooling kernel does).  Five launches per loop: [LN+QKV] -> attention -> [out_proj, coefficients, row
+        statistics] -> [LN2+fc1+GELU] -> [fc2, coefficients, row statistics].  Returns the updated streams."""
         _require_eval(self)
         P = self.packed()
         B, n_pad, C = r.shape
@@ -480,14 +470,16 @@ class CrossTransformerBlock(nn.Module):
         c = P["coef"]
         co = lambda a, b: (c[a - 1:a], c[b - 1:b])   # noqa: E731  (alpha, beta) device scalars
         r2, i2 = r.view(rows, C), i.view(rows, C)
-        for _ in range(self.loops):
-            a_v, a_i, A = self.crossatt.attend(r2, i2, B, N, n_pad)                         # common.py:745 (660-682)
+        new_stats = lambda: [torch.empty(rows, (C + 31) // 32, 2, dtype=torch.float32, device=r.device) for _ in range(2)]  # noqa: E731
+        for loop in range(self.loops):
+            a_v, a_i, A = self.crossatt.attend(r2, i2, B, N, n_pad, stats)                  # common.py:745 (660-682)
             # out_proj + coefficient pair: ra = c1*r + c2*o_r          common.py:683,685,747-748
-            ra, ia = ops.linear([a_v, a_i], [A["out_vis"], A["out_ir"]], res=[r2, i2], scaled=[co(1, 2), co(3, 4)])
-            # MLPs on LN2 (same LN2 for both)                          common.py:749-750
-            rl, il = ops.layernorm(ra, P["ln2"][0], P["ln2"][1], ia, P["ln2"][0], P["ln2"][1], P["ln2"][2])
-            hr, hi = ops.linear([rl, il], [P["fc1_vis"], P["fc1_ir"]])
-            r2, i2 = ops.linear([hr, hi], [P["fc2_vis"], P["fc2_ir"]], res=[ra, ia], scaled=[co(5, 6), co(7, 8)])
+            st_a = new_stats()
+            ra, ia = ops.linear([a_v, a_i], [A["out_vis"], A["out_ir"]], res=[r2, i2], scaled=[co(1, 2), co(3, 4)], stats_out=st_a)
+            # MLPs on LN2 (same LN2 for both), LayerNorm folded into fc1  common.py:749-750, 704-715
+            hr, hi = ops.linear([ra, ia], [P["fc1_vis"], P["fc1_ir"]], ln_stats=st_a)
+            stats = new_stats() if loop + 1 < self.loops else None                         # feeds the next loop's LN1 / LN2
+            r2, i2 = ops.linear([hr, hi], [P["fc2_vis"], P["fc2_ir"]], res=[ra, ia], scaled=[co(5, 6), co(7, 8)], stats_out=stats)
         return r2.view(B, n_pad, C), i2.view(B, n_pad, C)
 
     def forward(self, x):
@@ -543,9 +535,11 @@ class TransformerFusionBlock(nn.Module):
         if N != self.pos_emb_vis.shape[1]:
             raise ValueError(f"TransformerFusionBlock: {nh}x{nw} tokens but pos_emb has {self.pos_emb_vis.shape[1]} rows")
         pos_v, pos_i, mix = self._front()
-        r, i = ops.dmff_pool_tokens(rgb, ir, pos_v, pos_i, mix, nh, nw)            # common.py:817-823
+        r, i, sv, si = ops.dmff_pool_tokens(rgb, ir, pos_v, pos_i, mix, nh, nw, with_stats=True)   # common.py:817-823
+        stats = [sv, si]
         for blk in self.crosstransformer:
-            r, i = blk.run(r, i, N)                                                # common.py:825
+            r, i = blk.run(r, i, N, stats)                                         # common.py:825
+            stats = None
         cat = ops.dmff_upsample_cat(r, i, rgb, ir, nh, nw, mode=0)                 # common.py:827-840 (eval: bilinear)
         return Conv.run([self.conv1x1_out], [cat], None if out is None else [out])[0]   # common.py:841
 

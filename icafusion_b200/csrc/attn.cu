@@ -5,7 +5,9 @@
 // into 128B-swizzled shared memory, and a second UMMA computes P V into TMEM; running (max, sum, acc) live in
 // registers.  Q / K / V^T tiles are staged by TMA (cp.async.bulk.tensor) from a producer warp, K / V^T double-buffered.
 //
-// Layouts (see include/icaf_b200.h): qk (B, Npad, 2C) = [q | k] rows; vt (C, B*Npad) = V^T; out (B, Npad, C).
+// Layouts (see include/icaf_b200.h): either qkv (B, Npad, 3C) = [q | k | v] rows as ONE fused projection emits them (V is
+// then consumed as an MN-major UMMA operand straight from its token-major tile), or qk (B, Npad, 2C) + vt (C, B*Npad) = V^T
+// (K-major); out (B, Npad, C).
 // CTA = (128-query tile, batch*head, direction).
 #include <cmath>
 #include <cstdlib>
@@ -20,9 +22,10 @@ constexpr int kKV = 128;    // keys per tile   (UMMA N of S, K of PV)
 
 struct AttnParams {
   const __half* qk[2];   // [0]=vis, [1]=ir
-  const __half* vt[2];
+  const __half* vt[2];   // NULL in the fused-qkv form
   __half* out[2];
   int B, N, n_pad, C, heads;
+  int ld;                // row pitch of qk: 2C, or 3C in the fused-qkv form ([q | k | v])
   float scale_log2;      // log2(e) / sqrt(d)
 };
 
@@ -35,6 +38,7 @@ struct AttnParams {
 //   Q / K tiles: 2-D boxes (min(D,64) columns x 128 token rows) of the (B*Npad, 2C) projection matrix -> K-major rows of
 //                32 / 64 / 128 bytes with the matching swizzle (D = 128: two 64-column blocks)
 //   V^T tiles  : two boxes (64 keys x D feature rows) of the (C, B*Npad) matrix -> K-major SW128 (keys are the K dim of PV)
+//   V tiles    : (VF, fused [q|k|v] rows) boxes like K's at column 2C + head*D -> rows = keys, i.e. an MN-major B operand
 // Rows / keys past the tensor are zero-filled by the TMA unit; keys in [N, ...) are masked in the softmax.
 struct AttnMaps {
   CUtensorMap qk[2];   // [0] = vis, [1] = ir : (B*Npad rows, 2C cols), box (min(D,64), 128)
@@ -68,7 +72,7 @@ __device__ __forceinline__ float fast_exp2_t(float x) {
   return y;
 }
 
-template <int D>
+template <int D, bool VF>
 __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(const AttnParams P, const __grid_constant__ AttnMaps M) {
   using L = AttnSmemT<D>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
   if (warp == 4) tmem_alloc<L::kTmemCols>(tmem_slot);
   if (warp == 5 && lane_id() == 0) {
     tma_prefetch_desc(&M.qk[0]); tma_prefetch_desc(&M.qk[1]);
-    tma_prefetch_desc(dir == 0 ? &M.vt[0] : &M.vt[1]);
+    if (!VF) tma_prefetch_desc(dir == 0 ? &M.vt[0] : &M.vt[1]);
   }
   tc_fence_before();
   __syncthreads();
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = umma_idesc_f16(kQT, kKV);
-    constexpr uint32_t idesc_o = umma_idesc_f16(kQT, D);
+    constexpr uint32_t idesc_o = umma_idesc_f16_major(kQT, D, false, VF);      // VF: V tile is MN-major (rows = keys)
     mbar_wait(q_full, 0);
     for (int j = 0; j < nkv; ++j) {
       const int buf = j & 1;
@@ -247,7 +251,8 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
 #pragma unroll
         for (int k = 0; k < kKV / 16; ++k) {
           const uint64_t ad = umma_desc_sw128(sbase + L::kPOff + (k >> 2) * (kQT * 128)) + uint64_t(2 * (k & 3));
-          const uint64_t bd = umma_desc_sw128(sbase + L::kVOff + buf * L::kVBytes + (k >> 2) * (D * 128)) + uint64_t(2 * (k & 3));
+          const uint64_t bd = VF ? umma_desc_mnmajor(sbase + L::kVOff + buf * L::kVBytes + k * 16 * L::kRowB, L::kRowB, kKV * 128)
+                                 : umma_desc_sw128(sbase + L::kVOff + buf * L::kVBytes + (k >> 2) * (D * 128)) + uint64_t(2 * (k & 3));
           umma_f16_ss(tmem_O, ad, bd, idesc_o, k != 0);
         }
         umma_commit(o_full);
@@ -260,6 +265,7 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
     const CUtensorMap* mq = dir == 0 ? &M.qk[1] : &M.qk[0];
     const CUtensorMap* mk = dir == 0 ? &M.qk[0] : &M.qk[1];
     const CUtensorMap* mv = dir == 0 ? &M.vt[0] : &M.vt[1];
+    (void)mv;
     const int row_b = b * n_pad;
     mbar_arrive_expect_tx(q_full, L::kQBytes);
 #pragma unroll
@@ -272,8 +278,14 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
 #pragma unroll
       for (int kb = 0; kb < L::kKB; ++kb)
         tma_load_2d(sbase + L::kKOff + buf * L::kKBytes + kb * (kKV * 128), mk, kv_full(buf), C + head * D + kb * 64, row_b + j * kKV);
-      tma_load_2d(sbase + L::kVOff + buf * L::kVBytes, mv, kv_full(buf), row_b + j * kKV, head * D);
-      tma_load_2d(sbase + L::kVOff + buf * L::kVBytes + D * 128, mv, kv_full(buf), row_b + j * kKV + 64, head * D);
+      if (VF) {
+#pragma unroll
+        for (int kb = 0; kb < L::kKB; ++kb)
+          tma_load_2d(sbase + L::kVOff + buf * L::kVBytes + kb * (kKV * 128), mk, kv_full(buf), 2 * C + head * D + kb * 64, row_b + j * kKV);
+      } else {
+        tma_load_2d(sbase + L::kVOff + buf * L::kVBytes, mv, kv_full(buf), row_b + j * kKV, head * D);
+        tma_load_2d(sbase + L::kVOff + buf * L::kVBytes + D * 128, mv, kv_full(buf), row_b + j * kKV + 64, head * D);
+      }
     }
   }
   tc_fence_before();
@@ -306,10 +318,10 @@ __global__ void cross_attn_simt_kernel(const AttnParams P) {
     for (int i = 0; i < d; ++i) o[i] = __float2half(0.f);
     return;
   }
-  const __half* q = qsrc + (size_t(b) * P.n_pad + qn) * (2 * P.C) + head * d;
+  const __half* q = qsrc + (size_t(b) * P.n_pad + qn) * P.ld + head * d;
   float mx = -INFINITY;
   for (int k = 0; k < P.N; ++k) {
-    const __half* kp = ksrc + (size_t(b) * P.n_pad + k) * (2 * P.C) + P.C + head * d;
+    const __half* kp = ksrc + (size_t(b) * P.n_pad + k) * P.ld + P.C + head * d;
     float s = 0.f;
     for (int i = 0; i < d; ++i) s += __half2float(q[i]) * __half2float(kp[i]);
     mx = fmaxf(mx, s);
@@ -318,20 +330,22 @@ __global__ void cross_attn_simt_kernel(const AttnParams P) {
   float acc[128];
   for (int i = 0; i < d; ++i) acc[i] = 0.f;
   for (int k = 0; k < P.N; ++k) {
-    const __half* kp = ksrc + (size_t(b) * P.n_pad + k) * (2 * P.C) + P.C + head * d;
+    const __half* kp = ksrc + (size_t(b) * P.n_pad + k) * P.ld + P.C + head * d;
     float s = 0.f;
     for (int i = 0; i < d; ++i) s += __half2float(q[i]) * __half2float(kp[i]);
     float p = exp2f((s - mx) * P.scale_log2);
     l += p;
     for (int i = 0; i < d; ++i)
-      acc[i] += p * __half2float(vsrc[size_t(head * d + i) * (size_t(P.B) * P.n_pad) + size_t(b) * P.n_pad + k]);
+      acc[i] += p * __half2float(vsrc ? vsrc[size_t(head * d + i) * (size_t(P.B) * P.n_pad) + size_t(b) * P.n_pad + k]
+                                      : kp[P.C + i]);                     // fused form: v sits one C further in the key's row
   }
   for (int i = 0; i < d; ++i) o[i] = __float2half_rn(acc[i] / l);
 }
 
 static int fill_attn(const void* qk_vis, const void* qk_ir, const void* vt_vis, const void* vt_ir, void* out_vis,
                      void* out_ir, int B, int N, int n_pad, int C, int heads, AttnParams& P) {
-  if (!qk_vis || !qk_ir || !vt_vis || !vt_ir || !out_vis || !out_ir) return set_error(ICAF_ERR_BAD_ARG, "cross_attention: null pointer");
+  // vt_* both NULL: the fused form, qk_* are (B, Npad, 3C) [q | k | v] matrices
+  if (!qk_vis || !qk_ir || (!vt_vis != !vt_ir) || !out_vis || !out_ir) return set_error(ICAF_ERR_BAD_ARG, "cross_attention: null pointer");
   if (B < 1 || N < 1 || n_pad < N || n_pad % 8 || heads < 1 || C % heads) return set_error(ICAF_ERR_BAD_ARG, "cross_attention: bad shape");
   int d = C / heads;
   if (d != 16 && d != 32 && d != 64 && d != 128) return set_error(ICAF_ERR_UNSUPPORTED, "cross_attention: head dim must be 16/32/64/128");
@@ -339,27 +353,40 @@ static int fill_attn(const void* qk_vis, const void* qk_ir, const void* vt_vis, 
   P.vt[0] = (const __half*)vt_vis; P.vt[1] = (const __half*)vt_ir;
   P.out[0] = (__half*)out_vis; P.out[1] = (__half*)out_ir;
   P.B = B; P.N = N; P.n_pad = n_pad; P.C = C; P.heads = heads;
+  P.ld = vt_vis ? 2 * C : 3 * C;
   P.scale_log2 = 1.4426950408889634f / sqrtf(float(d));   // 1/sqrt(d_k), common.py:670
   return ICAF_OK;
 }
 
-template <int D>
+template <int D, bool VF>
 static int launch_attn_tma(const AttnParams& P, cudaStream_t st) {
   using L = AttnSmemT<D>;
   static bool configured[kMaxDevices] = {false};
-  if (int rc = configure_smem(cross_attn_tma_kernel<D>, L::kTotal, configured, "cross_attention: cudaFuncSetAttribute")) return rc;
+  if (int rc = configure_smem(cross_attn_tma_kernel<D, VF>, L::kTotal, configured, "cross_attention: cudaFuncSetAttribute")) return rc;
   AttnMaps maps;
   memset(&maps, 0, sizeof(maps));
   const uint64_t rows = uint64_t(P.B) * P.n_pad;
   for (int i = 0; i < 2; ++i) {
-    int rc = encode_tmap_2d(&maps.qk[i], P.qk[i], uint64_t(2 * P.C), rows, uint64_t(2 * P.C) * 2, D < 64 ? D : 64, kQT);
+    int rc = encode_tmap_2d(&maps.qk[i], P.qk[i], uint64_t(P.ld), rows, uint64_t(P.ld) * 2, D < 64 ? D : 64, kQT);
     if (rc) return rc;
-    rc = encode_tmap_2d(&maps.vt[i], P.vt[i], rows, uint64_t(P.C), rows * 2, 64, D);
-    if (rc) return rc;
+    if (!VF) {
+      rc = encode_tmap_2d(&maps.vt[i], P.vt[i], rows, uint64_t(P.C), rows * 2, 64, D);
+      if (rc) return rc;
+    }
   }
   dim3 grid((P.n_pad + kQT - 1) / kQT, P.B * P.heads, 2);
-  launch_k(cross_attn_tma_kernel<D>, dim3(grid), dim3(192), L::kTotal, st, P, maps);
+  launch_k(cross_attn_tma_kernel<D, VF>, dim3(grid), dim3(192), L::kTotal, st, P, maps);
   return check_launch("cross_attention");
+}
+
+template <bool VF>
+static int dispatch_attn(const AttnParams& P, cudaStream_t st) {
+  switch (P.C / P.heads) {
+    case 16: return launch_attn_tma<16, VF>(P, st);
+    case 32: return launch_attn_tma<32, VF>(P, st);
+    case 64: return launch_attn_tma<64, VF>(P, st);
+    default: return launch_attn_tma<128, VF>(P, st);
+  }
 }
 
 }  // namespace icaf
@@ -375,12 +402,7 @@ extern "C" int icaf_cross_attention(const void* qk_vis, const void* qk_ir, const
   if ((uint64_t(B) * n_pad * 2) % 16 || (reinterpret_cast<uintptr_t>(vt_vis) & 15) || (reinterpret_cast<uintptr_t>(qk_vis) & 15) ||
       (reinterpret_cast<uintptr_t>(vt_ir) & 15) || (reinterpret_cast<uintptr_t>(qk_ir) & 15))
     return set_error(ICAF_ERR_BAD_ARG, "cross_attention: TMA needs 16-byte aligned tensors and row pitches");
-  switch (C / heads) {
-    case 16: return launch_attn_tma<16>(P, st);
-    case 32: return launch_attn_tma<32>(P, st);
-    case 64: return launch_attn_tma<64>(P, st);
-    default: return launch_attn_tma<128>(P, st);
-  }
+  return vt_vis ? dispatch_attn<false>(P, st) : dispatch_attn<true>(P, st);
 }
 
 extern "C" int icaf_cross_attention_simt(const void* qk_vis, const void* qk_ir, const void* vt_vis, const void* vt_ir,

@@ -188,6 +188,7 @@ __global__ void copy_channels_kernel(const __half* __restrict__ x, long long x_l
 // DMFF front: avg+max pool with (kh,kw)/(sh,sw) windows, learnable mix, + pos_emb -> tokens (B,Npad,C)
 struct PoolTokParams {
   const __half* x[2]; const __half* pos[2]; __half* tok[2];
+  float2* stats[2];        // optional: (sum, sum of squares) of every token row per 32 channels, [B*Npad][C/32]
   const float* mix;
   long long x_ld;
   int B, H, W, C8, nh, nw, n_pad, kh, kw, sh, sw;
@@ -198,50 +199,61 @@ __global__ void dmff_pool_tokens_kernel(const PoolTokParams P) {
   const int mod = blockIdx.y;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)P.B * P.n_pad * P.C8;
-  if (i >= total) return;
+  const bool live = i < total;            // no early exit: groups of four lanes reduce the row statistics together
+  if (!live) i = total - 1;
   int c = int(i % P.C8);
   long long t = i / P.C8;
   int n = int(t % P.n_pad);
   int b = int(t / P.n_pad);
   __half* out = (mod ? P.tok[1] : P.tok[0]) + t * (P.C8 * 8) + c * 8;
   const int N = P.nh * P.nw;
-  if (n >= N) {
-    *reinterpret_cast<uint4*>(out) = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  const __half* x = mod ? P.x[1] : P.x[0];
-  const int ty = n / P.nw, tx = n % P.nw;
-  float sum[8], mx[8];
+  uint4 packed = make_uint4(0, 0, 0, 0);  // pad rows (n >= N) are zero
+  if (n < N) {
+    const __half* x = mod ? P.x[1] : P.x[0];
+    const int ty = n / P.nw, tx = n % P.nw;
+    float sum[8], mx[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { sum[e] = 0.f; mx[e] = -INFINITY; }
-  // window elements are fetched 8 at a time (independent 16-byte loads in flight) before they are reduced
-  const __half* x0 = x + ((long long)(b * P.H + ty * P.sh) * P.W + tx * P.sw) * P.x_ld + c * 8;
-  const int wn = P.kh * P.kw;
-  for (int w0 = 0; w0 < wn; w0 += 8) {
-    uint4 v[8];
+    for (int e = 0; e < 8; ++e) { sum[e] = 0.f; mx[e] = -INFINITY; }
+    // window elements are fetched 8 at a time (independent 16-byte loads in flight) before they are reduced
+    const __half* x0 = x + ((long long)(b * P.H + ty * P.sh) * P.W + tx * P.sw) * P.x_ld + c * 8;
+    const int wn = P.kh * P.kw;
+    for (int w0 = 0; w0 < wn; w0 += 8) {
+      uint4 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int w = w0 + j;
-      int ky = w / P.kw, kx = w - ky * P.kw;
-      if (w < wn) v[j] = ldg16(x0 + ((long long)ky * P.W + kx) * P.x_ld);
-    }
+      for (int j = 0; j < 8; ++j) {
+        int w = w0 + j;
+        int ky = w / P.kw, kx = w - ky * P.kw;
+        if (w < wn) v[j] = ldg16(x0 + ((long long)ky * P.W + kx) * P.x_ld);
+      }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (w0 + j < wn) {
-        float f[8];
-        unpack8(v[j], f);
+      for (int j = 0; j < 8; ++j) {
+        if (w0 + j < wn) {
+          float f[8];
+          unpack8(v[j], f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { sum[e] += f[e]; mx[e] = fmaxf(mx[e], f[e]); }
+          for (int e = 0; e < 8; ++e) { sum[e] += f[e]; mx[e] = fmaxf(mx[e], f[e]); }
+        }
       }
     }
-  }
-  const float w1 = P.mix[mod * 2], w2 = P.mix[mod * 2 + 1];
-  const float inv = 1.f / float(P.kh * P.kw);
-  float pe[8], o[8];
-  unpack8(ldg16((mod ? P.pos[1] : P.pos[0]) + (long long)n * (P.C8 * 8) + c * 8), pe);
+    const float w1 = P.mix[mod * 2], w2 = P.mix[mod * 2 + 1];
+    const float inv = 1.f / float(P.kh * P.kw);
+    float pe[8], o[8];
+    unpack8(ldg16((mod ? P.pos[1] : P.pos[0]) + (long long)n * (P.C8 * 8) + c * 8), pe);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) o[e] = w1 * (sum[e] * inv) + w2 * mx[e] + pe[e];
-  *reinterpret_cast<uint4*>(out) = pack8(o);
+    for (int e = 0; e < 8; ++e) o[e] = w1 * (sum[e] * inv) + w2 * mx[e] + pe[e];
+    packed = pack8(o);
+  }
+  if (live) *reinterpret_cast<uint4*>(out) = packed;
+  float2* st = mod ? P.stats[1] : P.stats[0];
+  if (st) {                               // statistics of the fp16-rounded token row, one partial per 32 channels (4 lanes)
+    float f[8], su = 0.f, sq = 0.f;
+    unpack8(packed, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { su += f[e]; sq += f[e] * f[e]; }
+    su += __shfl_xor_sync(0xffffffffu, su, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    su += __shfl_xor_sync(0xffffffffu, su, 2); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    if (live && (c & 3) == 0) st[t * (P.C8 >> 2) + (c >> 2)] = make_float2(su, sq);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -389,6 +401,31 @@ __global__ void detect_decode_kernel(const DetectParams P) {
     zo[o] = __float2half_rn(r);
     if (o >= 5) lo[o - 5] = raw;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (sum, sum of squares) per row of a (rows, C) fp16 matrix: one warp per row, 16-byte loads.
+__global__ void row_stats_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1, float2* __restrict__ s0,
+                                 float2* __restrict__ s1, long long rows, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const __half* x = (blockIdx.y ? x1 : x0) + row * C;
+  float su = 0.f, sq = 0.f;
+  for (int ch = lane; ch < (C >> 3); ch += 32) {
+    float v[8];
+    unpack8(ldg16(x + ch * 8), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { su += v[e]; sq += v[e] * v[e]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) (blockIdx.y ? s1 : s0)[row] = make_float2(su, sq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -622,8 +659,8 @@ extern "C" int icaf_copy_channels(const void* x, int64_t x_ld, void* y, int64_t 
 }
 
 extern "C" int icaf_dmff_pool_tokens(const void* x_vis, const void* x_ir, int64_t x_ld, const void* pos_vis,
-                                     const void* pos_ir, const float* mix, void* tok_vis, void* tok_ir, int B, int H,
-                                     int W, int C, int nh, int nw, int n_pad, void* stream) {
+                                     const void* pos_ir, const float* mix, void* tok_vis, void* tok_ir, float* stats_vis,
+                                     float* stats_ir, int B, int H, int W, int C, int nh, int nw, int n_pad, void* stream) {
   if (!x_vis || !x_ir || !pos_vis || !pos_ir || !mix || !tok_vis || !tok_ir) return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens: null pointer");
   if (C % 8 || x_ld % 8 || nh < 1 || nw < 1 || nh > H || nw > W || n_pad < nh * nw || n_pad % 8)
     return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens: bad shape (token grid must not exceed the map)");
@@ -631,6 +668,9 @@ extern "C" int icaf_dmff_pool_tokens(const void* x_vis, const void* x_ir, int64_
   P.x[0] = (const __half*)x_vis; P.x[1] = (const __half*)x_ir;
   P.pos[0] = (const __half*)pos_vis; P.pos[1] = (const __half*)pos_ir;
   P.tok[0] = (__half*)tok_vis; P.tok[1] = (__half*)tok_ir;
+  if ((stats_vis || stats_ir) && (!stats_vis || !stats_ir || C % 32))
+    return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens: row statistics need both outputs and C % 32 == 0");
+  P.stats[0] = (float2*)stats_vis; P.stats[1] = (float2*)stats_ir;
   P.mix = mix; P.x_ld = x_ld;
   P.B = B; P.H = H; P.W = W; P.C8 = C / 8; P.nh = nh; P.nw = nw; P.n_pad = n_pad;
   // AdaptivePool2d geometry, models/common.py:878-882 (identity when the map is not larger than the grid)
@@ -712,4 +752,12 @@ extern "C" int icaf_nms(const void* z, int B, int R, int no, float conf_thres, f
   P.order = (int*)((char*)workspace + (size_t)B * R * sizeof(unsigned long long));
   launch_k(nms_kernel, dim3(B), dim3(kNmsThreads), 0, (cudaStream_t)stream, P);
   return check_launch("nms");
+}
+
+extern "C" int icaf_row_stats(const void* x0, const void* x1, float* stats0, float* stats1, int64_t rows, int C, void* stream) {
+  if (!x0 || !stats0 || (x1 && !stats1) || rows < 1 || C < 8 || C % 8) return set_error(ICAF_ERR_BAD_ARG, "row_stats: bad argument");
+  dim3 grid(blocks_for(rows, 4), x1 ? 2 : 1);
+  launch_k(row_stats_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const __half*)x0, (const __half*)x1, (float2*)stats0,
+           (float2*)stats1, (long long)rows, C);
+  return check_launch("row_stats");
 }

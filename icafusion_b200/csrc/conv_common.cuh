@@ -16,6 +16,9 @@ struct ConvProblem {
   const __half* x; const float* bias; const __half* res; __half* y;
   const float* alpha; const float* beta;
   long long x_ld, res_ld, y_ld;
+  const float2* ln_stats;   // LN fold: (sum, sum of squares) partials of every INPUT row, [M][ln_parts]
+  const float* ln_s;        // LN fold: column sums of the gamma-folded filter, fp32 [Cout]
+  float2* stats_out;        // EMIT_STATS: (sum, sum of squares) partials of every OUTPUT row, [M][ceil(N/32)]
 };
 // ICAF_DBG(P, bit): compile-time false unless the library is built with -DICAF_PROBE (ICAF_PROBE=1 python -m icafusion_b200.build)
 #ifdef ICAF_PROBE
@@ -34,6 +37,8 @@ struct ConvParams {
   int splits;                             // split-K factor = cluster size along x (1 = no cluster); partial sums meet in DSMEM
   int cblk;                               // A_TMA4D: channels per TMA box = min(Cin, 64); < 64 only in the persistent kernel
   int halo;                               // conv_pair.cu: 3x3/s1 layers stage three x-shifted (th+2)-row copies per channel block (0 / 1)
+  int ln_parts;                           // LN fold: partials per input row (0 = no fold)
+  float ln_eps, ln_inv_k;                 // LN fold: epsilon, 1 / (normalised features = K)
   int dbg;                                // probe builds (-DICAF_PROBE, tools/conv_probe.py): 1 no stores, 2 no activation,
                                           // 8 no A loads, 16 no B loads, 32 no MMA; always 0 in the shipped library
 };
@@ -49,17 +54,48 @@ __device__ __forceinline__ ConvProblem pick_problem(const ConvParams& P, unsigne
   r.alpha = z ? P.p[1].alpha : P.p[0].alpha; r.beta = z ? P.p[1].beta : P.p[0].beta;
   r.x_ld = z ? P.p[1].x_ld : P.p[0].x_ld; r.res_ld = z ? P.p[1].res_ld : P.p[0].res_ld;
   r.y_ld = z ? P.p[1].y_ld : P.p[0].y_ld;
+  r.ln_stats = z ? P.p[1].ln_stats : P.p[0].ln_stats; r.ln_s = z ? P.p[1].ln_s : P.p[0].ln_s;
+  r.stats_out = z ? P.p[1].stats_out : P.p[0].stats_out;
   return r;
+}
+
+// Per-row extras of an epilogue thread.  XM = 1 (LayerNorm folded into this GEMM, common.py:660,665,749-750): the filter
+// carries gamma, the bias carries beta . W, and the row is normalised after the fact:
+//     LN(x) . W^T + b  =  rstd * (x . W'^T  -  mean * s)  +  b'          W' = W diag(gamma), s_n = sum_k W'[n][k]
+// XM = 2 (EMIT_STATS): sum and sum of squares of the fp16-rounded outputs of this row, for the LN fold of the NEXT GEMM.
+struct EpiRow {
+  float ln_a, ln_mu;     // rstd, mean of this thread's input row
+  const float* ln_s;     // s, offset to the first column of the current pass
+  float sum, sumsq;
+};
+__device__ __forceinline__ void epi_row_ln(EpiRow& ex, const ConvParams& P, const ConvProblem& pr, int m, bool mvalid) {
+  float su = 0.f, sq = 0.f;
+  if (mvalid) {
+    const float2* sp = pr.ln_stats + size_t(m) * P.ln_parts;
+    for (int i = 0; i < P.ln_parts; ++i) { const float2 v = __ldg(sp + i); su += v.x; sq += v.y; }
+  }
+  const float mu = su * P.ln_inv_k;
+  ex.ln_mu = mu;
+  ex.ln_a = rsqrtf(fmaxf(sq * P.ln_inv_k - mu * mu, 0.f) + P.ln_eps);
+}
+// slots [n_begin/32, n_end/32) of this row's partials: the first one carries the sums, the others zero
+__device__ __forceinline__ void epi_row_emit(const EpiRow& ex, const ConvParams& P, const ConvProblem& pr, int m, int n_begin, int n_end) {
+  const int slots = (P.N + 31) >> 5;
+  float2* sp = pr.stats_out + size_t(m) * slots;
+  const int s0 = n_begin >> 5, s1 = min((n_end + 31) >> 5, slots);
+  for (int i = s0; i < s1; ++i) sp[i] = i == s0 ? make_float2(ex.sum, ex.sumsq) : make_float2(0.f, 0.f);
 }
 
 // One 32-column chunk of one output row: + bias, activation, residual, fp16 store.
 // ACT: 0 none, 1 SiLU, 2 GELU(erf).  RES: 0 none, 1 y = act(v) + res, 2 y = alpha*res + beta*v.
-template <int ACT, int RES>
+template <int ACT, int RES, int XM = 0>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float* __restrict__ sb, float rbias,
                                           float alpha, float beta, const __half* __restrict__ rp,
-                                          __half* __restrict__ yp, bool vec, int ncols, bool do_store = true) {
+                                          __half* __restrict__ yp, bool vec, int ncols, EpiRow& ex, int cb, bool do_store = true) {
   auto f = [&](int j) {
-    float t = __uint_as_float(acc[j]) + sb[j] + rbias;
+    float a = __uint_as_float(acc[j]);
+    if (XM == 1) a = ex.ln_a * (a - ex.ln_mu * __ldg(ex.ln_s + cb + j));
+    float t = a + sb[j] + rbias;
     if (ACT == ICAF_ACT_SILU) t = silu_f(t);
     if (ACT == ICAF_ACT_GELU) t = gelu_erf_f(t);
     return t;
@@ -88,6 +124,15 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float
       uint4 o;
       o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
       o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+      if (XM == 2) {
+        const __half2* oh = reinterpret_cast<const __half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 w = __half22float2(oh[e]);
+          ex.sum += w.x + w.y;
+          ex.sumsq += w.x * w.x + w.y * w.y;
+        }
+      }
       if (do_store) *reinterpret_cast<uint4*>(yp + q * 8) = o;
     }
   } else {
@@ -99,7 +144,9 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float
           float rf = __half2float(rp[j]);
           t = RES == 2 ? alpha * rf + beta * t : t + rf;
         }
-        yp[j] = __float2half_rn(t);
+        const __half h = __float2half_rn(t);
+        if (XM == 2) { const float w = __half2float(h); ex.sum += w; ex.sumsq += w * w; }
+        yp[j] = h;
       }
     }
   }
@@ -109,10 +156,10 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&acc)[32], const float
 // aligned are written with one 256-bit store: a full L2 sector per lane and instruction.  `sb`: 16 bias floats (smem).
 // `al`: 2 = 32-byte aligned, 1 = 16-byte aligned, 0 = element-wise loads / stores of the first `ncols` columns (ragged N,
 // odd pitches); the math is shared by the three so the hot loop stays small (instruction cache, tools/conv_probe.py).
-template <int ACT, int RES>
+template <int ACT, int RES, int XM = 0>
 __device__ __forceinline__ void epi_chunk16(const uint32_t (&acc)[16], const float* __restrict__ sb, float rbias,
                                             float alpha, float beta, const __half* __restrict__ rp,
-                                            __half* __restrict__ yp, int al, int ncols, bool do_store) {
+                                            __half* __restrict__ yp, int al, int ncols, bool do_store, EpiRow& ex, int cb) {
   auto act = [&](float t) {
     if (ACT == ICAF_ACT_SILU) t = silu_f(t);
     if (ACT == ICAF_ACT_GELU) t = gelu_erf_f(t);
@@ -122,10 +169,17 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&acc)[16], const flo
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * q);
-    v[4 * q + 0] = act(__uint_as_float(acc[4 * q + 0]) + b4.x + rbias);
-    v[4 * q + 1] = act(__uint_as_float(acc[4 * q + 1]) + b4.y + rbias);
-    v[4 * q + 2] = act(__uint_as_float(acc[4 * q + 2]) + b4.z + rbias);
-    v[4 * q + 3] = act(__uint_as_float(acc[4 * q + 3]) + b4.w + rbias);
+    float a0 = __uint_as_float(acc[4 * q + 0]), a1 = __uint_as_float(acc[4 * q + 1]);
+    float a2 = __uint_as_float(acc[4 * q + 2]), a3 = __uint_as_float(acc[4 * q + 3]);
+    if (XM == 1) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(ex.ln_s + cb + 4 * q));
+      a0 = ex.ln_a * (a0 - ex.ln_mu * s4.x); a1 = ex.ln_a * (a1 - ex.ln_mu * s4.y);
+      a2 = ex.ln_a * (a2 - ex.ln_mu * s4.z); a3 = ex.ln_a * (a3 - ex.ln_mu * s4.w);
+    }
+    v[4 * q + 0] = act(a0 + b4.x + rbias);
+    v[4 * q + 1] = act(a1 + b4.y + rbias);
+    v[4 * q + 2] = act(a2 + b4.z + rbias);
+    v[4 * q + 3] = act(a3 + b4.w + rbias);
   }
   if (RES != 0) {
     uint32_t rr[8];
@@ -159,6 +213,16 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&acc)[16], const flo
   uint32_t o[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) o[e] = pack_half2(v[2 * e], v[2 * e + 1]);
+  if (XM == 2) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (2 * e < ncols) {                         // ragged tails: only the columns that exist
+        const float2 w = __half22float2(*reinterpret_cast<const __half2*>(&o[e]));
+        ex.sum += w.x; ex.sumsq += w.x * w.x;
+        if (2 * e + 1 < ncols) { ex.sum += w.y; ex.sumsq += w.y * w.y; }
+      }
+    }
+  }
   if (do_store) {
     if (al == 2) {
       st_global_v8(yp, o);

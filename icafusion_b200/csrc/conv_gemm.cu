@@ -180,9 +180,13 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
     for (int i = 0; i < (BN + 127) / 128; ++i)
       if (tid + 128 * i < BN) sbias[tid + 128 * i] = bias_r[i];
     named_bar_sync(1, 128);                // bias tile visible to the four epilogue warps
+    EpiRow ex;
+    ex.sum = ex.sumsq = 0.f; ex.ln_a = 1.f; ex.ln_mu = 0.f; ex.ln_s = pr.ln_s ? pr.ln_s + n0 : nullptr;
+    if (P.ln_parts > 0) epi_row_ln(ex, P, pr, m, mvalid);     // row statistics: fetched while the main loop still runs
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int mode_act = P.act * 3 + mode;
+    // 9 / 10: LayerNorm folded into this GEMM (no activation / GELU); 11: scaled residual + statistics of the output rows
+    const int mode_act = P.ln_parts > 0 ? (P.act == ICAF_ACT_GELU ? 10 : 9) : ((P.epi & ICAF_EPI_EMIT_STATS) ? 11 : P.act * 3 + mode);
     if (splits > 1) {
       // ---- split-K reduction through distributed shared memory ----
       // Every CTA's ring is idle once its accumulator is complete.  Barrier A: all accumulators done (so the leader's
@@ -236,18 +240,22 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
           __half* yp = yrow + nb;
           // act / residual mode are warp-uniform: dispatch once per chunk to straight-line specialisations
           switch (mode_act) {
-            case 0: epi_chunk<0, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 1: epi_chunk<0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 2: epi_chunk<0, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 3: epi_chunk<1, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 4: epi_chunk<1, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 5: epi_chunk<1, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 6: epi_chunk<2, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            case 7: epi_chunk<2, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
-            default: epi_chunk<2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols); break;
+            case 0: epi_chunk<0, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 1: epi_chunk<0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 2: epi_chunk<0, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 3: epi_chunk<1, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 4: epi_chunk<1, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 5: epi_chunk<1, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 6: epi_chunk<2, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 7: epi_chunk<2, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 8: epi_chunk<2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 9: epi_chunk<0, 0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            case 10: epi_chunk<2, 0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            default: epi_chunk<0, 2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
           }
         }
       }
+      if (mode_act == 11 && mvalid && n0 < P.N) epi_row_emit(ex, P, pr, m, n0, min(n0 + BN, P.N));
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
@@ -359,10 +367,16 @@ static int fill_geom(const icaf_conv_geom* g, int n_io, ConvParams& P) {
     return set_error(ICAF_ERR_BAD_ARG, "conv2d: size out of range");
   if ((g->epi & (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES)) == (ICAF_EPI_ADD_RES | ICAF_EPI_SCALED_RES))
     return set_error(ICAF_ERR_BAD_ARG, "conv2d: ADD_RES and SCALED_RES are exclusive");
+  if ((g->epi & ICAF_EPI_LN_FOLD) && ((g->epi & ~ICAF_EPI_LN_FOLD) != 0 || !(g->act == ICAF_ACT_NONE || g->act == ICAF_ACT_GELU) ||
+                                      g->kh != 1 || g->kw != 1 || g->stride != 1 || g->pad != 0))
+    return set_error(ICAF_ERR_UNSUPPORTED, "conv2d: LN_FOLD is a linear-layer (1x1) epilogue without residual, activation none / GELU");
+  if ((g->epi & ICAF_EPI_EMIT_STATS) && ((g->epi & ~ICAF_EPI_EMIT_STATS) != ICAF_EPI_SCALED_RES || g->act != ICAF_ACT_NONE))
+    return set_error(ICAF_ERR_UNSUPPORTED, "conv2d: EMIT_STATS rides on the SCALED_RES epilogue without activation");
   P.M = int(M); P.N = g->Cout; P.K = g->kh * g->kw * g->Cin; P.k_pad = g->k_pad;
   P.B = g->B; P.Hi = g->Hi; P.Wi = g->Wi; P.Cin = g->Cin; P.Ho = g->Ho; P.Wo = g->Wo;
   P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad = g->pad; P.act = g->act; P.epi = g->epi;
   P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.stages = 2; P.splits = 1; P.cblk = 64; P.halo = 0; P.dbg = g_dbg;
+  P.ln_parts = 0; P.ln_eps = 0.f; P.ln_inv_k = 0.f;
   memset(P.p, 0, sizeof(P.p));
   return ICAF_OK;
 }
@@ -378,8 +392,17 @@ static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io
     if ((reinterpret_cast<uintptr_t>(s.x) & 15) || (reinterpret_cast<uintptr_t>(s.w) & 15) || (s.x_ld % 8 && g->Cin != 4) ||
         (g->Cin == 4 && s.x_ld != 4))
       return set_error(ICAF_ERR_BAD_ARG, "conv2d: x / w must be 16-byte aligned with x_ld a multiple of 8");
+    if ((g->epi & ICAF_EPI_LN_FOLD) && (!s.ln_stats || !s.ln_colsum || s.ln_parts < 1 || s.ln_parts > 64))
+      return set_error(ICAF_ERR_BAD_ARG, "conv2d: LN_FOLD needs ln_stats, ln_colsum and 1..64 partials per row");
+    if ((g->epi & ICAF_EPI_EMIT_STATS) && !s.stats_out) return set_error(ICAF_ERR_BAD_ARG, "conv2d: EMIT_STATS needs stats_out");
+    if (i > 0 && (g->epi & ICAF_EPI_LN_FOLD) && (s.ln_parts != io[0].ln_parts || s.ln_eps != io[0].ln_eps))
+      return set_error(ICAF_ERR_BAD_ARG, "conv2d: grouped problems must share ln_parts / ln_eps");
     P.p[i] = ConvProblem{(const __half*)s.x, s.bias, need_res ? (const __half*)s.res : nullptr, (__half*)s.y, s.alpha, s.beta,
-                         s.x_ld, s.res_ld, s.y_ld};
+                         s.x_ld, s.res_ld, s.y_ld,
+                         (g->epi & ICAF_EPI_LN_FOLD) ? (const float2*)s.ln_stats : nullptr,
+                         (g->epi & ICAF_EPI_LN_FOLD) ? s.ln_colsum : nullptr,
+                         (g->epi & ICAF_EPI_EMIT_STATS) ? (float2*)s.stats_out : nullptr};
+    if (i == 0 && (g->epi & ICAF_EPI_LN_FOLD)) { P.ln_parts = s.ln_parts; P.ln_eps = s.ln_eps; P.ln_inv_k = 1.0f / float(P.K); }
     w[i] = (const __half*)s.w;
   }
   return ICAF_OK;

@@ -139,14 +139,14 @@ __device__ __forceinline__ PairTile pair_tile(const ConvParams& P, int t, int ra
 }
 
 // Same as conv_persist.cu's epi_tile, except that the accumulator buffer is handed back to the LEADER's MMA thread.
-template <int CW, int ACT, int RES>
+template <int CW, int ACT, int RES, int XM = 0>
 __device__ __forceinline__ void epi_tile_pair(uint32_t trow, uint32_t tempty_leader, const float* sb, float rbias, float alpha,
-                                              float beta, const __half* rrow, __half* yrow, int al_row, bool mvalid, int nrem) {
+                                              float beta, const __half* rrow, __half* yrow, int al_row, bool mvalid, int nrem, EpiRow& ex) {
   uint32_t acc0[16], acc1[16];
   auto chunk = [&](const uint32_t (&acc)[16], int cb) {
     const int nc = nrem - cb;
     if (mvalid && nc > 0)
-      epi_chunk16<ACT, RES>(acc, sb + cb, rbias, alpha, beta, rrow ? rrow + cb : nullptr, yrow + cb, nc >= 16 ? al_row : 0, nc, true);
+      epi_chunk16<ACT, RES, XM>(acc, sb + cb, rbias, alpha, beta, rrow ? rrow + cb : nullptr, yrow + cb, nc >= 16 ? al_row : 0, nc, true, ex, cb);
   };
   tmem_ld16(trow, acc0);
 #pragma unroll 1
@@ -240,7 +240,8 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
     const int ry = a_mode == A_TMA4D ? gt / P.tw : 0;
     const int rx = a_mode == A_TMA4D ? gt - ry * P.tw : 0;
     const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : ((P.epi & ICAF_EPI_ADD_RES) ? 1 : 0);
-    const int mode_act = P.act * 3 + mode;
+    // 9 / 10: LayerNorm folded into this GEMM (no activation / GELU); 11: scaled residual + statistics of the output rows
+    const int mode_act = P.ln_parts > 0 ? (P.act == ICAF_ACT_GELU ? 10 : 9) : ((P.epi & ICAF_EPI_EMIT_STATS) ? 11 : P.act * 3 + mode);
     const bool row_bias = (P.epi & ICAF_EPI_BIAS_ROW) != 0;
     float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + L::kBarBytes) + eg * 2 * kQCW;
     const uint32_t tempty_leader = map_to_cta(tempty_bar(buf), 0);
@@ -285,17 +286,24 @@ conv_gemm_pair_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps,
       tc_fence_after();
       const uint32_t trow = tmem_base + uint32_t(buf * kQBN + half * kQCW) + lane_off;
       const int nrem = P.N - nb0;
+      EpiRow ex;
+      ex.sum = ex.sumsq = 0.f; ex.ln_a = 1.f; ex.ln_mu = 0.f; ex.ln_s = pr.ln_s ? pr.ln_s + nb0 : nullptr;
+      if (P.ln_parts > 0) epi_row_ln(ex, P, pr, m, mvalid);
       switch (mode_act) {
-        case 0: epi_tile_pair<kQCW, 0, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
-        case 1: epi_tile_pair<kQCW, 0, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
-        case 2: epi_tile_pair<kQCW, 0, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
-        case 3: epi_tile_pair<kQCW, 1, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
-        case 4: epi_tile_pair<kQCW, 1, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
-        case 5: epi_tile_pair<kQCW, 1, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
-        case 6: epi_tile_pair<kQCW, 2, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
-        case 7: epi_tile_pair<kQCW, 2, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
-        default: epi_tile_pair<kQCW, 2, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem); break;
+        case 0: epi_tile_pair<kQCW, 0, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 1: epi_tile_pair<kQCW, 0, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 2: epi_tile_pair<kQCW, 0, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 3: epi_tile_pair<kQCW, 1, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 4: epi_tile_pair<kQCW, 1, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 5: epi_tile_pair<kQCW, 1, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 6: epi_tile_pair<kQCW, 2, 0>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 7: epi_tile_pair<kQCW, 2, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 8: epi_tile_pair<kQCW, 2, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 9: epi_tile_pair<kQCW, 0, 0, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        case 10: epi_tile_pair<kQCW, 2, 0, 1>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
+        default: epi_tile_pair<kQCW, 0, 2, 2>(trow, tempty_leader, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, ex); break;
       }
+      if (mode_act == 11 && mvalid && nrem > 0) epi_row_emit(ex, P, pr, m, nb0, min(nb0 + kQCW, P.N));
     }
   } else if (warp == kQEpiWarps) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)

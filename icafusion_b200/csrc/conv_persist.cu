@@ -82,17 +82,17 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& P, const TileI
 // of chunk i+1 is in flight during the math of chunk i (two register buffers, loop unrolled by two only: the hot loop
 // must fit the instruction cache); the accumulator buffer goes back to the MMA warp as soon as the last chunk sits in
 // registers.
-template <int CW, int ACT, int RES>
+template <int CW, int ACT, int RES, int XM = 0>
 __device__ __forceinline__ void epi_tile(uint32_t trow, uint32_t tempty, const float* sb, float rbias, float alpha,
                                          float beta, const __half* rrow, __half* yrow, int al_row, bool mvalid, int nrem,
-                                         bool do_store) {
+                                         bool do_store, EpiRow& ex) {
   static_assert(CW % 32 == 0, "two chunks per iteration");
   uint32_t acc0[16], acc1[16];
   auto chunk = [&](const uint32_t (&acc)[16], int cb) {
     const int nc = nrem - cb;
     if (mvalid && nc > 0)
-      epi_chunk16<ACT, RES>(acc, sb + cb, rbias, alpha, beta, rrow ? rrow + cb : nullptr, yrow + cb, nc >= 16 ? al_row : 0, nc,
-                            do_store);
+      epi_chunk16<ACT, RES, XM>(acc, sb + cb, rbias, alpha, beta, rrow ? rrow + cb : nullptr, yrow + cb, nc >= 16 ? al_row : 0, nc,
+                                do_store, ex, cb);
   };
   tmem_ld16(trow, acc0);
 #pragma unroll 1
@@ -172,7 +172,9 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
       const int ry = a_mode == A_TMA4D ? gt / P.tw : 0;
       const int rx = a_mode == A_TMA4D ? gt - ry * P.tw : 0;
       const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : ((P.epi & ICAF_EPI_ADD_RES) ? 1 : 0);
-      const int mode_act = ICAF_DBG(P, 2) ? mode : P.act * 3 + mode;
+      // 9 / 10: LayerNorm folded into this GEMM (no activation / GELU); 11: scaled residual + statistics of the output rows
+      const int mode_act = ICAF_DBG(P, 2) ? mode
+                           : (P.ln_parts > 0 ? (P.act == ICAF_ACT_GELU ? 10 : 9) : ((P.epi & ICAF_EPI_EMIT_STATS) ? 11 : P.act * 3 + mode));
       const bool dst = !ICAF_DBG(P, 1);
       const bool row_bias = (P.epi & ICAF_EPI_BIAS_ROW) != 0;
       float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256) + eg * 2 * kCW;   // [tile parity][kCW]
@@ -219,17 +221,24 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         const uint32_t trow = tmem_base + uint32_t(buf * BN + half * kCW) + lane_off;
         const uint32_t te = tempty_bar(buf);
         const int nrem = P.N - nb0;
+        EpiRow ex;
+        ex.sum = ex.sumsq = 0.f; ex.ln_a = 1.f; ex.ln_mu = 0.f; ex.ln_s = pr.ln_s ? pr.ln_s + nb0 : nullptr;
+        if (P.ln_parts > 0) epi_row_ln(ex, P, pr, m, mvalid);
         switch (mode_act) {
-          case 0: epi_tile<kCW, 0, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
-          case 1: epi_tile<kCW, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
-          case 2: epi_tile<kCW, 0, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
-          case 3: epi_tile<kCW, 1, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
-          case 4: epi_tile<kCW, 1, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
-          case 5: epi_tile<kCW, 1, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
-          case 6: epi_tile<kCW, 2, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
-          case 7: epi_tile<kCW, 2, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
-          default: epi_tile<kCW, 2, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst); break;
+          case 0: epi_tile<kCW, 0, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 1: epi_tile<kCW, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 2: epi_tile<kCW, 0, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 3: epi_tile<kCW, 1, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 4: epi_tile<kCW, 1, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 5: epi_tile<kCW, 1, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 6: epi_tile<kCW, 2, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 7: epi_tile<kCW, 2, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 8: epi_tile<kCW, 2, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 9: epi_tile<kCW, 0, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          case 10: epi_tile<kCW, 2, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          default: epi_tile<kCW, 0, 2, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
         }
+        if (mode_act == 11 && mvalid && nrem > 0) epi_row_emit(ex, P, pr, m, nb0, min(nb0 + kCW, P.N));
       }
     }
   } else if (warp == kPEpiWarps) {

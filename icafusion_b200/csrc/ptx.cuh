@@ -157,6 +157,26 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t ro
   return d;
 }
 
+// MN-major operand tile (the M / N index is the contiguous one): rows of `row_bytes` (32 / 64 / 128) hold 16 / 32 / 64
+// consecutive M|N elements of ONE k, consecutive k are consecutive rows, 8-row groups are 8*row_bytes apart (SBO); the next
+// block of 64 (32, 16) M|N elements starts `lbo_bytes` further (LBO).  This is the layout a TMA box (cols = M|N, rows = k)
+// with the matching swizzle produces -- CUTLASS' Layout_MN_SW{32,64,128}_Atom.  One MMA (K = 16) spans two 8-row groups:
+// advance the start address by 16 * row_bytes per K step.  Needs the matching "major" bit in the instruction descriptor.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr, uint32_t row_bytes, uint32_t lbo_bytes) {
+  const uint64_t lt = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFF) >> 4);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((8 * row_bytes) >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= lt << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with MN-major A and / or B (bit 15 / bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_major(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             bool accumulate) {

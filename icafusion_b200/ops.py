@@ -13,7 +13,8 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_SILU, EPI_ADD_RES, EPI_BIAS_ROW, EPI_SCALED_RES  # noqa: F401
+from ._lib import (ACT_GELU, ACT_NONE, ACT_SILU, EPI_ADD_RES, EPI_BIAS_ROW, EPI_EMIT_STATS, EPI_LN_FOLD,  # noqa: F401
+                   EPI_SCALED_RES)
 
 
 _PROFILE = None        # when a list: every call appends (name, work dict, start event, end event)
@@ -196,6 +197,8 @@ class PackedConv:
     pad: int
     act: int
     is_weight: bool = True            # False when the "filter" operand is an activation (swap-AB linears)
+    colsum: Optional[torch.Tensor] = None   # LN fold (pack_linear_ln): fp32 [w_rows] row sums of the gamma-folded fp16 filter
+    ln_eps: float = 0.0
 
 
 def pack_conv_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, pad: int, act: int,
@@ -229,15 +232,44 @@ def _addr(t: Optional[torch.Tensor]) -> Optional[int]:
     return 0 if t.device.type == "meta" else t.data_ptr()
 
 
+def pack_linear_ln(weight: torch.Tensor, bias: Optional[torch.Tensor], ln_weight: torch.Tensor, ln_bias: torch.Tensor,
+                   ln_eps: float, act: int = ACT_NONE, device=None) -> PackedConv:
+    """nn.Linear applied to nn.LayerNorm(x) (common.py:660-668, 749-750 + 704), LayerNorm folded into the GEMM:
+    filter W diag(gamma), bias b + W beta, colsum[n] = sum_k fp16(W'[n][k]) -- the kernel normalises in its epilogue
+    (ICAF_EPI_LN_FOLD, include/icaf_b200.h)."""
+    w = weight.detach().float()
+    wf = w * ln_weight.detach().float()[None, :]
+    b = (bias.detach().float() if bias is not None else torch.zeros(w.shape[0], device=w.device)) + w @ ln_bias.detach().float()
+    pk = pack_conv_weight(wf[:, :, None, None], b, 1, 0, act, device)
+    pk.colsum = pk.w.float().sum(1).contiguous()                # of the ROUNDED filter: the identity holds for what the MMA sees
+    pk.ln_eps = float(ln_eps)
+    return pk
+
+
+def row_stats(x0: torch.Tensor, x1: Optional[torch.Tensor] = None):
+    """(sum, sum of squares) per row of (rows, C) fp16 matrices -> fp32 (rows, 1, 2) each (ln_parts = 1)."""
+    rows, Cc = x0.shape
+    assert x0.is_contiguous() and x0.dtype == torch.float16 and (x1 is None or (x1.shape == x0.shape and x1.is_contiguous()))
+    s0 = torch.empty(rows, 1, 2, dtype=torch.float32, device=x0.device)
+    s1 = torch.empty_like(s0) if x1 is not None else None
+    _call("icaf_row_stats", _lib.lib().icaf_row_stats, (_ptr(x0), _ptr(x1), _ptr(s0), _ptr(s1), rows, Cc),
+          {"bytes": 2.0 * x0.numel() * (2 if x1 is not None else 1)})
+    return (s0, s1) if x1 is not None else s0
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(_addr(t) or 0)
 
 
 def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Optional[Sequence[torch.Tensor]] = None,
            res: Optional[Sequence[torch.Tensor]] = None, scaled: Optional[Sequence] = None,
-           bias_row: bool = False, simt: bool = False) -> List[torch.Tensor]:
+           bias_row: bool = False, simt: bool = False, ln_stats: Optional[Sequence[torch.Tensor]] = None,
+           stats_out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
     """Grouped (1 or 2 problems of identical geometry) Conv+bias+act(+residual).
-    `scaled`: per problem (alpha, beta) device fp32 scalars -> y = alpha*res + beta*(acc+bias)."""
+    `scaled`: per problem (alpha, beta) device fp32 scalars -> y = alpha*res + beta*(acc+bias).
+    `ln_stats`: per problem fp32 (M, parts, 2) row statistics of the input -> LayerNorm-folded linear (packs from
+    pack_linear_ln).  `stats_out`: per problem fp32 (M, ceil(Cout/32), 2) receiving the row statistics of the output
+    (with `scaled` only)."""
     n = len(xs)
     assert n in (1, 2) and len(packs) == n
     p0 = packs[0]
@@ -246,7 +278,8 @@ def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Option
         raise ValueError(f"conv2d: input has {Cx} channels, filter expects {p0.cin}")
     Ho = (Hi + 2 * p0.pad - p0.kh) // p0.stride + 1
     Wo = (Wi + 2 * p0.pad - p0.kw) // p0.stride + 1
-    epi = (EPI_BIAS_ROW if bias_row else 0) | (EPI_SCALED_RES if scaled is not None else (EPI_ADD_RES if res is not None else 0))
+    epi = (EPI_BIAS_ROW if bias_row else 0) | (EPI_SCALED_RES if scaled is not None else (EPI_ADD_RES if res is not None else 0)) | \
+        (EPI_LN_FOLD if ln_stats is not None else 0) | (EPI_EMIT_STATS if stats_out is not None else 0)
     g = _lib.ConvGeom(B, Hi, Wi, p0.cin, Ho, Wo, p0.cout, p0.kh, p0.kw, p0.stride, p0.pad, p0.w.shape[1],
                       p0.w.shape[0], p0.act, epi)
     if outs is None:
@@ -271,6 +304,17 @@ def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Option
             ios[i].res, ios[i].res_ld = _addr(res[i]), _check_view(res[i], "conv2d residual")
         if scaled is not None:
             ios[i].alpha, ios[i].beta = _addr(scaled[i][0]), _addr(scaled[i][1])
+        if ln_stats is not None:
+            st = ln_stats[i]
+            if pk.colsum is None or st.dtype != torch.float32 or st.dim() != 3 or st.shape[0] != B * Ho * Wo or st.shape[2] != 2 or \
+                    not st.is_contiguous():
+                raise ValueError("conv2d: ln_stats must be contiguous fp32 (M, parts, 2) and the filter packed by pack_linear_ln")
+            ios[i].ln_stats, ios[i].ln_colsum, ios[i].ln_parts, ios[i].ln_eps = _addr(st), _addr(pk.colsum), st.shape[1], pk.ln_eps
+        if stats_out is not None:
+            so = stats_out[i]
+            if tuple(so.shape) != (B * Ho * Wo, (p0.cout + 31) // 32, 2) or so.dtype != torch.float32 or not so.is_contiguous():
+                raise ValueError(f"conv2d: stats_out must be contiguous fp32 {(B * Ho * Wo, (p0.cout + 31) // 32, 2)}")
+            ios[i].stats_out = _addr(so)
     fn = _lib.lib().icaf_conv2d_fwd_simt if simt else _lib.lib().icaf_conv2d_fwd
     M = B * Ho * Wo
     kk = p0.kh * p0.kw * p0.cin
@@ -283,12 +327,12 @@ def conv2d(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs: Option
 
 
 def linear(xs: Sequence[torch.Tensor], packs: Sequence[PackedConv], outs=None, res=None, scaled=None,
-           bias_row: bool = False, simt: bool = False) -> List[torch.Tensor]:
+           bias_row: bool = False, simt: bool = False, ln_stats=None, stats_out=None) -> List[torch.Tensor]:
     """Rows-as-pixels view of conv2d: xs are (rows, K) fp16 matrices (row pitch = stride(0))."""
     def as4(t):
         return None if t is None else t.unflatten(0, (1, 1, t.shape[0])) if t.dim() == 2 else t
     o = conv2d([as4(x) for x in xs], packs, None if outs is None else [as4(t) for t in outs],
-               None if res is None else [as4(t) for t in res], scaled, bias_row, simt)
+               None if res is None else [as4(t) for t in res], scaled, bias_row, simt, ln_stats, stats_out)
     return [t[0, 0] for t in o]
 
 
@@ -351,18 +395,22 @@ def copy_channels(x: torch.Tensor, out: torch.Tensor) -> None:
                                                               B * H * W, Cc), {"bytes": 4.0 * x.numel()})
 
 
-def dmff_pool_tokens(x_vis, x_ir, pos_vis, pos_ir, mix, nh: int, nw: int):
-    """-> (tok_vis, tok_ir) fp16 (B, Npad, C)."""
+def dmff_pool_tokens(x_vis, x_ir, pos_vis, pos_ir, mix, nh: int, nw: int, with_stats: bool = False):
+    """-> (tok_vis, tok_ir) fp16 (B, Npad, C); with_stats: also (stats_vis, stats_ir) fp32 (B*Npad, C/32, 2) row statistics."""
     B, H, W, Cc = x_vis.shape
     n_pad = round_up(nh * nw, 8)
     tv = torch.empty(B, n_pad, Cc, dtype=torch.float16, device=x_vis.device)
     ti = torch.empty_like(tv)
     ld = _check_view(x_vis, "dmff x_vis")
     assert _check_view(x_ir, "dmff x_ir") == ld
+    sv = si = None
+    if with_stats:
+        sv = torch.empty(B * n_pad, Cc // 32, 2, dtype=torch.float32, device=x_vis.device)
+        si = torch.empty_like(sv)
     _call("icaf_dmff_pool_tokens", _lib.lib().icaf_dmff_pool_tokens,
-          (_ptr(x_vis), _ptr(x_ir), ld, _ptr(pos_vis), _ptr(pos_ir), _ptr(mix), _ptr(tv), _ptr(ti), B, H, W, Cc, nh, nw, n_pad),
-          {"bytes": 4.0 * x_vis.numel() + 4.0 * tv.numel() + 4.0 * pos_vis.numel()})
-    return tv, ti
+          (_ptr(x_vis), _ptr(x_ir), ld, _ptr(pos_vis), _ptr(pos_ir), _ptr(mix), _ptr(tv), _ptr(ti), _ptr(sv), _ptr(si), B, H, W, Cc, nh, nw,
+           n_pad), {"bytes": 4.0 * x_vis.numel() + 4.0 * tv.numel() + 4.0 * pos_vis.numel()})
+    return (tv, ti, sv, si) if with_stats else (tv, ti)
 
 
 def layernorm(x0, g0, b0, x1=None, g1=None, b1=None, eps: float = 1e-5):
@@ -379,11 +427,19 @@ def layernorm(x0, g0, b0, x1=None, g1=None, b1=None, eps: float = 1e-5):
 
 
 def cross_attention(qk_vis, qk_ir, vt_vis, vt_ir, B: int, N: int, n_pad: int, Cc: int, heads: int, simt: bool = False):
+    """Both directions of the DMFF cross-attention.  Fused form: vt_vis = vt_ir = None and qk_* are (B, Npad, 3C) [q|k|v]
+    rows; split form: qk_* (B, Npad, 2C) and vt_* (C, B*Npad)."""
     out_v = torch.empty(B, n_pad, Cc, dtype=torch.float16, device=qk_vis.device)
     out_i = torch.empty_like(out_v)
     fn = _lib.lib().icaf_cross_attention_simt if simt else _lib.lib().icaf_cross_attention
-    for t in (qk_vis, qk_ir, vt_vis, vt_ir):
+    fused = vt_vis is None
+    if fused != (vt_ir is None):
+        raise ValueError("cross_attention: pass both V^T tensors or neither")
+    for t in (qk_vis, qk_ir) + (() if fused else (vt_vis, vt_ir)):
         assert t.is_contiguous() and t.dtype == torch.float16
+    want = (B, n_pad, (3 if fused else 2) * Cc)
+    if tuple(qk_vis.shape) != want or tuple(qk_ir.shape) != want:
+        raise ValueError(f"cross_attention: projection tensors must be {want}, got {tuple(qk_vis.shape)}")
     _call("icaf_cross_attention_simt" if simt else "icaf_cross_attention", fn,
           (_ptr(qk_vis), _ptr(qk_ir), _ptr(vt_vis), _ptr(vt_ir), _ptr(out_v), _ptr(out_i), B, N, n_pad, Cc, heads),
           {"flops": 8.0 * B * N * N * Cc, "bytes": 2.0 * 2 * (3 * B * n_pad * Cc + B * n_pad * Cc)})

@@ -98,6 +98,8 @@ class Detect(nn.Module):
 def check_anchor_order(m: "Detect") -> None:
     """Anchor areas must grow with the stride; flip the levels if the YAML lists them the other way round
     (reference: utils/autoanchor.py:12-20, called from Model.__init__, yolo_test.py:106)."""
+    if m.anchor_grid.device.type == "meta":       # shape-only construction (torch.device("meta")): nothing to compare
+        return
     a = m.anchor_grid.prod(-1).view(-1)
     if (a[-1] - a[0]).sign() != (m.stride[-1] - m.stride[0]).sign():
         m.anchors[:] = m.anchors.flip(0)

@@ -39,6 +39,15 @@ extern "C" {
 #define ICAF_EPI_BIAS_ROW 1   /* bias indexed by output row (swap-AB linears) instead of channel   */
 #define ICAF_EPI_ADD_RES 2    /* y = act(acc+bias) + res          (Bottleneck shortcut, common.py:194) */
 #define ICAF_EPI_SCALED_RES 4 /* y = alpha*res + beta*(acc+bias)  (LearnableCoefficient pairs, common.py:747-750) */
+/* LayerNorm folded into the linear layer that consumes it (common.py:660-668, 749-750 + 704-706): the caller packs
+ * W' = W diag(gamma), bias' = bias + W beta, ln_colsum[n] = sum_k W'[n][k]; the kernel runs the GEMM on the RAW rows and
+ * normalises in the epilogue, y = act( rstd_m * (acc - mean_m * ln_colsum[n]) + bias'[n] ), with (mean, rstd) of input row m
+ * from `ln_stats`: ln_parts (sum, sum of squares) fp32 pairs per row, as an EMIT_STATS producer or icaf_row_stats wrote
+ * them.  1x1 geometry only, no residual, activation none or GELU. */
+#define ICAF_EPI_LN_FOLD 8
+/* With SCALED_RES: also write, per output row, (sum, sum of squares) partials of the fp16-rounded outputs to `stats_out`:
+ * float2 [M][ceil(Cout/32)] (partials of one row sum to the row's totals) -- the ln_stats of the next LN_FOLD layer. */
+#define ICAF_EPI_EMIT_STATS 16
 
 int icaf_version(void);
 const char* icaf_last_error(void);
@@ -75,6 +84,11 @@ typedef struct {
   void* y;           int64_t y_ld;   /* fp16 output view                                   */
   const float* alpha;                /* device scalars for SCALED_RES                      */
   const float* beta;
+  const float* ln_stats;             /* LN_FOLD: fp32 pairs [M][ln_parts] (sum, sum of squares) of the input rows */
+  const float* ln_colsum;            /* LN_FOLD: fp32 [w_rows]                              */
+  int ln_parts;                      /* LN_FOLD: partials per row, 1..64                     */
+  float ln_eps;                      /* LN_FOLD: LayerNorm epsilon                           */
+  float* stats_out;                  /* EMIT_STATS: fp32 pairs [M][ceil(Cout/32)]            */
 } icaf_conv_io;
 
 int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, void* stream);
@@ -137,21 +151,30 @@ int icaf_copy_channels(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64
  * ------------------------------------------------------------------------------------------- */
 /* AdaptivePool2d avg+max (common.py:868-891) + LearnableWeights (:579-587) + flatten/permute + pos_emb (:817-823):
  *   tok[b, n, c] = w[0]*avgpool + w[1]*maxpool + pos[n, c];  rows n in [N, Npad) are zeroed.
- * Two modalities per launch (x0/x1 ...). `mix` = 4 device floats {w1_vis, w2_vis, w1_ir, w2_ir}. */
+ * Two modalities per launch (x0/x1 ...). `mix` = 4 device floats {w1_vis, w2_vis, w1_ir, w2_ir}.
+ * stats_* (both or neither; C % 32 == 0): fp32 pairs [B*Npad][C/32] (sum, sum of squares) of every token row per 32
+ * channels -- the ln_stats (ln_parts = C/32) of the LN_FOLD projection that consumes the tokens. */
 int icaf_dmff_pool_tokens(const void* x_vis, const void* x_ir, int64_t x_ld, const void* pos_vis, const void* pos_ir,
-                          const float* mix, void* tok_vis, void* tok_ir, int B, int H, int W, int C, int nh, int nw,
-                          int n_pad, void* stream);
+                          const float* mix, void* tok_vis, void* tok_ir, float* stats_vis, float* stats_ir, int B, int H,
+                          int W, int C, int nh, int nw, int n_pad, void* stream);
 
 /* nn.LayerNorm over the last dim (eps 1e-5) of `rows` x C fp16 tokens; two independent problems per launch
  * (x1 may be NULL).  gamma/beta are fp32 [C].  Replaces common.py:660,665,749-750. */
 int icaf_layernorm(const void* x0, const void* x1, const float* g0, const float* b0, const float* g1,
                    const float* b1, void* y0, void* y1, int64_t rows, int C, float eps, void* stream);
 
+/* (sum, sum of squares) of every row of a (rows, C) fp16 matrix -> fp32 pairs [rows][1]: the `ln_stats` (ln_parts = 1) of
+ * an LN_FOLD layer whose input no EMIT_STATS epilogue produced (first loop of a DMFF block, stand-alone calls).
+ * Two problems per launch (x1 may be NULL). */
+int icaf_row_stats(const void* x0, const void* x1, float* stats0, float* stats1, int64_t rows, int C, void* stream);
+
 /* Bidirectional cross-attention core (common.py:670-684), flash style: no N x N score matrix in HBM.
  *   out_vis = softmax(q_ir k_vis^T / sqrt(d)) v_vis ;  out_ir = softmax(q_vis k_ir^T / sqrt(d)) v_ir
- * qk_*: fp16 (B, Npad, 2C) rows [q | k] as the fused projection emits them;
- * vt_*: fp16 (C, B*Npad) value projection stored transposed (swap-AB linear);
- * out_*: fp16 (B, Npad, C) heads merged (the layout out_proj consumes). */
+ * Two input forms:
+ *   fused  (vt_vis == vt_ir == NULL): qk_* are fp16 (B, Npad, 3C) rows [q | k | v] exactly as ONE fused projection GEMM
+ *          emits them; the V tiles feed the tensor core as MN-major operands, no transpose anywhere;
+ *   split  : qk_* fp16 (B, Npad, 2C) rows [q | k], vt_* fp16 (C, B*Npad) value projection stored transposed.
+ * out_*: fp16 (B, Npad, C) heads merged (the layout out_proj consumes).  Every tile is staged by TMA. */
 int icaf_cross_attention(const void* qk_vis, const void* qk_ir, const void* vt_vis, const void* vt_ir, void* out_vis,
                          void* out_ir, int B, int N, int n_pad, int C, int heads, void* stream);
 

@@ -197,3 +197,61 @@ def test_linear_epilogues(cuda_device):
     vt = ops.linear([wv.to(cuda_device)], [tok], bias_row=True)[0]
     torch.cuda.synchronize()
     assert err(vt, (F.linear(x.float(), wv.float(), bv)).t()) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LayerNorm folded into the consuming linear layer (ICAF_EPI_LN_FOLD) and row statistics emitted by the producing one
+# (ICAF_EPI_EMIT_STATS): the DMFF loop's LN1/LN2 (common.py:660,665,749-750) without a LayerNorm launch.
+@pytest.mark.parametrize("M,K,N,n_io,act", [(400, 256, 768, 2, 0), (104, 1024, 4096, 2, 2), (6400, 256, 768, 2, 0), (6400, 256, 1024, 2, 2),
+                                            (20480, 512, 1536, 1, 0), (1664, 1024, 3072, 2, 0), (77 * 8, 128, 384, 1, 2)])
+def test_linear_with_folded_layernorm(cuda_device, M, K, N, n_io, act):
+    from icafusion_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    xs, packs, refs = [], [], []
+    for _ in range(n_io):
+        x = (torch.randn(M, K, generator=g) * (0.5 + torch.rand(M, 1, generator=g)) + 0.3 * torch.randn(M, 1, generator=g)).half()
+        w = torch.randn(N, K, generator=g) / K ** 0.5
+        b = torch.randn(N, generator=g) * 0.3
+        gamma, beta = 1 + 0.2 * torch.randn(K, generator=g), 0.2 * torch.randn(K, generator=g)
+        y = F.layer_norm(x.float(), (K,), gamma, beta, 1e-5) @ w.t() + b
+        refs.append(F.gelu(y) if act == 2 else y)
+        xs.append(x.to(cuda_device))
+        packs.append(ops.pack_linear_ln(w, b, gamma, beta, 1e-5, act, device=cuda_device))
+    stats = ops.row_stats(*xs) if n_io == 2 else [ops.row_stats(xs[0])]
+    ys = ops.linear(xs, packs, ln_stats=list(stats))
+    torch.cuda.synchronize()
+    e = max(err(y, r) for y, r in zip(ys, refs))
+    print(f"\n[LN-folded linear M{M} K{K} N{N} x{n_io} act{act}] {e:.2e}")
+    assert e < 1e-3
+
+
+@pytest.mark.parametrize("M,K,N,n_io", [(400, 256, 256, 2), (104, 4096, 1024, 2), (6400, 1024, 256, 2), (20480, 512, 512, 1), (4096, 512, 2048, 2)])
+def test_scaled_residual_emits_row_statistics(cuda_device, M, K, N, n_io):
+    """y = alpha*res + beta*(x W^T + b) with EMIT_STATS: the partials of every row sum to (sum y, sum y^2) of the fp16 output,
+    and feeding them to an LN-folded linear reproduces LayerNorm(y) W2^T."""
+    from icafusion_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    al = torch.tensor([0.8, 1.3], device=cuda_device)
+    xs, rs, packs, packs2, outs_ref = [], [], [], [], []
+    for _ in range(n_io):
+        x = torch.randn(M, K, generator=g).half()
+        r = torch.randn(M, N, generator=g).half()
+        w = torch.randn(N, K, generator=g) / K ** 0.5
+        b = torch.randn(N, generator=g) * 0.3
+        xs.append(x.to(cuda_device)); rs.append(r.to(cuda_device))
+        packs.append(ops.pack_linear(w, b, device=cuda_device))
+        w2 = torch.randn(64, N, generator=g) / N ** 0.5
+        gamma, beta = 1 + 0.2 * torch.randn(N, generator=g), 0.2 * torch.randn(N, generator=g)
+        packs2.append(ops.pack_linear_ln(w2, None, gamma, beta, 1e-5, device=cuda_device))
+        outs_ref.append((0.8 * r.float() + 1.3 * (x.float() @ w.t() + b), w2, gamma, beta))
+    so = [torch.full((M, (N + 31) // 32, 2), float("nan"), device=cuda_device) for _ in range(n_io)]
+    ys = ops.linear(xs, packs, res=rs, scaled=[(al[0:1], al[1:2])] * n_io, stats_out=so)
+    zs = ops.linear(ys, packs2, ln_stats=so)
+    torch.cuda.synchronize()
+    for y, st, z, (ref, w2, gamma, beta) in zip(ys, so, zs, outs_ref):
+        assert err(y, ref) < 1e-3
+        tot = st.sum(1).double().cpu()
+        yf = y.double().cpu()
+        assert torch.allclose(tot[:, 0], yf.sum(1), rtol=1e-4, atol=1e-2) and torch.allclose(tot[:, 1], (yf * yf).sum(1), rtol=1e-4, atol=1e-2)
+        zr = F.layer_norm(y.float().cpu(), (N,), gamma, beta, 1e-5) @ w2.t()
+        assert err(z, zr) < 1e-3
