@@ -164,16 +164,20 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
           for (int i = 0; i < 32; i += 2) {
             const float p0 = fast_exp2_t(fmaf(__uint_as_float(r[i]), sl2, -moff));
             const float p1 = fast_exp2_t(fmaf(__uint_as_float(r[i + 1]), sl2, -moff));
-            rs += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
+            const __half2 h = __floats2half2_rn(p0, p1);
+            const float2 hf = __half22float2(h);            // sum what the PV MMA will actually see
+            rs += hf.x + hf.y;
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float p0 = (kv0 + cb + i < N) ? fast_exp2_t(fmaf(__uint_as_float(r[i]), sl2, -moff)) : 0.f;
             const float p1 = (kv0 + cb + i + 1 < N) ? fast_exp2_t(fmaf(__uint_as_float(r[i + 1]), sl2, -moff)) : 0.f;
-            rs += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
+            const __half2 h = __floats2half2_rn(p0, p1);
+            const float2 hf = __half22float2(h);
+            rs += hf.x + hf.y;
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           }
         }
         // P row -> K-major SW128 smem (block = cb/64, 16-byte chunks (cb%64)/8 ..)

@@ -41,7 +41,9 @@ struct SmemLayout {
   static int total(int stages) { return stages * kStageBytes + kTailBytes; }
 };
 
-template <int BN>
+// XM: the LayerNorm-fold / row-statistics epilogues (DMFF linears) live in their own instantiation so that the epilogue
+// of every other layer keeps its round-1 size (the hot loops are instruction-cache sensitive).
+template <int BN, bool XM>
 __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
 conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
   extern __shared__ uint8_t smem_raw[];
@@ -181,12 +183,15 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
       if (tid + 128 * i < BN) sbias[tid + 128 * i] = bias_r[i];
     named_bar_sync(1, 128);                // bias tile visible to the four epilogue warps
     EpiRow ex;
-    ex.sum = ex.sumsq = 0.f; ex.ln_a = 1.f; ex.ln_mu = 0.f; ex.ln_s = pr.ln_s ? pr.ln_s + n0 : nullptr;
-    if (P.ln_parts > 0) epi_row_ln(ex, P, pr, m, mvalid);     // row statistics: fetched while the main loop still runs
+    ex.sum = ex.sumsq = 0.f; ex.ln_a = 1.f; ex.ln_mu = 0.f; ex.ln_s = nullptr;
+    if (XM) {
+      ex.ln_s = pr.ln_s ? pr.ln_s + n0 : nullptr;
+      if (P.ln_parts > 0) epi_row_ln(ex, P, pr, m, mvalid);   // row statistics: fetched while the main loop still runs
+    }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    // 9 / 10: LayerNorm folded into this GEMM (no activation / GELU); 11: scaled residual + statistics of the output rows
-    const int mode_act = P.ln_parts > 0 ? (P.act == ICAF_ACT_GELU ? 10 : 9) : ((P.epi & ICAF_EPI_EMIT_STATS) ? 11 : P.act * 3 + mode);
+    // XM: 9 / 10 = LayerNorm folded into this GEMM (no activation / GELU); 11 = scaled residual + statistics of the output rows
+    const int mode_act = XM ? (P.ln_parts > 0 ? (P.act == ICAF_ACT_GELU ? 10 : 9) : 11) : P.act * 3 + mode;
     if (splits > 1) {
       // ---- split-K reduction through distributed shared memory ----
       // Every CTA's ring is idle once its accumulator is complete.  Barrier A: all accumulators done (so the leader's
@@ -239,23 +244,28 @@ conv_gemm_tc_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps) {
           const __half* rp = rrow ? rrow + nb : nullptr;
           __half* yp = yrow + nb;
           // act / residual mode are warp-uniform: dispatch once per chunk to straight-line specialisations
-          switch (mode_act) {
-            case 0: epi_chunk<0, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 1: epi_chunk<0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 2: epi_chunk<0, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 3: epi_chunk<1, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 4: epi_chunk<1, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 5: epi_chunk<1, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 6: epi_chunk<2, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 7: epi_chunk<2, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 8: epi_chunk<2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 9: epi_chunk<0, 0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            case 10: epi_chunk<2, 0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
-            default: epi_chunk<0, 2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+          if (XM) {
+            switch (mode_act) {
+              case 9: epi_chunk<0, 0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              case 10: epi_chunk<2, 0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              default: epi_chunk<0, 2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            }
+          } else {
+            switch (mode_act) {
+              case 0: epi_chunk<0, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              case 1: epi_chunk<0, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              case 2: epi_chunk<0, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              case 3: epi_chunk<1, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              case 4: epi_chunk<1, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              case 5: epi_chunk<1, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              case 6: epi_chunk<2, 0>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              case 7: epi_chunk<2, 1>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+              default: epi_chunk<2, 2>(acc, sb, rbias, alpha, beta, rp, yp, vec, ncols, ex, cb); break;
+            }
           }
         }
       }
-      if (mode_act == 11 && mvalid && n0 < P.N) epi_row_emit(ex, P, pr, m, n0, min(n0 + BN, P.N));
+      if (XM && mode_act == 11 && mvalid && n0 < P.N) epi_row_emit(ex, P, pr, m, n0, min(n0 + BN, P.N));
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
@@ -479,10 +489,10 @@ static int plan_tc(ConvParams& P, int n_io, ConvPlan& pl) {
   return ICAF_OK;
 }
 
-template <int BN>
-static int launch_tc(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+template <int BN, bool XM>
+static int launch_tc_x(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
   static bool configured[kMaxDevices] = {false};
-  if (int rc = configure_smem(conv_gemm_tc_kernel<BN>, 227 * 1024, configured, "conv2d: cudaFuncSetAttribute")) return rc;
+  if (int rc = configure_smem(conv_gemm_tc_kernel<BN, XM>, 227 * 1024, configured, "conv2d: cudaFuncSetAttribute")) return rc;
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < n_io; ++i) {
@@ -497,8 +507,12 @@ static int launch_tc(const ConvParams& P, const ConvPlan& pl, const __half* cons
     if (rc) return rc;
   }
   if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
-  launch_kc(conv_gemm_tc_kernel<BN>, dim3(pl.grid_x, pl.grid_y, pl.grid_z), dim3(kThreads), (size_t)pl.smem, st, pl.cluster, P, maps);
+  launch_kc(conv_gemm_tc_kernel<BN, XM>, dim3(pl.grid_x, pl.grid_y, pl.grid_z), dim3(kThreads), (size_t)pl.smem, st, pl.cluster, P, maps);
   return check_launch("conv2d_fwd");
+}
+template <int BN>
+static int launch_tc(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
+  return (P.epi & (ICAF_EPI_LN_FOLD | ICAF_EPI_EMIT_STATS)) ? launch_tc_x<BN, true>(P, pl, w, g, n_io, st) : launch_tc_x<BN, false>(P, pl, w, g, n_io, st);
 }
 
 // ---------------------------------------------------------------------------------------------------

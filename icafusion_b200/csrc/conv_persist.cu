@@ -112,7 +112,7 @@ __device__ __forceinline__ void epi_tile(uint32_t trow, uint32_t tempty, const f
   }
 }
 
-template <int BN>
+template <int BN, bool XM>
 __global__ void __launch_bounds__(kPThreads, 1)
 conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps maps, int total_tiles, int m_tiles, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -172,9 +172,9 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
       const int ry = a_mode == A_TMA4D ? gt / P.tw : 0;
       const int rx = a_mode == A_TMA4D ? gt - ry * P.tw : 0;
       const int mode = (P.epi & ICAF_EPI_SCALED_RES) ? 2 : ((P.epi & ICAF_EPI_ADD_RES) ? 1 : 0);
-      // 9 / 10: LayerNorm folded into this GEMM (no activation / GELU); 11: scaled residual + statistics of the output rows
-      const int mode_act = ICAF_DBG(P, 2) ? mode
-                           : (P.ln_parts > 0 ? (P.act == ICAF_ACT_GELU ? 10 : 9) : ((P.epi & ICAF_EPI_EMIT_STATS) ? 11 : P.act * 3 + mode));
+      // XM instantiation (DMFF linears): 9 / 10 = LayerNorm folded into this GEMM (no activation / GELU); 11 = scaled
+      // residual + statistics of the output rows
+      const int mode_act = XM ? (P.ln_parts > 0 ? (P.act == ICAF_ACT_GELU ? 10 : 9) : 11) : (ICAF_DBG(P, 2) ? mode : P.act * 3 + mode);
       const bool dst = !ICAF_DBG(P, 1);
       const bool row_bias = (P.epi & ICAF_EPI_BIAS_ROW) != 0;
       float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 256) + eg * 2 * kCW;   // [tile parity][kCW]
@@ -222,23 +222,29 @@ conv_gemm_persist_kernel(const ConvParams P, const __grid_constant__ ConvMaps ma
         const uint32_t te = tempty_bar(buf);
         const int nrem = P.N - nb0;
         EpiRow ex;
-        ex.sum = ex.sumsq = 0.f; ex.ln_a = 1.f; ex.ln_mu = 0.f; ex.ln_s = pr.ln_s ? pr.ln_s + nb0 : nullptr;
-        if (P.ln_parts > 0) epi_row_ln(ex, P, pr, m, mvalid);
-        switch (mode_act) {
-          case 0: epi_tile<kCW, 0, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 1: epi_tile<kCW, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 2: epi_tile<kCW, 0, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 3: epi_tile<kCW, 1, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 4: epi_tile<kCW, 1, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 5: epi_tile<kCW, 1, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 6: epi_tile<kCW, 2, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 7: epi_tile<kCW, 2, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 8: epi_tile<kCW, 2, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 9: epi_tile<kCW, 0, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          case 10: epi_tile<kCW, 2, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
-          default: epi_tile<kCW, 0, 2, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+        ex.sum = ex.sumsq = 0.f; ex.ln_a = 1.f; ex.ln_mu = 0.f; ex.ln_s = nullptr;
+        if (XM) {
+          ex.ln_s = pr.ln_s ? pr.ln_s + nb0 : nullptr;
+          if (P.ln_parts > 0) epi_row_ln(ex, P, pr, m, mvalid);
+          switch (mode_act) {
+            case 9: epi_tile<kCW, 0, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            case 10: epi_tile<kCW, 2, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            default: epi_tile<kCW, 0, 2, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          }
+          if (mode_act == 11 && mvalid && nrem > 0) epi_row_emit(ex, P, pr, m, nb0, min(nb0 + kCW, P.N));
+        } else {
+          switch (mode_act) {
+            case 0: epi_tile<kCW, 0, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            case 1: epi_tile<kCW, 0, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            case 2: epi_tile<kCW, 0, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            case 3: epi_tile<kCW, 1, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            case 4: epi_tile<kCW, 1, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            case 5: epi_tile<kCW, 1, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            case 6: epi_tile<kCW, 2, 0>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            case 7: epi_tile<kCW, 2, 1>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+            default: epi_tile<kCW, 2, 2>(trow, te, sb, rbias, alpha, beta, rrow, yrow, al_row, mvalid, nrem, dst, ex); break;
+          }
         }
-        if (mode_act == 11 && mvalid && nrem > 0) epi_row_emit(ex, P, pr, m, nb0, min(nb0 + kCW, P.N));
       }
     }
   } else if (warp == kPEpiWarps) {
@@ -366,8 +372,11 @@ int plan_persist(ConvParams& P, int n_io, ConvPlan& pl) {
 
 template <int BN>
 int launch_persist(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st) {
-  static bool configured[kMaxDevices] = {false};
-  if (int rc = configure_smem(conv_gemm_persist_kernel<BN>, 227 * 1024, configured, "conv2d: cudaFuncSetAttribute (persistent)")) return rc;
+  const bool xm = (P.epi & (ICAF_EPI_LN_FOLD | ICAF_EPI_EMIT_STATS)) != 0;
+  static bool configured[2][kMaxDevices] = {{false}, {false}};
+  if (int rc = xm ? configure_smem(conv_gemm_persist_kernel<BN, true>, 227 * 1024, configured[1], "conv2d: cudaFuncSetAttribute (persistent)")
+                  : configure_smem(conv_gemm_persist_kernel<BN, false>, 227 * 1024, configured[0], "conv2d: cudaFuncSetAttribute (persistent)"))
+    return rc;
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < n_io; ++i) {
@@ -382,7 +391,8 @@ int launch_persist(const ConvParams& P, const ConvPlan& pl, const __half* const 
     if (rc) return rc;
   }
   if (n_io == 1) { maps.w[1] = maps.w[0]; maps.a[1] = maps.a[0]; }
-  launch_k(conv_gemm_persist_kernel<BN>, dim3(pl.grid_x), dim3(kPThreads), (size_t)pl.smem, st, P, maps, pl.total, pl.m_tiles, pl.n_tiles);
+  if (xm) launch_k(conv_gemm_persist_kernel<BN, true>, dim3(pl.grid_x), dim3(kPThreads), (size_t)pl.smem, st, P, maps, pl.total, pl.m_tiles, pl.n_tiles);
+  else launch_k(conv_gemm_persist_kernel<BN, false>, dim3(pl.grid_x), dim3(kPThreads), (size_t)pl.smem, st, P, maps, pl.total, pl.m_tiles, pl.n_tiles);
   return check_launch("conv2d_fwd(persistent)");
 }
 
