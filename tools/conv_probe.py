@@ -30,6 +30,13 @@ GEOMS = [
     ("3x3_N128_K1152_x1", 16, 64, 80, 128, 128, 3, 1, 1, 1, False),
     ("3x3s2_N256_K1152", 16, 128, 160, 128, 256, 3, 2, 1, 2, False),
     ("3x3s2_N128_K576", 16, 256, 320, 64, 128, 3, 2, 1, 2, False),
+    ("1x1_N128_K128_P3", 16, 64, 80, 128, 128, 1, 1, 0, 2, False),
+    ("1x1_N256_K256_P4", 16, 32, 40, 256, 256, 1, 1, 0, 2, False),
+    ("1x1_N512_K512_P5", 16, 16, 20, 512, 512, 1, 1, 0, 2, False),
+    ("1x1_N256_K256_P3cv3", 16, 64, 80, 256, 256, 1, 1, 0, 2, False),
+    ("1x1_N512_K512_P4cv3", 16, 32, 40, 512, 512, 1, 1, 0, 2, False),
+    ("1x1_N1024_K1024_P5cv3", 16, 16, 20, 1024, 1024, 1, 1, 0, 2, False),
+    ("3x3_N512_K4608_x1", 16, 16, 20, 512, 512, 3, 1, 1, 1, False),
 ]
 DBG = [0, 1, 2, 3, 8, 16, 24, 32, 35]
 
