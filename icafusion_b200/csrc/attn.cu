@@ -18,7 +18,6 @@
 namespace icaf {
 
 constexpr int kQT = 128;    // queries per CTA (UMMA M)
-constexpr int kKV = 128;    // keys per tile   (UMMA N of S, K of PV)
 
 struct AttnParams {
   const __half* qk[2];   // [0]=vis, [1]=ir
@@ -41,28 +40,38 @@ struct AttnParams {
 //   V tiles    : (VF, fused [q|k|v] rows) boxes like K's at column 2C + head*D -> rows = keys, i.e. an MN-major B operand
 // Rows / keys past the tensor are zero-filled by the TMA unit; keys in [N, ...) are masked in the softmax.
 struct AttnMaps {
-  CUtensorMap qk[2];   // [0] = vis, [1] = ir : (B*Npad rows, 2C cols), box (min(D,64), 128)
-  CUtensorMap vt[2];   // (C rows, B*Npad cols), box (64, D)
+  CUtensorMap qk[2];   // [0] = vis, [1] = ir : (B*Npad rows, 2C | 3C cols), box (min(D,64), 128) -- Q tiles
+  CUtensorMap kv[2];   // same matrices, box (min(D,64), KV) -- K tiles (and V tiles in the fused form)
+  CUtensorMap vt[2];   // split form: (C rows, B*Npad cols), box (64, D)
 };
 
+// KV = keys per tile (UMMA N of S, K of PV).  Head dims 16 / 32 run 64-key tiles: S + O then fit 128 TMEM columns and the
+// small tiles let 4 / 3 CTAs share an SM -- these head dims are exp-bound, and with one or two CTAs per SM every TMEM load,
+// MUFU and barrier latency of the single softmax warp per sub-partition is exposed (probe: profiles/r02_attn_probe_*).
 template <int D>
+struct AttnCfg {
+  static constexpr int kKV = D <= 32 ? 64 : 128;
+  static constexpr int kCtas = D == 16 ? 4 : (D == 32 ? 3 : (D == 64 ? 2 : 1));
+};
+
+template <int D, int KV>
 struct AttnSmemT {
   static constexpr int kKB = (D + 63) / 64;                 // 64-wide column blocks of the head dim
   static constexpr int kRowB = D >= 64 ? 128 : D * 2;       // bytes per staged Q / K row (= swizzle span)
   static constexpr int kQBytes = kKB * kQT * kRowB;
-  static constexpr int kKBytes = kKB * kKV * kRowB;         // per buffer
-  static constexpr int kVBytes = 2 * D * 128;               // per buffer: two 64-key blocks of D rows
-  static constexpr int kPBytes = 2 * kQT * 128;
+  static constexpr int kKBytes = kKB * KV * kRowB;          // per buffer
+  static constexpr int kVBytes = (KV / 64) * D * 128;       // per buffer: 64-key blocks of D rows (= KV rows of D halfs)
+  static constexpr int kPBytes = (KV / 64) * kQT * 128;
   static constexpr int kQOff = 0;
   static constexpr int kKOff = kQOff + kQBytes;
   static constexpr int kVOff = kKOff + 2 * kKBytes;
   static constexpr int kPOff = kVOff + 2 * kVBytes;
   static constexpr int kBarOff = kPOff + kPBytes;
-  static constexpr int kCtas = D <= 64 ? 2 : 1;             // CTAs per SM
+  static constexpr int kCtas = AttnCfg<D>::kCtas;           // CTAs per SM
   // two CTAs of the D = 64 variant fill the SM to the byte: no alignment slack (the kernel checks its base is 1024-aligned)
   static constexpr bool kSlack = (kBarOff + 128 + 1024) * kCtas + kCtas * 1024 <= 228 * 1024;
   static constexpr int kTotal = kBarOff + 128 + (kSlack ? 1024 : 0);
-  static constexpr int kTmemCols = 256;                     // S (128) + O (D <= 128)
+  static constexpr int kTmemCols = KV + D <= 128 ? 128 : 256;   // S (KV) + O (D)
   static_assert(kQBytes % 1024 == 0 && kKBytes % 1024 == 0 && kVBytes % 1024 == 0, "tiles must keep 1024-byte alignment");
 };
 
@@ -73,8 +82,9 @@ __device__ __forceinline__ float fast_exp2_t(float x) {
 }
 
 template <int D, bool VF>
-__global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(const AttnParams P, const __grid_constant__ AttnMaps M) {
-  using L = AttnSmemT<D>;
+__global__ void __launch_bounds__(192, AttnCfg<D>::kCtas) cross_attn_tma_kernel(const AttnParams P, const __grid_constant__ AttnMaps M) {
+  constexpr int kKV = AttnCfg<D>::kKV;
+  using L = AttnSmemT<D, kKV>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = L::kSlack ? ((smem_u32(smem_raw) + 1023u) & ~1023u) : smem_u32(smem_raw);
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -104,7 +114,8 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
   }
   if (warp == 4) tmem_alloc<L::kTmemCols>(tmem_slot);
   if (warp == 5 && lane_id() == 0) {
-    tma_prefetch_desc(&M.qk[0]); tma_prefetch_desc(&M.qk[1]);
+    tma_prefetch_desc(dir == 0 ? &M.qk[1] : &M.qk[0]);
+    tma_prefetch_desc(dir == 0 ? &M.kv[0] : &M.kv[1]);
     if (!VF) tma_prefetch_desc(dir == 0 ? &M.vt[0] : &M.vt[1]);
   }
   tc_fence_before();
@@ -267,7 +278,7 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
   } else if (lane_id() == 0) {
     // ------------------------------------------------------------------ TMA producer (one thread)
     const CUtensorMap* mq = dir == 0 ? &M.qk[1] : &M.qk[0];
-    const CUtensorMap* mk = dir == 0 ? &M.qk[0] : &M.qk[1];
+    const CUtensorMap* mk = dir == 0 ? &M.kv[0] : &M.kv[1];
     const CUtensorMap* mv = dir == 0 ? &M.vt[0] : &M.vt[1];
     (void)mv;
     const int row_b = b * n_pad;
@@ -287,8 +298,9 @@ __global__ void __launch_bounds__(192, (D <= 64 ? 2 : 1)) cross_attn_tma_kernel(
         for (int kb = 0; kb < L::kKB; ++kb)
           tma_load_2d(sbase + L::kVOff + buf * L::kVBytes + kb * (kKV * 128), mk, kv_full(buf), 2 * C + head * D + kb * 64, row_b + j * kKV);
       } else {
-        tma_load_2d(sbase + L::kVOff + buf * L::kVBytes, mv, kv_full(buf), row_b + j * kKV, head * D);
-        tma_load_2d(sbase + L::kVOff + buf * L::kVBytes + D * 128, mv, kv_full(buf), row_b + j * kKV + 64, head * D);
+#pragma unroll
+        for (int kb = 0; kb < kKV / 64; ++kb)
+          tma_load_2d(sbase + L::kVOff + buf * L::kVBytes + kb * (D * 128), mv, kv_full(buf), row_b + j * kKV + kb * 64, head * D);
       }
     }
   }
@@ -364,7 +376,8 @@ static int fill_attn(const void* qk_vis, const void* qk_ir, const void* vt_vis, 
 
 template <int D, bool VF>
 static int launch_attn_tma(const AttnParams& P, cudaStream_t st) {
-  using L = AttnSmemT<D>;
+  constexpr int kKV = AttnCfg<D>::kKV;
+  using L = AttnSmemT<D, kKV>;
   static bool configured[kMaxDevices] = {false};
   if (int rc = configure_smem(cross_attn_tma_kernel<D, VF>, L::kTotal, configured, "cross_attention: cudaFuncSetAttribute")) return rc;
   AttnMaps maps;
@@ -372,6 +385,8 @@ static int launch_attn_tma(const AttnParams& P, cudaStream_t st) {
   const uint64_t rows = uint64_t(P.B) * P.n_pad;
   for (int i = 0; i < 2; ++i) {
     int rc = encode_tmap_2d(&maps.qk[i], P.qk[i], uint64_t(P.ld), rows, uint64_t(P.ld) * 2, D < 64 ? D : 64, kQT);
+    if (rc) return rc;
+    rc = encode_tmap_2d(&maps.kv[i], P.qk[i], uint64_t(P.ld), rows, uint64_t(P.ld) * 2, D < 64 ? D : 64, kKV);
     if (rc) return rc;
     if (!VF) {
       rc = encode_tmap_2d(&maps.vt[i], P.vt[i], rows, uint64_t(P.C), rows * 2, 64, D);
