@@ -35,6 +35,11 @@ class ConvPlan(C.Structure):
                                        "work_items")]
 
 
+class LossHyp(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("box", "obj", "cls", "cls_pw", "obj_pw", "anchor_t", "fl_gamma", "gr", "cp", "cn")] + \
+               [("balance", C.c_float * 5)]
+
+
 KERNEL_TC, KERNEL_PERSIST, KERNEL_PAIR = 0, 1, 2
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -49,6 +54,7 @@ SIGNATURES = {
     "icaf_conv2d_fwd_simt": [C.POINTER(ConvGeom), C.POINTER(ConvIO), _i, _vp],
     "icaf_pack_image": [_vp, _i, _f, _i, _i, _i, _vp, _vp],
     "icaf_pack_image_s2d": [_vp, _i, _f, _i, _i, _i, _vp, _vp],
+    "icaf_letterbox": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "icaf_sppf_pool": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "icaf_upsample2x": [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp],
     "icaf_copy_channels": [_vp, _i64, _vp, _i64, _i64, _i, _vp],
@@ -61,6 +67,9 @@ SIGNATURES = {
     "icaf_dmff_upsample_cat": [_vp, _vp, _i, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp],
     "icaf_nms_workspace_bytes": [_i, _i],
     "icaf_nms": [_vp, _i, _i, _i, _f, _f, _i, C.c_uint64, _i, _vp, _vp, _vp, C.c_size_t, _vp],
+    "icaf_loss_workspace_bytes": [_i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i],
+    "icaf_compute_loss_fwd": [C.POINTER(C.c_void_p), _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _i, _i, _i, _vp, _i,
+                              C.POINTER(C.c_float), C.POINTER(LossHyp), _vp, _vp, C.c_size_t, _vp],
     "icaf_axpby": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "icaf_detect_decode": [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.POINTER(C.c_float), _vp],
 }
@@ -84,7 +93,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)            # AttributeError here = header/.so drift
             fn.argtypes = argtypes
             fn.restype = {"icaf_last_error": C.c_char_p, "icaf_kernel_launches": C.c_longlong,
-                          "icaf_nms_workspace_bytes": C.c_size_t}.get(name, C.c_int)
+                          "icaf_nms_workspace_bytes": C.c_size_t, "icaf_loss_workspace_bytes": C.c_size_t}.get(name, C.c_int)
         _lib = L
     return _lib
 

@@ -404,6 +404,49 @@ __global__ void detect_decode_kernel(const DetectParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Letterbox (utils/datasets.py:1404-1427) + BGR->RGB + HWC->CHW (datasets.py:238) for a batch of frames:
+// cv2.resize(INTER_LINEAR) on uint8 is fixed-point -- horizontal taps a0, a1 (x 2048, from the host-built tables), vertical
+// dst = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2 -- reproduced bit for bit; the border is `pad`.
+struct LetterboxParams {
+  const unsigned char* src; unsigned char* dst;
+  const int* xtab; const int* ytab;     // [new_w][4] = {x0, x1, a0, a1}, [new_h][4] = {y0, y1, b0, b1}; NULL = no resize
+  int B, H0, W0, H, W, top, left, new_h, new_w, pad;
+};
+__global__ void letterbox_kernel(const LetterboxParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long hw = (long long)P.H * P.W;
+  if (i >= (long long)P.B * hw) return;
+  const int b = int(i / hw);
+  const long long r = i - b * hw;
+  const int y = int(r / P.W), x = int(r - (long long)y * P.W);
+  const int yy = y - P.top, xx = x - P.left;
+  int v0 = P.pad, v1 = P.pad, v2 = P.pad;               // B, G, R of the source order
+  if (yy >= 0 && yy < P.new_h && xx >= 0 && xx < P.new_w) {
+    const unsigned char* S = P.src + (long long)b * P.H0 * P.W0 * 3;
+    if (!P.xtab) {
+      const unsigned char* s = S + ((long long)yy * P.W0 + xx) * 3;
+      v0 = s[0]; v1 = s[1]; v2 = s[2];
+    } else {
+      const int4 tx = reinterpret_cast<const int4*>(P.xtab)[xx], ty = reinterpret_cast<const int4*>(P.ytab)[yy];
+      const unsigned char* r0 = S + (long long)ty.x * P.W0 * 3;
+      const unsigned char* r1 = S + (long long)ty.y * P.W0 * 3;
+      int out[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int h0 = r0[tx.x * 3 + c] * tx.z + r0[tx.y * 3 + c] * tx.w;
+        const int h1 = r1[tx.x * 3 + c] * tx.z + r1[tx.y * 3 + c] * tx.w;
+        out[c] = (((ty.z * (h0 >> 4)) >> 16) + ((ty.w * (h1 >> 4)) >> 16) + 2) >> 2;
+      }
+      v0 = out[0]; v1 = out[1]; v2 = out[2];
+    }
+  }
+  unsigned char* d = P.dst + (long long)b * 3 * hw + r;  // planar RGB: channel 0 = R = source channel 2
+  d[0] = (unsigned char)v2; d[hw] = (unsigned char)v1; d[2 * hw] = (unsigned char)v0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // (sum, sum of squares) per row of a (rows, C) fp16 matrix: one warp per row, 16-byte loads.
 __global__ void row_stats_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1, float2* __restrict__ s0,
                                  float2* __restrict__ s1, long long rows, int C) {
@@ -760,4 +803,19 @@ extern "C" int icaf_row_stats(const void* x0, const void* x1, float* stats0, flo
   launch_k(row_stats_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const __half*)x0, (const __half*)x1, (float2*)stats0,
            (float2*)stats1, (long long)rows, C);
   return check_launch("row_stats");
+}
+
+extern "C" int icaf_letterbox(const void* src, int B, int H0, int W0, void* dst, int H, int W, int top, int left, int new_h, int new_w,
+                              const int* xtab, const int* ytab, int pad_value, void* stream) {
+  if (!src || !dst || B < 1 || H0 < 1 || W0 < 1 || H < 1 || W < 1 || new_h < 1 || new_w < 1 || top < 0 || left < 0 || top + new_h > H ||
+      left + new_w > W || pad_value < 0 || pad_value > 255)
+    return set_error(ICAF_ERR_BAD_ARG, "letterbox: bad shape");
+  const bool resize = new_h != H0 || new_w != W0;
+  if (resize && (!xtab || !ytab || (reinterpret_cast<uintptr_t>(xtab) & 15) || (reinterpret_cast<uintptr_t>(ytab) & 15)))
+    return set_error(ICAF_ERR_BAD_ARG, "letterbox: resizing needs the 16-byte aligned tap tables");
+  LetterboxParams P;
+  P.src = (const unsigned char*)src; P.dst = (unsigned char*)dst; P.xtab = resize ? xtab : nullptr; P.ytab = resize ? ytab : nullptr;
+  P.B = B; P.H0 = H0; P.W0 = W0; P.H = H; P.W = W; P.top = top; P.left = left; P.new_h = new_h; P.new_w = new_w; P.pad = pad_value;
+  launch_k(letterbox_kernel, dim3(blocks_for((long long)B * H * W, 256)), dim3(256), 0, (cudaStream_t)stream, P);
+  return check_launch("letterbox");
 }

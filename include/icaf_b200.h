@@ -126,6 +126,15 @@ int icaf_conv2d_fwd_simt(const icaf_conv_geom* g, const icaf_conv_io* io, int n_
  * ------------------------------------------------------------------------------------------- */
 int icaf_pack_image(const void* src, int src_dtype, float scale, int B, int H, int W, void* dst, void* stream);
 
+/* Letterbox + BGR->RGB + HWC->CHW for a batch of decoded frames, on the device.  Replaces utils/datasets.py:1404-1427
+ * letterbox (cv2.resize INTER_LINEAR + cv2.copyMakeBorder) and the `img[:, :, ::-1].transpose(2, 0, 1)` of datasets.py:238.
+ * src: uint8 (B, H0, W0, 3) BGR; dst: uint8 (B, 3, H, W) RGB planar; the resized (new_h, new_w) frame sits at (top, left),
+ * the rest is pad_value (114).  xtab / ytab: device int32 [new_w][4] = {x0, x1, a0, a1} and [new_h][4] = {y0, y1, b0, b1},
+ * cv2's fixed-point bilinear taps (x 2048) -- built on the host (icafusion_b200/datasets.py:resize_taps); may be NULL when
+ * (new_h, new_w) == (H0, W0).  Bit-exact against the cv2 pipeline. */
+int icaf_letterbox(const void* src, int B, int H0, int W0, void* dst, int H, int W, int top, int left, int new_h, int new_w,
+                   const int* xtab, const int* ytab, int pad_value, void* stream);
+
 /* Same staging, space-to-depth layout: dst is (B, H/2, W/2, 16) fp16 with channel (dy*2+dx)*4 + c (c = r,g,b,0).
  * A 6x6 / stride 2 / pad 2 stem convolution over the image (yolov5 "P1/2" row of the model YAML) is then exactly a
  * 3x3 / stride 1 / pad 1 convolution over this tensor (ky = 2*ty+dy, kx = 2*tx+dx), which runs on the TMA path. H, W even. */
@@ -208,6 +217,29 @@ int icaf_detect_decode(const void* p, int64_t p_ld, void* x_out, void* z, void* 
 size_t icaf_nms_workspace_bytes(int B, int R);
 int icaf_nms(const void* z, int B, int R, int no, float conf_thres, float iou_thres, int agnostic, uint64_t class_mask,
              int max_det, float* det, int* count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Detection loss, forward only (the validation loss test.py:132-133 accumulates; the training backward is not built):
+ * utils/loss.py:325-463 ComputeLoss.__call__ + build_targets -- anchor-ratio matching with the four half-cell neighbour
+ * offsets, CIoU box loss, objectness BCE against IoU-valued targets (largest IoU wins a contested cell), class BCE.
+ * p: nl device pointers to the Detect training outputs (B, na, ny[i], nx[i], no), fp16 (p_fp32 = 0) or fp32 (1); arithmetic
+ * in fp32.  targets: device fp32 (nt, 6) rows [image, class, x, y, w, h] normalised to [0, 1].  anchors_host: nl*na*2 floats
+ * in grid units (Detect.anchors).  out: 5 device floats [loss * batch, lbox, lobj, lcls, 0].  fl_gamma must be 0.
+ * Deterministic: no floating-point atomics.  workspace: icaf_loss_workspace_bytes(...) bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  float box, obj, cls;   /* loss gains hyp['box'], hyp['obj'], hyp['cls'] (already scaled as train.py:226-228 does) */
+  float cls_pw, obj_pw;  /* BCE positive weights                                                                   */
+  float anchor_t;        /* anchor-multiple threshold                                                              */
+  float fl_gamma;        /* focal-loss gamma; only 0 is supported                                                  */
+  float gr;              /* model.gr: objectness target = (1 - gr) + gr * iou                                      */
+  float cp, cn;          /* smoothed positive / negative class targets (smooth_BCE, loss.py:15-17)                 */
+  float balance[5];      /* per-level objectness weights: {4, 1, 0.4} for three levels (loss.py:346)               */
+} icaf_loss_hyp;
+size_t icaf_loss_workspace_bytes(int B, int na, int nt, const int* ny, const int* nx, int nl);
+int icaf_compute_loss_fwd(const void* const* p, int p_fp32, const int* ny, const int* nx, int nl, int B, int na, int no,
+                          const float* targets, int nt, const float* anchors_host, const icaf_loss_hyp* hyp, float* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* out = a[0] * x (+ b[0] * y when y != NULL) over n fp16 elements (n % 8 == 0, 16-byte aligned); a, b device fp32 scalars.
  * LearnableCoefficient.forward / LearnableWeights.forward called stand-alone (models/common.py:569-587). */

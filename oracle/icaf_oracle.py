@@ -295,6 +295,89 @@ def fold_bn(sd: SD, bn_eps=BN_EPS_MODEL) -> SD:
 
 
 # ----------------------------------------------------------------------------------------
+# detection loss (utils/loss.py), forward
+# ----------------------------------------------------------------------------------------
+def ciou_xywh(box1, box2, eps=1e-7):
+    """bbox_iou(box1, box2, x1y1x2y2=False, CIoU=True), utils/general.py:410-447.  box1: (4, n), box2: (n, 4), xywh."""
+    b2 = box2.T
+    x1a, x1b = box1[0] - box1[2] / 2, box1[0] + box1[2] / 2
+    y1a, y1b = box1[1] - box1[3] / 2, box1[1] + box1[3] / 2
+    x2a, x2b = b2[0] - b2[2] / 2, b2[0] + b2[2] / 2
+    y2a, y2b = b2[1] - b2[3] / 2, b2[1] + b2[3] / 2
+    inter = (torch.min(x1b, x2b) - torch.max(x1a, x2a)).clamp(0) * (torch.min(y1b, y2b) - torch.max(y1a, y2a)).clamp(0)
+    w1, h1 = x1b - x1a, y1b - y1a + eps
+    w2, h2 = x2b - x2a, y2b - y2a + eps
+    union = w1 * h1 + w2 * h2 - inter + eps
+    iou = inter / union
+    cw = torch.max(x1b, x2b) - torch.min(x1a, x2a)
+    ch = torch.max(y1b, y2b) - torch.min(y1a, y2a)
+    c2 = cw ** 2 + ch ** 2 + eps
+    rho2 = ((x2a + x2b - x1a - x1b) ** 2 + (y2a + y2b - y1a - y1b) ** 2) / 4
+    v = (4 / math.pi ** 2) * torch.pow(torch.atan(w2 / h2) - torch.atan(w1 / h1), 2)
+    alpha = v / (v - iou + (1 + eps))
+    return iou - (rho2 / c2 + v * alpha)
+
+
+def compute_loss(p, targets, anchors, hyp: dict, gr: float = 1.0):
+    """ComputeLoss.__call__ + build_targets, utils/loss.py:356-463 (fl_gamma = 0, autobalance off, ranking loss disabled as
+    upstream).  p: list of (B, na, ny, nx, no) fp32; targets (nt, 6) [image, class, x, y, w, h]; anchors (nl, na, 2) in grid
+    units.  Candidates are enumerated target-major per (level, anchor, offset) like the device kernel; the reference's
+    order only matters for its IoU-sorted scatter, restated here as a max per cell."""
+    nl, na = anchors.shape[0], anchors.shape[1]
+    nc = p[0].shape[-1] - 5
+    balance = {3: [4.0, 1.0, 0.4]}.get(nl, [4.0, 1.0, 0.25, 0.06, 0.02])
+    eps_s = hyp.get("label_smoothing", 0.0)
+    cp, cn = 1.0 - 0.5 * eps_s, 0.5 * eps_s
+    bce = lambda x, y, pw: F.binary_cross_entropy_with_logits(x, y, pos_weight=torch.tensor([pw]))   # noqa: E731
+    lbox = lobj = lcls = torch.zeros(())
+    off = torch.tensor([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1]]).float() * 0.5
+    nt = targets.shape[0]
+    for i, pi in enumerate(p):
+        B, _, ny, nx, no = pi.shape
+        tobj = torch.zeros_like(pi[..., 0])
+        rows = []
+        if nt:
+            gain = torch.tensor([1, 1, nx, ny, nx, ny]).float()
+            t = targets * gain
+            for a in range(na):
+                r = t[:, 4:6] / anchors[i, a][None]
+                keep = torch.max(r, 1.0 / r).max(1)[0] < hyp["anchor_t"]                          # :429-430
+                ta = t[keep]
+                gxy = ta[:, 2:4]
+                gxi = torch.tensor([nx, ny]).float() - gxy
+                jk = (gxy % 1.0 < 0.5) & (gxy > 1.0)
+                lm = (gxi % 1.0 < 0.5) & (gxi > 1.0)
+                sel = torch.stack((torch.ones_like(jk[:, 0]), jk[:, 0], jk[:, 1], lm[:, 0], lm[:, 1]))  # (5, n)   :434-440
+                for k in range(5):
+                    tk = ta[sel[k]]
+                    if tk.shape[0]:
+                        rows.append(torch.cat((tk, torch.full((tk.shape[0], 1), float(a)), off[k].expand(tk.shape[0], 2)), 1))
+        if rows:
+            t = torch.cat(rows, 0)
+            b, c, a = t[:, 0].long(), t[:, 1].long(), t[:, 6].long()
+            gxy, gwh, offs = t[:, 2:4], t[:, 4:6], t[:, 7:9]
+            gij = (gxy - offs).long()
+            gi, gj = gij[:, 0].clamp(0, nx - 1), gij[:, 1].clamp(0, ny - 1)                         # :455 (clamp_ in place)
+            tbox = torch.cat((gxy - torch.stack((gi, gj), 1), gwh), 1)
+            ps = pi[b, a, gj, gi]
+            pxy = ps[:, :2].sigmoid() * 2.0 - 0.5
+            pwh = (ps[:, 2:4].sigmoid() * 2) ** 2 * anchors[i][a]
+            iou = ciou_xywh(torch.cat((pxy, pwh), 1).T, tbox)
+            lbox = lbox + (1.0 - iou).mean()
+            score = (1.0 - gr) + gr * iou.detach().clamp(0)
+            order = torch.argsort(score)                                                           # :374-377: largest IoU written last
+            tobj[b[order], a[order], gj[order], gi[order]] = score[order]
+            if nc > 1:
+                tc = torch.full_like(ps[:, 5:], cn)
+                tc[torch.arange(t.shape[0]), c] = cp
+                lcls = lcls + bce(ps[:, 5:], tc, hyp["cls_pw"])
+        lobj = lobj + bce(pi[..., 4], tobj, hyp["obj_pw"]) * balance[i]
+    lbox, lobj, lcls = lbox * hyp["box"], lobj * hyp["obj"], lcls * hyp["cls"]
+    bs = p[0].shape[0]
+    return (lbox + lobj + lcls) * bs, torch.stack((lbox, lobj, lcls, torch.zeros(())))
+
+
+# ----------------------------------------------------------------------------------------
 # post-processing (utils/general.py)
 # ----------------------------------------------------------------------------------------
 def greedy_nms(boxes, scores, iou_thres: float):

@@ -111,3 +111,23 @@ def test_stem_space_to_depth_repack_is_the_same_convolution():
     # the packed filter is fp16: compare against the fp16-rounded 6x6 filter
     ref16 = F.conv2d(img, w.half().float(), b, stride=2, padding=2)
     assert float((out - ref16).abs().max()) < 1e-4
+
+
+def test_resize_taps_reproduce_cv2_bilinear():
+    """icafusion_b200/datasets.py:resize_taps + the kernel's integer arithmetic (restated in numpy) == cv2.resize(INTER_LINEAR)
+    on uint8, bit for bit -- the host half of the device letterbox (utils/datasets.py:1404-1427)."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from icafusion_b200.datasets import letterbox_geometry, resize_taps
+    g = np.random.Generator(np.random.PCG64(1))
+    for (H0, W0), (h, w) in (((300, 400), (480, 640)), ((1080, 1920), (360, 640)), ((333, 517), (412, 640)), ((64, 80), (640, 800)),
+                             ((720, 1280), (378, 672)), ((517, 333), (640, 412))):
+        img = g.integers(0, 256, (H0, W0, 3), dtype=np.uint8)
+        xt, yt = resize_taps(W0, w).astype(np.int64), resize_taps(H0, h, vertical=True).astype(np.int64)
+        src = img.astype(np.int64)
+        rows = src[:, xt[:, 0]] * xt[:, 2][None, :, None] + src[:, xt[:, 1]] * xt[:, 3][None, :, None]        # (H0, w, 3)
+        out = (((yt[:, 2][:, None, None] * (rows[yt[:, 0]] >> 4)) >> 16) + ((yt[:, 3][:, None, None] * (rows[yt[:, 1]] >> 4)) >> 16) + 2) >> 2
+        want = cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(out.astype(np.uint8), want), (H0, W0, h, w, int(np.abs(out - want).max()))
+    (nw, nh), ratio, (dw, dh), (top, bottom, left, right) = letterbox_geometry((512, 640), (640, 640))
+    assert (nw, nh, top, bottom, left, right) == (640, 512, 64, 64, 0, 0) and ratio == (1.0, 1.0)      # the KAIST frame: bands only

@@ -79,3 +79,17 @@ def test_nms_oracle_matches_reference_golden():
     boxes, scores = torch.cat([xy, xy + wh], 1), (torch.rand(3000, generator=g) * 64).round() / 64     # many score ties
     for thr in (0.3, 0.45, 0.6):
         assert torch.equal(O.greedy_nms(boxes, scores, thr), torchvision.ops.nms(boxes, scores, thr))
+
+
+def test_loss_oracle_matches_reference_golden():
+    """oracle.compute_loss reproduces the REAL reference's ComputeLoss outputs (tests/golden/loss_cases.npz,
+    oracle/gen_golden_loss.py) on the seeded predictions / stored targets."""
+    from oracle.gen_golden_loss import synth_case
+    m, d = load_golden("loss_cases")
+    for cs in m["cases"]:
+        p, t = synth_case(cs["name"], cs["nc"], cs["B"], cs["nt"])
+        assert np.array_equal(t, d[f"{cs['name']}_targets"])
+        loss, items = O.compute_loss([torch.from_numpy(x) for x in p], torch.from_numpy(t), torch.from_numpy(d[f"{cs['name']}_anchors"]),
+                                     cs["hyp"], cs["gr"])
+        got = np.concatenate([loss.numpy().reshape(1), items.numpy()])
+        assert np.allclose(got, d[f"{cs['name']}_out"], rtol=2e-5, atol=1e-6), (cs["name"], got, d[f"{cs['name']}_out"])
