@@ -41,6 +41,18 @@ def resize_taps(src: int, dst: int, vertical: bool = False) -> np.ndarray:
     return np.ascontiguousarray(np.stack([i0, i1, w0, w1], 1).astype(np.int32))
 
 
+_TAPS_ON_DEVICE = {}
+
+
+def _device_taps(src: int, dst: int, vertical: bool, device) -> torch.Tensor:
+    """Tap table on the device, cached per (geometry, device): a CUDA-graph capture must not see the upload."""
+    key = (src, dst, vertical, str(device))
+    t = _TAPS_ON_DEVICE.get(key)
+    if t is None:
+        t = _TAPS_ON_DEVICE[key] = torch.from_numpy(resize_taps(src, dst, vertical)).to(device)
+    return t
+
+
 def letterbox_geometry(shape: Tuple[int, int], new_shape=(640, 640), scaleup: bool = True):
     """reference arithmetic of utils/datasets.py:1404-1424 -> (new_unpad (w, h), ratio, (dw, dh), (top, bottom, left, right))."""
     if isinstance(new_shape, int):
@@ -56,7 +68,7 @@ def letterbox_geometry(shape: Tuple[int, int], new_shape=(640, 640), scaleup: bo
 
 
 def letterbox(img: torch.Tensor, new_shape=(640, 640), color=(114, 114, 114), auto: bool = True, scaleFill: bool = False,
-              scaleup: bool = True, stride: int = 32):
+              scaleup: bool = True, stride: int = 32, out: torch.Tensor = None):
     """reference: utils/datasets.py:1404-1427 (`auto` / `scaleFill` / `stride` are accepted and, as in the reference, unused:
     its minimum-rectangle branch is commented out).  img: CUDA uint8 (B, H0, W0, 3) BGR frames (or (H0, W0, 3)).
     Returns (uint8 (B, 3, H, W) RGB planar -- letterboxed, channel-swapped, transposed: what datasets.py:238-239 hands to the
@@ -71,11 +83,14 @@ def letterbox(img: torch.Tensor, new_shape=(640, 640), color=(114, 114, 114), au
     B, H0, W0, _ = img.shape
     (new_w, new_h), ratio, pad, (top, bottom, left, right) = letterbox_geometry((H0, W0), new_shape, scaleup)
     H, W = new_h + top + bottom, new_w + left + right
-    out = torch.empty(B, 3, H, W, dtype=torch.uint8, device=img.device)
+    if out is None:
+        out = torch.empty(B, 3, H, W, dtype=torch.uint8, device=img.device)
+    elif tuple(out.shape) != (B, 3, H, W) or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError(f"letterbox: `out` must be contiguous uint8 {(B, 3, H, W)}")
     xt = yt = None
     if (new_h, new_w) != (H0, W0):
-        xt = torch.from_numpy(resize_taps(W0, new_w)).to(img.device)
-        yt = torch.from_numpy(resize_taps(H0, new_h, vertical=True)).to(img.device)
+        xt = _device_taps(W0, new_w, False, img.device)
+        yt = _device_taps(H0, new_h, True, img.device)
     ops._call("icaf_letterbox", _lib.lib().icaf_letterbox,
               (ops._ptr(img), B, H0, W0, ops._ptr(out), H, W, top, left, new_h, new_w, ops._ptr(xt), ops._ptr(yt), int(color[0])),
               {"bytes": float(img.numel() + out.numel())})

@@ -19,8 +19,12 @@ from .yolo_test import Model
 
 class GraphedDetector:
     def __init__(self, model: Model, batch: int, height: int, width: int, in_dtype: torch.dtype = torch.float16,
-                 device: Optional[torch.device] = None, warmup: int = 2, nms: Optional[dict] = None):
-        """`nms`: keyword arguments of :func:`icafusion_b200.ops.nms` (e.g. ``dict(conf_thres=0.25, iou_thres=0.45)``); when
+                 device: Optional[torch.device] = None, warmup: int = 2, nms: Optional[dict] = None,
+                 frame_hw: Optional[Tuple[int, int]] = None):
+        """`frame_hw`: (H0, W0) of the raw decoded BGR frames; when given, the device letterbox (utils/datasets.py:1404-1427 +
+        the BGR->RGB / HWC->CHW of :238) is captured in front of the forward and ``infer_frames`` takes the raw uint8
+        (B, H0, W0, 3) frames -- the whole detect_twostream.py:70-86 loop body as one graph.
+        `nms`: keyword arguments of :func:`icafusion_b200.ops.nms` (e.g. ``dict(conf_thres=0.25, iou_thres=0.45)``); when
         given, the batched device NMS (utils/general.py:518-607) is captured behind the forward and ``infer_detections``
         returns its fixed-capacity result -- the whole detect_twostream.py:84-86 step without a host round trip in between."""
         if model.training:
@@ -32,9 +36,23 @@ class GraphedDetector:
         self.shape = (batch, 3, height, width)
         self.rgb = torch.zeros(self.shape, dtype=in_dtype, device=self.device)
         self.ir = torch.zeros(self.shape, dtype=in_dtype, device=self.device)
+        self.frame_hw = frame_hw
+        self.rgb_raw = self.ir_raw = None
+        if frame_hw is not None:
+            from .datasets import letterbox, letterbox_geometry
+            if in_dtype != torch.uint8:
+                raise ValueError("GraphedDetector(frame_hw=...) stages uint8 frames: use in_dtype=torch.uint8")
+            (nw, nh), _, _, (top, bottom, left, right) = letterbox_geometry(frame_hw, (height, width))
+            if (nh + top + bottom, nw + left + right) != (height, width):
+                raise ValueError(f"letterboxing {frame_hw} frames to {(height, width)} does not give {(height, width)}")
+            self.rgb_raw = torch.zeros(batch, frame_hw[0], frame_hw[1], 3, dtype=torch.uint8, device=self.device)
+            self.ir_raw = torch.zeros_like(self.rgb_raw)
+            self._letterbox = lambda t, o: letterbox(t, (height, width), out=o)[0]
         self.stream = torch.cuda.Stream(self.device)
         self.launches_per_step = 0
         with torch.no_grad(), torch.cuda.stream(self.stream):
+            if frame_hw is not None:
+                self._letterbox(self.rgb_raw, self.rgb)    # uploads the tap tables outside the capture
             for _ in range(max(1, warmup)):            # packs filters, configures kernels, warms the allocator
                 self.model(self.rgb, self.ir)
             if self.model.__dict__.get("_icaf_arena") is None:
@@ -51,6 +69,9 @@ class GraphedDetector:
             self.graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
             with torch.cuda.graph(self.graph, stream=self.stream):
+                if frame_hw is not None:
+                    self._letterbox(self.rgb_raw, self.rgb)
+                    self._letterbox(self.ir_raw, self.ir)
                 self.z, self.logits, self.xs = self.model(self.rgb, self.ir)
                 if nms is not None:
                     ops.nms(self.z, det=self.det, count=self.count, workspace=self._nms_ws, **nms)
@@ -72,6 +93,8 @@ class GraphedDetector:
         shape / dtype.  Returns device tensors (z, logits, [x0,x1,x2]) valid until the next call."""
         if tuple(rgb.shape) != self.shape or tuple(ir.shape) != self.shape:
             raise ValueError(f"GraphedDetector was captured for {self.shape}, got {tuple(rgb.shape)}")
+        if self.rgb_raw is not None:
+            raise RuntimeError("this GraphedDetector letterboxes raw frames inside its graph: call infer_frames(rgb_frames, ir_frames)")
         self.rgb.copy_(rgb, non_blocking=True)
         self.ir.copy_(ir, non_blocking=True)
         self.graph.replay()
@@ -91,6 +114,20 @@ class GraphedDetector:
         if self.det is None:
             raise RuntimeError("GraphedDetector was built without nms=...")
         self(rgb_host, ir_host)
+        self._det_host.copy_(self.det, non_blocking=True)
+        self._count_host.copy_(self.count, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._det_host, self._count_host
+
+
+    def infer_frames(self, rgb_frames_host: torch.Tensor, ir_frames_host: torch.Tensor):
+        """The detect_twostream.py loop body for one batch of raw decoded frames (uint8 (B, H0, W0, 3) BGR, ideally pinned):
+        H2D, letterbox + channel swap, staging, forward, NMS, D2H of the detections.  Needs frame_hw= and nms=."""
+        if self.rgb_raw is None or self.det is None:
+            raise RuntimeError("GraphedDetector.infer_frames needs frame_hw=... and nms=...")
+        self.rgb_raw.copy_(rgb_frames_host, non_blocking=True)
+        self.ir_raw.copy_(ir_frames_host, non_blocking=True)
+        self.graph.replay()
         self._det_host.copy_(self.det, non_blocking=True)
         self._count_host.copy_(self.count, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

@@ -60,3 +60,28 @@ def test_letterboxed_pair_through_the_detector(cuda_device):
         wb = torch.from_numpy(_reference_letterbox(ir0[0])[None]).to(cuda_device)
         zr = model(wa, wb)[0]
     assert tuple(z.shape) == (1, 25200, 6) and torch.equal(z, zr)
+
+
+def test_graphed_detect_loop_body(cuda_device):
+    """GraphedDetector(frame_hw=..., nms=...): raw BGR frames -> letterbox -> forward -> NMS as ONE graph; equals the separate
+    calls (device letterbox, eager model, device NMS) on the same frames."""
+    from helpers import load_synth
+    from icafusion_b200 import Model, ops
+    from icafusion_b200.datasets import letterbox
+    from icafusion_b200.engine import GraphedDetector
+    model = Model("yolov5s_Transfusion_kaist").eval()
+    load_synth(model, 6)
+    model = model.fuse().half().to(cuda_device)
+    eng = GraphedDetector(model, 2, 384, 640, in_dtype=torch.uint8, device=cuda_device, nms=dict(conf_thres=0.25, iou_thres=0.45),
+                          frame_hw=(300, 500))
+    g = np.random.Generator(np.random.PCG64(8))
+    for _ in range(2):
+        a = torch.from_numpy(g.integers(0, 256, (2, 300, 500, 3), dtype=np.uint8)).pin_memory()
+        b = torch.from_numpy(g.integers(0, 256, (2, 300, 500, 3), dtype=np.uint8)).pin_memory()
+        det, count = eng.infer_frames(a, b)
+        with torch.no_grad():
+            la, lb = letterbox(a.to(cuda_device), (384, 640))[0], letterbox(b.to(cuda_device), (384, 640))[0]
+            z = model(la, lb)[0]
+            d2, c2 = ops.nms(z, 0.25, 0.45)
+        torch.cuda.synchronize()
+        assert count.tolist() == c2.tolist() and torch.equal(det, d2.cpu())
