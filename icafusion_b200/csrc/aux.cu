@@ -495,7 +495,7 @@ __global__ void axpby_kernel(const __half* __restrict__ x, const __half* __restr
 
 // ------------------------------------------------------------------------------------------------
 // Batched non-maximum suppression on the decoded predictions (reference: utils/general.py:518-607, best-class branch +
-// torchvision.ops.nms).  One block per image, three phases, no host round trip:
+// torchvision.ops.nms).  Three launches, no host round trip:
 //   1. candidates: obj > conf_thres and conf = obj * max_k cls_k > conf_thres (fp32 from the fp16 predictions), class filter;
 //      key = (conf bits << 32) | ~row  -> descending key order = descending confidence, ties in row order (= stable sort)
 //   2. rank sort: rank[i] = #{j : key_j > key_i} (keys are unique), order[rank] = row
@@ -536,48 +536,56 @@ __device__ __forceinline__ bool nms_iou_gt(const float4& a, const float4& b, flo
   const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
 }
+// phase 1: grid (ceil(R / 256), B) -- candidate keys, compacted per image through one integer counter (order is irrelevant:
+// the keys are unique and the rank sort below orders them)
+__global__ void __launch_bounds__(256) nms_filter_kernel(const NmsParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y, r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= P.R) return;
+  const __half* row = P.z + ((size_t)b * P.R + r) * P.no;
+  if (!(__half2float(row[4]) > P.conf_thres)) return;
+  const NmsBox bx = nms_box(row, P.no);
+  if (!(bx.conf > P.conf_thres)) return;
+  if (P.class_mask && !((P.class_mask >> int(bx.cls)) & 1ull)) return;
+  const int slot = atomicAdd(P.count + b, 1);                 // `count` doubles as the candidate counter until phase 3 overwrites it
+  P.keys[(size_t)b * P.R + slot] = ((unsigned long long)__float_as_uint(bx.conf) << 32) | (unsigned long long)(~(unsigned)r);
+}
+// phase 2: grid (ceil(R / 256), B) -- rank of each candidate = number of larger keys (all SMs work on the O(n^2) compares)
+__global__ void __launch_bounds__(256) nms_rank_kernel(const NmsParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ unsigned long long skeys[256];
+  const int b = blockIdx.y;
+  const int n = P.count[b];
+  if (blockIdx.x * 256 >= n) return;
+  const unsigned long long* keys = P.keys + (size_t)b * P.R;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const unsigned long long ki = i < n ? keys[i] : 0ull;
+  int rank = 0;
+  for (int t0 = 0; t0 < n; t0 += 256) {
+    __syncthreads();
+    skeys[threadIdx.x] = t0 + threadIdx.x < n ? keys[t0 + threadIdx.x] : 0ull;
+    __syncthreads();
+    const int m = min(256, n - t0);
+    for (int j = 0; j < m; ++j) rank += skeys[j] > ki;
+  }
+  if (i < n) P.order[(size_t)b * P.R + rank] = int(~(unsigned)(ki & 0xffffffffull));
+}
+// phase 3: one block per image -- greedy suppression in confidence order, 16 candidates per round
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams P) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ unsigned long long skeys[kNmsThreads];
   __shared__ float4 kept[kNmsMaxDet];        // offset boxes of the kept detections
   __shared__ float4 round_box[16];
   __shared__ int round_sup[16];
-  __shared__ int s_n, s_kept;
+  __shared__ int s_kept;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const __half* z = P.z + (size_t)b * P.R * P.no;
-  unsigned long long* keys = P.keys + (size_t)b * P.R;
-  int* order = P.order + (size_t)b * P.R;
-  if (tid == 0) { s_n = 0; s_kept = 0; }
+  const int* order = P.order + (size_t)b * P.R;
+  const int n = P.count[b];
+  if (tid == 0) s_kept = 0;
   __syncthreads();
-  // ---- phase 1: candidates
-  for (int r = tid; r < P.R; r += kNmsThreads) {
-    const __half* row = z + (size_t)r * P.no;
-    if (!(__half2float(row[4]) > P.conf_thres)) continue;
-    const NmsBox bx = nms_box(row, P.no);
-    if (!(bx.conf > P.conf_thres)) continue;
-    if (P.class_mask && !((P.class_mask >> int(bx.cls)) & 1ull)) continue;
-    const int slot = atomicAdd(&s_n, 1);
-    keys[slot] = ((unsigned long long)__float_as_uint(bx.conf) << 32) | (unsigned long long)(~(unsigned)r);
-  }
-  __syncthreads();
-  const int n = s_n;
-  // ---- phase 2: rank sort (descending key)
-  for (int base = 0; base < n; base += kNmsThreads) {
-    const int i = base + tid;
-    const unsigned long long ki = i < n ? keys[i] : 0ull;
-    int rank = 0;
-    for (int t0 = 0; t0 < n; t0 += kNmsThreads) {
-      __syncthreads();
-      skeys[tid] = t0 + tid < n ? keys[t0 + tid] : 0ull;
-      __syncthreads();
-      const int m = min(kNmsThreads, n - t0);
-      for (int j = 0; j < m; ++j) rank += skeys[j] > ki;
-    }
-    if (i < n) order[rank] = int(~(unsigned)(ki & 0xffffffffull));
-  }
-  __syncthreads();
-  // ---- phase 3: greedy suppression, 16 candidates per round
   const int n_eff = min(n, P.max_nms);
   float* det = P.det + (size_t)b * P.max_det * 6;
   for (int c0 = 0; c0 < n_eff; c0 += 16) {
@@ -793,7 +801,15 @@ extern "C" int icaf_nms(const void* z, int B, int R, int no, float conf_thres, f
   P.conf_thres = conf_thres; P.iou_thres = iou_thres; P.class_mask = class_mask; P.det = det; P.count = count;
   P.keys = (unsigned long long*)workspace;
   P.order = (int*)((char*)workspace + (size_t)B * R * sizeof(unsigned long long));
-  launch_k(nms_kernel, dim3(B), dim3(kNmsThreads), 0, (cudaStream_t)stream, P);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(count, 0, (size_t)B * sizeof(int), st);      // candidate counters
+  if (e != cudaSuccess) return set_cuda_error(e, "nms: cudaMemsetAsync");
+  const dim3 grid((unsigned)((R + 255) / 256), (unsigned)B);
+  launch_k(nms_filter_kernel, grid, dim3(256), 0, st, P);
+  if (int rc = check_launch("nms(filter)")) return rc;
+  launch_k(nms_rank_kernel, grid, dim3(256), 0, st, P);
+  if (int rc = check_launch("nms(rank)")) return rc;
+  launch_k(nms_kernel, dim3(B), dim3(kNmsThreads), 0, st, P);
   return check_launch("nms");
 }
 
