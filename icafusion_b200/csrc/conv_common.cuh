@@ -37,6 +37,7 @@ struct ConvParams {
   int splits;                             // split-K factor = cluster size along x (1 = no cluster); partial sums meet in DSMEM
   int cblk;                               // A_TMA4D: channels per TMA box = min(Cin, 64); < 64 only in the persistent kernel
   int halo;                               // conv_pair.cu: 3x3/s1 layers stage three x-shifted (th+2)-row copies per channel block (0 / 1)
+  int dense16;                            // host only: every problem's input has pixel pitch 16 (stem kernel eligibility)
   int ln_parts;                           // LN fold: partials per input row (0 = no fold)
   float ln_eps, ln_inv_k;                 // LN fold: epsilon, 1 / (normalised features = K)
   int dbg;                                // probe builds (-DICAF_PROBE, tools/conv_probe.py): 1 no stores, 2 no activation,
@@ -240,6 +241,12 @@ __device__ __forceinline__ void epi_chunk16(const uint32_t (&acc)[16], const flo
   }
 }
 
+__device__ __forceinline__ ConvProblem pick_problem_stem(const ConvProblem (&p)[2], int z) {
+  ConvProblem r = p[0];
+  if (z) r = p[1];
+  return r;
+}
+
 // Host-side launch plan: everything the dispatcher decides before it touches CUDA.  icaf_conv2d_plan (host only, no
 // device needed) exposes it so that a CPU test can walk every layer geometry through the dispatcher's invariants.
 struct ConvPlan {
@@ -258,6 +265,11 @@ template <int BN>
 int plan_persist(ConvParams& P, int n_io, ConvPlan& pl);
 template <int BN>
 int launch_persist(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
+
+// image-stem kernel (conv_stem.cu): 3x3 / s1 over the 16-channel space-to-depth frame, x-merged rows
+bool stem_eligible(const icaf_conv_geom* g);
+int plan_stem(ConvParams& P, const icaf_conv_geom* g, int n_io, ConvPlan& pl);
+int launch_stem(const ConvParams& P, const ConvPlan& pl, const __half* const (&w)[2], const icaf_conv_geom* g, int n_io, cudaStream_t st);
 
 // CTA-pair kernel (conv_pair.cu): 256 x BN tiles over two SMs, tcgen05.mma.cta_group::2 (BN = 64, 128, 256)
 template <int BN>

@@ -387,6 +387,7 @@ static int fill_geom(const icaf_conv_geom* g, int n_io, ConvParams& P) {
   P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad = g->pad; P.act = g->act; P.epi = g->epi;
   P.a_mode = A_GATHER; P.tw = P.th = P.tiles_x = P.tiles_y = 0; P.stages = 2; P.splits = 1; P.cblk = 64; P.halo = 0; P.dbg = g_dbg;
   P.ln_parts = 0; P.ln_eps = 0.f; P.ln_inv_k = 0.f;
+  P.dense16 = 1;                          // plan-only calls have no pointers: assume a dense input frame
   memset(P.p, 0, sizeof(P.p));
   return ICAF_OK;
 }
@@ -413,6 +414,7 @@ static int fill_params(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io
                          (g->epi & ICAF_EPI_LN_FOLD) ? s.ln_colsum : nullptr,
                          (g->epi & ICAF_EPI_EMIT_STATS) ? (float2*)s.stats_out : nullptr};
     if (i == 0 && (g->epi & ICAF_EPI_LN_FOLD)) { P.ln_parts = s.ln_parts; P.ln_eps = s.ln_eps; P.ln_inv_k = 1.0f / float(P.K); }
+    if (i < n_io && s.x_ld != 16) P.dense16 = 0;
     w[i] = (const __half*)s.w;
   }
   return ICAF_OK;
@@ -569,6 +571,12 @@ static int plan_conv(const icaf_conv_geom* g, int n_io, int sms, int pair_mode, 
   // (A wave-tail scheme -- peel total % SMs tiles off into a split-K cluster launch -- was measured and dropped: these
   // layers are bound by chip-wide L2->SM bandwidth, so a partly filled last wave just streams the same bytes through
   // fewer, faster CTAs; the second launch only added its fixed cost: 65 -> 87 us on the 320-tile P4 3x3 layer.)
+  // The image stem (3x3 / s1 over the 16-channel space-to-depth frame) has its own kernel once a wave of tiles exists
+  // (conv_stem.cu: x-merged rows, four accumulators per tile, resident filter).  ICAF_STEM=0 keeps the generic kernels.
+  static const bool stem_on = []() { const char* e = getenv("ICAF_STEM"); return !(e && e[0] == '0'); }();
+  if (stem_on && P.dense16 && stem_eligible(g) &&
+      (long long)g->B * ((g->Wo / 4 + 7) / 8) * ((g->Ho + 15) / 16) * n_io >= sms / 2)
+    return plan_stem(P, g, n_io, pl);
   if (pair_env && halo_on && P.a_mode == A_TMA4D && P.cblk < 64 && g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1) {
     // 16- / 32-channel 3x3 layers (the image stem over the space-to-depth frame): CTA pairs + halo copies, 64-wide tiles
     const int tx = (g->Wo + 7) / 8, ty = (g->Ho + 15) / 16;
@@ -661,6 +669,8 @@ extern "C" int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, 
     case ICAF_KERNEL_TC * 1000 + 128: return launch_tc<128>(P, pl, w, g, n_io, st);
     case ICAF_KERNEL_TC * 1000 + 64: return launch_tc<64>(P, pl, w, g, n_io, st);
     case ICAF_KERNEL_TC * 1000 + 32: return launch_tc<32>(P, pl, w, g, n_io, st);
+    case ICAF_KERNEL_STEM * 1000 + 64:
+    case ICAF_KERNEL_STEM * 1000 + 32: return launch_stem(P, pl, w, g, n_io, st);
     default: return set_error(ICAF_ERR_BAD_ARG, "conv2d: the planner produced an unknown kernel / tile width");
   }
 }

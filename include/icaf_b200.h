@@ -101,6 +101,8 @@ int icaf_conv2d_fwd(const icaf_conv_geom* g, const icaf_conv_io* io, int n_io, v
 #define ICAF_KERNEL_TC 0      /* one 128 x BN tile per CTA, split-K clusters   (conv_gemm.cu)    */
 #define ICAF_KERNEL_PERSIST 1 /* one CTA per SM looping over tiles              (conv_persist.cu) */
 #define ICAF_KERNEL_PAIR 2    /* CTA pairs, tcgen05 cta_group::2, halo copies   (conv_pair.cu)    */
+#define ICAF_KERNEL_STEM 3    /* image stem over the space-to-depth frame, x-merged rows (conv_stem.cu); the plan
+                                 assumes a dense frame (pixel pitch 16), which icaf_conv2d_fwd checks on the pointers */
 typedef struct {
   int kernel;                            /* ICAF_KERNEL_*                                                     */
   int bn;                                /* output-channel tile width (32/64/128/256)                         */

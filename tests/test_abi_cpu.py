@@ -100,10 +100,15 @@ def _dry_geometries(size: str, B: int, H: int = 512, W: int = 640):
 def _check_plan(g, n, pl, sms, tag):
     from icafusion_b200 import _lib
     where = f"{tag}: kernel {pl.kernel} bn {pl.bn} a_mode {pl.a_mode} halo {pl.halo}"
-    assert pl.kernel in (_lib.KERNEL_TC, _lib.KERNEL_PERSIST, _lib.KERNEL_PAIR) and pl.bn in (32, 64, 128, 256), where
+    assert pl.kernel in (_lib.KERNEL_TC, _lib.KERNEL_PERSIST, _lib.KERNEL_PAIR, _lib.KERNEL_STEM) and pl.bn in (32, 64, 128, 256), where
     assert 0 < pl.smem_bytes <= 227 * 1024, where
     assert pl.grid_x >= 1 and pl.grid_y >= 1 and pl.grid_z >= 1 and pl.stages >= 1, where
     ctas = pl.grid_x * pl.grid_y * pl.grid_z
+    if pl.kernel == _lib.KERNEL_STEM:      # the space-to-depth image stem: 16 rows x 8 super-pixels (= 32 pixels) per tile
+        assert (g.Cin, g.kh, g.kw, g.stride, g.pad) == (16, 3, 3, 1, 1) and g.Cout <= pl.bn <= 64 and g.Wo % 4 == 0, where
+        assert (pl.tile_w, pl.tile_h) == (32, 16) and pl.tiles_x * 32 >= g.Wo and pl.tiles_y * 16 >= g.Ho, where
+        assert pl.cluster == 1 and pl.grid_x <= sms and pl.work_items == g.B * pl.tiles_x * pl.tiles_y * n, where
+        return
     if pl.a_mode == 2:       # 4-D TMA tiles cover the output map with <= 128 pixels per tile
         assert 1 <= pl.tile_w * pl.tile_h <= 128, where
         assert pl.tiles_x * pl.tile_w >= g.Wo and pl.tiles_y * pl.tile_h >= g.Ho, where
@@ -145,8 +150,8 @@ def test_dispatcher_plans_every_layer_geometry(size, B):
                     assert pl.kernel != _lib.KERNEL_PAIR
                 if sms == 148 and pair_mode == 1:
                     kernels.add((pl.kernel, pl.halo))
-    if (size, B) == ("l", 16):     # the compute-bound config exercises all three kernel families and both halo modes
-        assert {(0, 0), (1, 0), (2, 0), (2, 1), (2, 2)} <= kernels, kernels
+    if (size, B) == ("l", 16):     # the compute-bound config exercises every kernel family (tc, persistent, pair with and without halo copies, stem)
+        assert {(0, 0), (1, 0), (2, 0), (2, 1), (3, 0)} <= kernels, kernels
 
 
 def test_dispatcher_plan_matches_small_and_odd_geometries():

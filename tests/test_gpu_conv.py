@@ -61,6 +61,9 @@ CASES = [
     (1, 64, 301, 128, 512, 1, 1, 0, 1),   # CTA-pair kernel, odd M-tile count (301): the last pair's peer tile is all padding
     (99, 64, 16, 24, 256, 3, 1, 1, 1),    # CTA-pair kernel, 4-D TMA, 297 M tiles: peer tile past the last image
     (16, 512, 16, 20, 512, 3, 1, 1, 1),   # yolov5l P5 at batch 16: CTA pairs + halo copies, 16x8 tiles hang over the 20-wide map
+    (4, 16, 128, 160, 64, 3, 1, 1, 1),    # space-to-depth stem kernel (x-merged rows), N = 64, 200 tiles
+    (12, 16, 50, 36, 48, 3, 1, 1, 0),     # stem kernel, ragged: 9 super-pixels per row (tiles hang over), 50 rows, N = 48, no activation
+    (2, 16, 256, 320, 32, 3, 1, 1, 1),    # stem kernel at the yolov5s frame size, N = 32
 ]
 
 
