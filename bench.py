@@ -390,7 +390,7 @@ def dmff_block_metrics(dev):
                      "frac_of_roofline": round(t_bound / (ms * 1e-3), 4),
                      "bound": "tensor" if F / (tf_peak * 1e12) > by / (hbm * 1e9) else "hbm"}
     out["note"] = ("TransformerFusionBlock(256) on 1x256x32x40 RGB+IR maps, CUDA-graph replay, L2 flushed; roofline time = "
-                   "max(F/peak_tensor, ideal_bytes/peak_hbm); latency-bound at batch 1 (13 kernels)")
+                   "max(F/peak_tensor, ideal_bytes/peak_hbm); latency-bound at batch 1 (8 launches per block: pooling, 5 per loop, tail, 1x1 conv)")
     return out
 
 

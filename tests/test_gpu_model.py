@@ -145,4 +145,6 @@ def test_bench_shape_yolov5l_b16_through_graph(cuda_device):
             z1 = model(rgb_u8[j:j + 1].to(cuda_device), ir_u8[j:j + 1].to(cuda_device))[0]
             worst = max(worst, err(z[j:j + 1], z1))
         print(f"[yolov5l b16 graph] worst pair vs the eager batch-1 forward {worst:.2e}")
-        assert worst < 1.5e-3
+        # two fp16 runs of ~100 layers with different tile plans / split-K factors (the plans depend on the batch): each sits
+        # ~1e-3 from the fp32 oracle (above), so their mutual distance can reach the sum of the two
+        assert worst < 2.5e-3
