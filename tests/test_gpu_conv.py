@@ -258,3 +258,24 @@ def test_scaled_residual_emits_row_statistics(cuda_device, M, K, N, n_io):
         assert torch.allclose(tot[:, 0], yf.sum(1), rtol=1e-4, atol=1e-2) and torch.allclose(tot[:, 1], (yf * yf).sum(1), rtol=1e-4, atol=1e-2)
         zr = F.layer_norm(y.float().cpu(), (N,), gamma, beta, 1e-5) @ w2.t()
         assert err(z, zr) < 1e-3
+
+
+def test_full_size_linearity(cuda_device):
+    """Size-independent property at a BASELINE-size layer (yolov5l P3 bottleneck, batch 16: M = 81920, K = 1152; too big for
+    the CPU oracle in a test): without bias and activation the convolution is linear, conv(x1 + x2) == conv(x1) + conv(x2)
+    up to the fp16 rounding of the three outputs, and conv(0) == 0 exactly."""
+    from icafusion_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 16, 128, 64, 80
+    x1 = (torch.randn(B, H, W, C, generator=g) * 0.5).half().to(cuda_device)
+    x2 = (torch.randn(B, H, W, C, generator=g) * 0.5).half().to(cuda_device)
+    w = torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5
+    pk = ops.pack_conv_weight(w, None, 1, 1, ops.ACT_NONE, device=cuda_device)
+    xs = (x1.float() + x2.float()).half()
+    y1, y2, ys = (ops.conv2d([t], [pk])[0].float() for t in (x1, x2, xs))
+    y0 = ops.conv2d([torch.zeros_like(x1)], [pk])[0]
+    torch.cuda.synchronize()
+    assert float(y0.abs().max()) == 0.0
+    e = float((ys - (y1 + y2)).abs().max() / ys.abs().max())
+    print(f"\n[linearity M{B * H * W} K{C * 9}] {e:.2e}")
+    assert e < 2e-3            # three fp16 output roundings + the fp16 rounding of x1 + x2 carried through K = 1152

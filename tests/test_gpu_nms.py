@@ -111,3 +111,31 @@ def test_graphed_detector_with_captured_nms(cuda_device):
         assert count.tolist() == [int(r.shape[0]) for r in ref]
         for i, r in enumerate(ref):
             assert np.array_equal(det[i, :r.shape[0]].numpy(), r.numpy())
+
+
+def test_nms_idempotent_at_full_size(cuda_device):
+    """Size-independent property at the full 20160-row prediction size: suppressing the survivors again (as predictions with
+    objectness = confidence, class score 1) keeps every one of them, in the same order."""
+    from icafusion_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    B, R = 4, 20160
+    z = torch.zeros(B, R, 6)
+    z[..., 0:2] = torch.rand(B, R, 2, generator=g) * 600
+    z[..., 2:4] = torch.rand(B, R, 2, generator=g) * 80 + 4
+    z[..., 4] = torch.rand(B, R, generator=g) ** 4
+    z[..., 5] = 1.0
+    z = z.half().to(cuda_device)
+    det, cnt = ops.nms(z, 0.05, 0.5)
+    n = cnt.tolist()
+    z2 = torch.zeros(B, 304, 6, device=cuda_device)
+    for b in range(B):
+        d = det[b, :n[b]]
+        z2[b, :n[b], 0] = (d[:, 0] + d[:, 2]) / 2
+        z2[b, :n[b], 1] = (d[:, 1] + d[:, 3]) / 2
+        z2[b, :n[b], 2] = d[:, 2] - d[:, 0]
+        z2[b, :n[b], 3] = d[:, 3] - d[:, 1]
+        z2[b, :n[b], 4] = d[:, 4]
+        z2[b, :n[b], 5] = 1.0
+    det2, cnt2 = ops.nms(z2.half(), 0.04, 0.5 + 2e-2)       # survivors overlap at most 0.5 (+ fp16 re-rounding of the boxes)
+    torch.cuda.synchronize()
+    assert min(n) > 50 and cnt2.tolist() == n
