@@ -71,7 +71,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__cluster_size", "launch__occupancy_limit_shared_mem", "smsp__cycles_active.avg", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
         "lts__t_sectors_srcunit_tex_op_read.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
-        "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed.sum"]
+        "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
 def full_summary(name):
@@ -120,7 +122,7 @@ for wl in ("yolov5s_b1", "yolov5l_b16"):
         traffic[wl] = s
 if traffic:
     json.dump(traffic, open(os.path.join(OUT, f"{tag}_traffic.json"), "w"), indent=1)
-for name in ("full_conv_l_b16_head", "full_conv_l_b16_pair", "full_conv_l_b16_pair2", "full_conv_s_b1", "full_attn_l_b16"):
+for name in ("full_conv_l_b16_head", "full_conv_l_b16_pair", "full_conv_l_b16_pair2", "full_conv_s_b1", "full_attn_l_b16", "full_attn_big"):
     full_summary(name)
 print(json.dumps(traffic, indent=1))
 print(sorted(os.listdir(OUT)))
