@@ -70,6 +70,10 @@ SIGNATURES = {
     "icaf_loss_workspace_bytes": [_i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i],
     "icaf_compute_loss_fwd": [C.POINTER(C.c_void_p), _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _i, _i, _i, _vp, _i,
                               C.POINTER(C.c_float), C.POINTER(LossHyp), _vp, _vp, C.c_size_t, _vp],
+    "icaf_conv2d_wgrad_workspace_bytes": [C.POINTER(ConvGeom)],
+    "icaf_conv2d_wgrad": [C.POINTER(ConvGeom), _vp, _i64, _vp, _i64, _vp, _f, _i, _vp, C.c_size_t, _vp],
+    "icaf_zero_stuff2": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "icaf_colsum": [_vp, _i64, _i, _vp, _f, _i, _vp, C.c_size_t, _vp],
     "icaf_axpby": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "icaf_detect_decode": [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.POINTER(C.c_float), _vp],
 }
@@ -93,7 +97,8 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)            # AttributeError here = header/.so drift
             fn.argtypes = argtypes
             fn.restype = {"icaf_last_error": C.c_char_p, "icaf_kernel_launches": C.c_longlong,
-                          "icaf_nms_workspace_bytes": C.c_size_t, "icaf_loss_workspace_bytes": C.c_size_t}.get(name, C.c_int)
+                          "icaf_nms_workspace_bytes": C.c_size_t, "icaf_loss_workspace_bytes": C.c_size_t,
+                          "icaf_conv2d_wgrad_workspace_bytes": C.c_size_t}.get(name, C.c_int)
         _lib = L
     return _lib
 

@@ -525,3 +525,77 @@ def nms(z: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45, agno
           (_ptr(z), B, R, no, float(conf_thres), float(iou_thres), int(bool(agnostic)), C.c_uint64(mask), int(max_det), _ptr(det), _ptr(count),
            _ptr(workspace), C.c_size_t(workspace.numel() * workspace.element_size())), {"bytes": 2.0 * z.numel()})
     return det, count
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training-step building blocks (operator level; see include/icaf_b200.h).  Gradients of Conv2d / Linear layers.
+def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, stride: int, pad: int, scale: float = 1.0,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW (Cout, Cin, kh, kw) fp32 = scale * sum_pixels dy x.  x (B,Hi,Wi,Cin), dy (B,Ho,Wo,Cout): fp16 NHWC views.  With
+    `out` the gradient is ACCUMULATED into it (`.grad` semantics)."""
+    B, Hi, Wi, Cin = x.shape
+    _, Ho, Wo, Cout = dy.shape
+    g = _lib.ConvGeom(B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, round_up(kh * kw * Cin, 64), round_up(Cout, 32), 0, 0)
+    need = int(_lib.lib().icaf_conv2d_wgrad_workspace_bytes(C.byref(g)))
+    if need == 0:
+        raise _lib.IcafError(f"conv2d_wgrad: unsupported geometry Cin={Cin} Cout={Cout} k={kh}x{kw} s={stride}")
+    ws = torch.empty((need + 7) // 8, dtype=torch.int64, device=x.device)
+    acc = out is not None
+    if out is None:
+        out = torch.empty(Cout, Cin, kh, kw, dtype=torch.float32, device=x.device)
+    elif tuple(out.shape) != (Cout, Cin, kh, kw) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("conv2d_wgrad: `out` must be contiguous fp32 (Cout, Cin, kh, kw)")
+    _call("icaf_conv2d_wgrad", _lib.lib().icaf_conv2d_wgrad,
+          (C.byref(g), _ptr(x), _check_view(x, "wgrad x"), _ptr(dy), _check_view(dy, "wgrad dy"), _ptr(out), float(scale), int(acc), _ptr(ws),
+           C.c_size_t(ws.numel() * 8)), {"flops": 2.0 * B * Ho * Wo * Cout * Cin * kh * kw, "bytes": 2.0 * (x.numel() + dy.numel())})
+    return out
+
+
+def linear_wgrad(x: torch.Tensor, dy: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW (N, K) fp32 of y = x W^T for (rows, K) x and (rows, N) dy."""
+    o4 = None if out is None else out.view(out.shape[0], out.shape[1], 1, 1)
+    return conv2d_wgrad(x.unflatten(0, (1, 1, x.shape[0])), dy.unflatten(0, (1, 1, dy.shape[0])), 1, 1, 1, 0, scale, o4).view(dy.shape[1], x.shape[1])
+
+
+def pack_dgrad_weight(weight: torch.Tensor, device=None) -> PackedConv:
+    """Filter of the data-gradient convolution: W'[c][n][ky][kx] = W[n][c][kh-1-ky][kw-1-kx], stride 1, pad k-1-p is set by
+    the caller through conv2d_dgrad (no bias, no activation)."""
+    w = weight.detach().float().flip(2, 3).permute(1, 0, 2, 3).contiguous()
+    return pack_conv_weight(w, None, 1, 0, ACT_NONE, device)
+
+
+def zero_stuff2(dy: torch.Tensor, H2: int, W2: int) -> torch.Tensor:
+    B, H, W, Cc = dy.shape
+    out = torch.empty(B, H2, W2, Cc, dtype=torch.float16, device=dy.device)
+    _call("icaf_zero_stuff2", _lib.lib().icaf_zero_stuff2, (_ptr(dy.contiguous()), _ptr(out), B, H, W, Cc, H2, W2), {"bytes": 2.0 * (dy.numel() + out.numel())})
+    return out
+
+
+def conv2d_dgrad(dy: torch.Tensor, weight: torch.Tensor, stride: int, pad: int, in_hw) -> torch.Tensor:
+    """dx (B,Hi,Wi,Cin) fp16 of y = conv2d(x, weight, stride, pad): the forward tensor-core kernel on the flipped / transposed
+    filter; a stride-2 layer first spreads dy over the input grid (icaf_zero_stuff2)."""
+    k = weight.shape[2]
+    Hi, Wi = in_hw
+    pk = pack_dgrad_weight(weight, dy.device)
+    if stride == 2:
+        dy = zero_stuff2(dy, Hi + 2 * pad - k + 1, Wi + 2 * pad - k + 1)
+    elif stride != 1:
+        raise NotImplementedError("conv2d_dgrad: stride 1 or 2")
+    pk.pad = k - 1 - pad
+    dx = conv2d([dy], [pk])[0]
+    if tuple(dx.shape[1:3]) != (Hi, Wi):
+        raise ValueError(f"conv2d_dgrad: got a {tuple(dx.shape[1:3])} gradient map for a {(Hi, Wi)} input")
+    return dx
+
+
+def colsum(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Column sums (fp32) of a dense fp16 (rows, C) matrix -- bias gradients; accumulates into `out` when given."""
+    rows, Cc = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float16
+    acc = out is not None
+    if out is None:
+        out = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    ws = torch.empty(64 * Cc, dtype=torch.float32, device=x.device)
+    _call("icaf_colsum", _lib.lib().icaf_colsum, (_ptr(x), rows, Cc, _ptr(out), float(scale), int(acc), _ptr(ws), C.c_size_t(ws.numel() * 4)),
+          {"bytes": 2.0 * x.numel()})
+    return out

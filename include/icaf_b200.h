@@ -243,6 +243,26 @@ int icaf_compute_loss_fwd(const void* const* p, int p_fp32, const int* ny, const
                           const float* targets, int nt, const float* anchors_host, const icaf_loss_hyp* hyp, float* out,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-step building blocks (train.py:344 backward of the hot path's nn.Conv2d / nn.Linear layers).  Operator level
+ * only: the whole-model backward / optimiser / DDP loop is not built.
+ * ------------------------------------------------------------------------------------------- */
+/* Weight gradient dW[n][c][ky][kx] (fp32, PyTorch layout) = (accumulate ? dW : 0) + scale * sum_pixels dy[.., n] * x[.. shifted .., c]
+ * of the convolution / linear layer described by `g` (Cin 16, 32 or a multiple of 64; Cout % 8 == 0; stride 1 or 2).
+ * x, dy: fp16 NHWC views (pixel pitch x_ld / dy_ld).  tcgen05 GEMM over pixels with both operands MN-major, split over
+ * the pixel range, splits summed in a fixed order (deterministic).  scale: 1 / loss scale.  workspace: caller owned,
+ * icaf_conv2d_wgrad_workspace_bytes(g) bytes, 16-byte aligned. */
+size_t icaf_conv2d_wgrad_workspace_bytes(const icaf_conv_geom* g);
+int icaf_conv2d_wgrad(const icaf_conv_geom* g, const void* x, int64_t x_ld, const void* dy, int64_t dy_ld, float* dw, float scale,
+                      int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* y (B, H2, W2, C) = x (B, H, W, C) with a zero between every two pixels (y[b, 2i, 2j] = x[b, i, j]): the data gradient of a
+ * stride-2 convolution is the stride-1 icaf_conv2d_fwd of this tensor with the flipped, transposed filter. */
+int icaf_zero_stuff2(const void* x, void* y, int B, int H, int W, int C, int H2, int W2, void* stream);
+/* out[c] (fp32) = (accumulate ? out[c] : 0) + scale * sum_rows x[r][c] of a dense fp16 (rows, C) matrix: bias gradients.
+ * Deterministic two-stage sum; workspace: 64 * C floats. */
+int icaf_colsum(const void* x, int64_t rows, int C, float* out, float scale, int accumulate, float* workspace, size_t workspace_bytes,
+                void* stream);
+
 /* out = a[0] * x (+ b[0] * y when y != NULL) over n fp16 elements (n % 8 == 0, 16-byte aligned); a, b device fp32 scalars.
  * LearnableCoefficient.forward / LearnableWeights.forward called stand-alone (models/common.py:569-587). */
 int icaf_axpby(const void* x, const void* y, const float* a, const float* b, void* out, int64_t n, void* stream);
