@@ -74,6 +74,14 @@ SIGNATURES = {
     "icaf_conv2d_wgrad": [C.POINTER(ConvGeom), _vp, _i64, _vp, _i64, _vp, _f, _i, _vp, C.c_size_t, _vp],
     "icaf_zero_stuff2": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "icaf_colsum": [_vp, _i64, _i, _vp, _f, _i, _vp, C.c_size_t, _vp],
+    "icaf_train_workspace_bytes": [_i],
+    "icaf_bn_act_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp, C.c_size_t, _vp],
+    "icaf_bn_act_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, C.c_size_t, _vp],
+    "icaf_eltwise": [_i, _vp, _vp, _vp, _i64, _f, C.c_uint32, _vp],
+    "icaf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp, C.c_size_t, _vp],
+    "icaf_dot": [_vp, _vp, _i64, _i, _vp, _f, _i, _vp, C.c_size_t, _vp],
+    "icaf_upsample2x_bwd": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "icaf_maxpool5_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "icaf_axpby": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "icaf_detect_decode": [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.POINTER(C.c_float), _vp],
 }
@@ -98,7 +106,7 @@ def lib() -> C.CDLL:
             fn.argtypes = argtypes
             fn.restype = {"icaf_last_error": C.c_char_p, "icaf_kernel_launches": C.c_longlong,
                           "icaf_nms_workspace_bytes": C.c_size_t, "icaf_loss_workspace_bytes": C.c_size_t,
-                          "icaf_conv2d_wgrad_workspace_bytes": C.c_size_t}.get(name, C.c_int)
+                          "icaf_conv2d_wgrad_workspace_bytes": C.c_size_t, "icaf_train_workspace_bytes": C.c_size_t}.get(name, C.c_int)
         _lib = L
     return _lib
 

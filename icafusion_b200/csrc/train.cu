@@ -1,0 +1,421 @@
+// Training-mode kernels of the hot path that are not GEMMs (forward and backward): BatchNorm with batch statistics + SiLU
+// (Conv.forward, models/common.py:56-57), exact-erf GELU, LayerNorm backward, the SPPF max-pool chain, nearest up-sampling,
+// the DMFF token pooling / nearest tail, dropout, and the small reductions behind scalar-parameter gradients.
+// fp16 activations / gradients, fp32 statistics and parameter gradients.  Every reduction is two-stage with a fixed
+// summation order (deterministic; the reference trains with torch.use_deterministic_algorithms, utils/general.py:53-54).
+#include "icaf_internal.cuh"
+
+namespace icaf {
+
+constexpr int kRedChunks = 64;
+
+__device__ __forceinline__ void unpack8h(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack_half2(f[0], f[1]); v.y = pack_half2(f[2], f[3]); v.z = pack_half2(f[4], f[5]); v.w = pack_half2(f[6], f[7]);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-channel partial sums over row chunks: out[chunk][which][c], which = 0 / 1.
+// MODE 0: (x, x^2)  [BatchNorm statistics]      MODE 1: (dz, dz * xhat) with dz = dy * silu'(x*a + b)  [BN + SiLU backward]
+// MODE 2: (dy, dy * xhat_row) with per-ROW (mean, rstd)  [LayerNorm gamma / beta gradients]   MODE 3: (x * y, 0)  [dot products]
+template <int MODE>
+__global__ void __launch_bounds__(256) chan_partial_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const float* __restrict__ a,
+                                                           const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           float* __restrict__ out, long long rows, int C, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8][32][17];
+  const int cg = blockIdx.x * 32 + threadIdx.x;            // 8-channel group
+  const int C8 = C >> 3;
+  const long long per = (rows + kRedChunks - 1) / kRedChunks;
+  const long long r0 = blockIdx.y * per, r1 = min(r0 + per, rows);
+  float s0[8], s1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
+  if (cg < C8) {
+    float av[8], bv[8], mv[8], iv[8];
+    if (MODE == 1) {                                        // a = gamma, b = beta on entry -> per-channel affine of the BN apply
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        mv[e] = mean[cg * 8 + e]; iv[e] = invstd[cg * 8 + e];
+        av[e] = a[cg * 8 + e] * iv[e]; bv[e] = b[cg * 8 + e] - mv[e] * av[e];
+      }
+    }
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      float xv[8], dv[8];
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(x + r * C + cg * 8)), xv);
+      if (MODE != 0) unpack8h(__ldg(reinterpret_cast<const uint4*>(dy + r * C + cg * 8)), dv);
+      float rm = 0.f, ri = 0.f;
+      if (MODE == 2) { rm = mean[r]; ri = invstd[r]; }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (MODE == 0) { s0[e] += xv[e]; s1[e] += xv[e] * xv[e]; }
+        if (MODE == 1) {
+          const float z = xv[e] * av[e] + bv[e];
+          float dz = dv[e];
+          if (act) { const float sg = sigmoidf_(z); dz *= sg * (1.f + z * (1.f - sg)); }
+          s0[e] += dz; s1[e] += dz * (xv[e] - mv[e]) * iv[e];
+        }
+        if (MODE == 2) { s0[e] += dv[e]; s1[e] += dv[e] * (xv[e] - rm) * ri; }
+        if (MODE == 3) { s0[e] += xv[e] * dv[e]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red[threadIdx.y][threadIdx.x][e] = s0[e]; red[threadIdx.y][threadIdx.x][8 + e] = s1[e]; }
+  __syncthreads();
+  if (threadIdx.y == 0 && cg < C8) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float s = 0.f;
+      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][e];
+      out[(size_t(blockIdx.y) * 2 + (e >> 3)) * C + cg * 8 + (e & 7)] = s;
+    }
+  }
+}
+
+// BatchNorm statistics, second stage: mean, invstd, and the running statistics update (momentum, unbiased variance)
+__global__ void bn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ invstd, float* run_mean,
+                                   float* run_var, int C, long long rows, float eps, float momentum) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f, q = 0.f;
+  for (int k = 0; k < kRedChunks; ++k) { s += part[(size_t(k) * 2) * C + c]; q += part[(size_t(k) * 2 + 1) * C + c]; }
+  const float m = s / float(rows);
+  const float var = fmaxf(q / float(rows) - m * m, 0.f);
+  mean[c] = m;
+  invstd[c] = rsqrtf(var + eps);
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (rows > 1 ? float(rows) / float(rows - 1) : 1.f);
+  }
+}
+// generic second stage: out[which][c] = (accumulate ? out : 0) + scale * sum_chunks part
+__global__ void chan_final_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1, int C, float scale, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f, q = 0.f;
+  for (int k = 0; k < kRedChunks; ++k) { s += part[(size_t(k) * 2) * C + c]; q += part[(size_t(k) * 2 + 1) * C + c]; }
+  if (out0) out0[c] = (accumulate ? out0[c] : 0.f) + scale * s;
+  if (out1) out1[c] = (accumulate ? out1[c] : 0.f) + scale * q;
+}
+// scalar second stage of MODE 3 partials: out[0] = (accumulate ? out[0] : 0) + scale * sum of everything
+__global__ void scalar_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C, float scale, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int k = 0; k < kRedChunks; ++k)
+    for (int c = threadIdx.x; c < C; c += 256) s += part[(size_t(k) * 2) * C + c];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + scale * red[0];
+}
+
+// y = act(x * a[c] + b[c])   (BatchNorm apply + SiLU; a = gamma * invstd, b = beta - mean * a)
+__global__ void affine_act_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd, __half* __restrict__ y, long long n8, int C8, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int cg = int(i % C8);
+  float v[8];
+  unpack8h(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    const float a = gamma[c] * invstd[c];
+    const float z = v[e] * a + (beta[c] - mean[c] * a);
+    v[e] = act ? z * sigmoidf_(z) : z;
+  }
+  reinterpret_cast<uint4*>(y)[i] = pack8h(v);
+}
+// dx = gamma * invstd * (dz - S1 / M - xhat * S2 / M),  dz = dy * act'(z)   (S1 = sum dz, S2 = sum dz xhat: `sums` = [2][C])
+__global__ void bn_bwd_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ sums, __half* __restrict__ dx, long long n8, int C8, float inv_m, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int cg = int(i % C8), C = C8 * 8;
+  float xv[8], dv[8];
+  unpack8h(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
+  unpack8h(__ldg(reinterpret_cast<const uint4*>(dy) + i), dv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    const float a = gamma[c] * invstd[c];
+    const float xh = (xv[e] - mean[c]) * invstd[c];
+    const float z = xv[e] * a + (beta[c] - mean[c] * a);
+    float dz = dv[e];
+    if (act) { const float sg = sigmoidf_(z); dz *= sg * (1.f + z * (1.f - sg)); }
+    xv[e] = a * (dz - sums[c] * inv_m - xh * sums[C + c] * inv_m);
+  }
+  reinterpret_cast<uint4*>(dx)[i] = pack8h(xv);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// element-wise: MODE 0 gelu(x) [erf], 1 dy * gelu'(x), 2 dropout (x * keep / (1 - p); the same call is its own backward on dy)
+__device__ __forceinline__ uint32_t hash_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+template <int MODE>
+__global__ void eltwise_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ y, long long n8, float p, uint32_t seed) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float xv[8], dv[8];
+  unpack8h(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
+  if (MODE == 1) unpack8h(__ldg(reinterpret_cast<const uint4*>(dy) + i), dv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (MODE == 0) xv[e] = gelu_erf_f(xv[e]);
+    if (MODE == 1) {
+      const float v = xv[e];
+      const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
+      xv[e] = dv[e] * (cdf + v * 0.3989422804014327f * __expf(-0.5f * v * v));
+    }
+    if (MODE == 2) {
+      const long long idx = i * 8 + e;
+      const uint32_t h = hash_u32(uint32_t(idx), uint32_t(idx >> 32), seed);
+      xv[e] = (float(h >> 8) * (1.f / 16777216.f) >= p) ? xv[e] / (1.f - p) : 0.f;
+    }
+  }
+  reinterpret_cast<uint4*>(y)[i] = pack8h(xv);
+}
+
+// LayerNorm backward, dx part (one warp per row, C <= 2048): dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma
+__global__ void ln_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const float* __restrict__ gamma, __half* __restrict__ dx,
+                              float* __restrict__ row_mean, float* __restrict__ row_rstd, long long rows, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nch = C >> 3;
+  float xv[8][8], gv[8][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < nch) {
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(x + row * C + ch * 8)), xv[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += xv[j][e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / float(C);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (lane + 32 * j < nch)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = xv[j][e] - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / float(C) + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < nch) {
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(dy + row * C + ch * 8)), gv[j]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        gv[j][e] *= gamma[ch * 8 + e];
+        xv[j][e] = (xv[j][e] - mean) * rstd;
+        sg += gv[j][e]; sgx += gv[j][e] * xv[j][e];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sgx += __shfl_xor_sync(0xffffffffu, sgx, o); }
+  sg /= float(C); sgx /= float(C);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < nch) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rstd * (gv[j][e] - sg - xv[j][e] * sgx);
+      *reinterpret_cast<uint4*>(dx + row * C + ch * 8) = pack8h(o);
+    }
+  }
+  if (lane == 0) { row_mean[row] = mean; row_rstd[row] = rstd; }
+}
+
+// nearest 2x up-sampling backward: dx[b, y, x] = sum of the 2x2 block of dy
+__global__ void upsample2x_bwd_kernel(const __half* __restrict__ dy, __half* __restrict__ dx, int B, int H, int W, int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * H * W * C8) return;
+  const int c = int(i % C8);
+  long long p = i / C8;
+  const int x = int(p % W);
+  p /= W;
+  const int y = int(p % H), b = int(p / H);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int dyy = 0; dyy < 2; ++dyy)
+    for (int dxx = 0; dxx < 2; ++dxx) {
+      float v[8];
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(dy + ((size_t(b) * 2 * H + 2 * y + dyy) * (2 * W) + 2 * x + dxx) * (C8 * 8) + c * 8)), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  reinterpret_cast<uint4*>(dx)[i] = pack8h(acc);
+}
+
+// MaxPool2d(5, 1, 2) backward (one stage of SPPF's chain): dx[q] = sum over the windows w containing q of dy[w] * [argmax_w == q],
+// argmax = first maximum in row-major window order (torch's max_pool2d_with_indices).  Gather form: deterministic.
+__global__ void maxpool5_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ dx, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * H * W * C) return;
+  const int c = int(i % C);
+  long long p = i / C;
+  const int qx = int(p % W);
+  p /= W;
+  const int qy = int(p % H), b = int(p / H);
+  const __half* xb = x + size_t(b) * H * W * C + c;
+  const __half* db = dy + size_t(b) * H * W * C + c;
+  const float xq = __half2float(xb[(size_t(qy) * W + qx) * C]);
+  float acc = 0.f;
+  for (int wy = max(qy - 2, 0); wy <= min(qy + 2, H - 1); ++wy)
+    for (int wx = max(qx - 2, 0); wx <= min(qx + 2, W - 1); ++wx) {
+      // is q the first maximum of the window centred at (wy, wx)?
+      bool win = true;
+      for (int yy = max(wy - 2, 0); yy <= min(wy + 2, H - 1) && win; ++yy)
+        for (int xx = max(wx - 2, 0); xx <= min(wx + 2, W - 1); ++xx) {
+          const float v = __half2float(xb[(size_t(yy) * W + xx) * C]);
+          const bool before = yy < qy || (yy == qy && xx < qx);
+          if (v > xq || (before && v == xq)) { win = false; break; }
+        }
+      if (win) acc += __half2float(db[(size_t(wy) * W + wx) * C]);
+    }
+  dx[i] = __float2half_rn(acc);
+}
+
+static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace icaf
+
+using namespace icaf;
+
+extern "C" size_t icaf_train_workspace_bytes(int C) { return size_t(kRedChunks) * 2 * (C > 0 ? C : 1) * sizeof(float); }
+
+extern "C" int icaf_bn_act_fwd(const void* x, const float* gamma, const float* beta, float* run_mean, float* run_var, void* y, float* save_mean,
+                               float* save_invstd, int64_t rows, int C, float eps, float momentum, int act, float* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (!x || !gamma || !beta || !y || !save_mean || !save_invstd || !workspace || rows < 1 || C < 8 || C % 8) return set_error(ICAF_ERR_BAD_ARG, "bn_act_fwd: bad argument");
+  if (workspace_bytes < icaf_train_workspace_bytes(C)) return set_error(ICAF_ERR_BAD_ARG, "bn_act_fwd: workspace too small (icaf_train_workspace_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_k(chan_partial_kernel<0>, dim3(nblk(C / 8, 32), kRedChunks), dim3(32, 8), 0, st, (const __half*)x, (const __half*)nullptr, (const float*)nullptr,
+           (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0);
+  if (int rc = check_launch("bn_act_fwd(stats)")) return rc;
+  launch_k(bn_finalize_kernel, dim3(nblk(C, 128)), dim3(128), 0, st, (const float*)workspace, save_mean, save_invstd, run_mean, run_var, C, (long long)rows, eps, momentum);
+  if (int rc = check_launch("bn_act_fwd(finalize)")) return rc;
+  const long long n8 = rows * (C / 8);
+  launch_k(affine_act_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, gamma, beta, (const float*)save_mean, (const float*)save_invstd, (__half*)y, n8, C / 8, act);
+  return check_launch("bn_act_fwd");
+}
+
+extern "C" int icaf_bn_act_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                               void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int act, float grad_scale, int accumulate, float* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!x || !dy || !gamma || !beta || !save_mean || !save_invstd || !dx || !workspace || rows < 1 || C < 8 || C % 8) return set_error(ICAF_ERR_BAD_ARG, "bn_act_bwd: bad argument");
+  if (workspace_bytes < icaf_train_workspace_bytes(C) + 2 * size_t(C) * sizeof(float)) return set_error(ICAF_ERR_BAD_ARG, "bn_act_bwd: workspace too small (icaf_train_workspace_bytes + 2 C floats)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* sums = workspace + size_t(kRedChunks) * 2 * C;     // [2][C]: S1 = sum dz, S2 = sum dz xhat
+  launch_k(chan_partial_kernel<1>, dim3(nblk(C / 8, 32), kRedChunks), dim3(32, 8), 0, st, (const __half*)x, (const __half*)dy, gamma, beta, save_mean, save_invstd,
+           workspace, (long long)rows, C, act);
+  if (int rc = check_launch("bn_act_bwd(partial)")) return rc;
+  launch_k(chan_final_kernel, dim3(nblk(C, 128)), dim3(128), 0, st, (const float*)workspace, sums, sums + C, C, 1.0f, 0);
+  if (int rc = check_launch("bn_act_bwd(sums)")) return rc;
+  if (dgamma || dbeta) {                                    // parameter gradients: dbeta = S1, dgamma = S2 (unscaled by the loss scale)
+    launch_k(chan_final_kernel, dim3(nblk(C, 128)), dim3(128), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate);
+    if (int rc = check_launch("bn_act_bwd(param grads)")) return rc;
+  }
+  const long long n8 = rows * (C / 8);
+  launch_k(bn_bwd_apply_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, gamma, beta, save_mean, save_invstd, (const float*)sums,
+           (__half*)dx, n8, C / 8, 1.0f / float(rows), act);
+  return check_launch("bn_act_bwd");
+}
+
+// mode 0: y = gelu(x); 1: y = dy * gelu'(x); 2: y = dropout(x; p, seed) (apply it to dy with the same seed for the backward)
+extern "C" int icaf_eltwise(int mode, const void* x, const void* dy, void* y, int64_t n, float p, uint32_t seed, void* stream) {
+  if (!x || !y || n < 0 || n % 8 || (mode == 1 && !dy) || mode < 0 || mode > 2 || (mode == 2 && !(p >= 0.f && p < 1.f))) return set_error(ICAF_ERR_BAD_ARG, "eltwise: bad argument");
+  if (n == 0) return ICAF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n8 = n / 8;
+  if (mode == 0) launch_k(eltwise_kernel<0>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed);
+  else if (mode == 1) launch_k(eltwise_kernel<1>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed);
+  else launch_k(eltwise_kernel<2>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed);
+  return check_launch("eltwise");
+}
+
+extern "C" int icaf_layernorm_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, float eps,
+                                  float grad_scale, int accumulate, float* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !dy || !gamma || !dx || !workspace || rows < 1 || C % 8 || C > 2048) return set_error(ICAF_ERR_BAD_ARG, "layernorm_bwd: bad argument (C % 8, C <= 2048)");
+  if (workspace_bytes < icaf_train_workspace_bytes(C) + 2 * size_t(rows) * sizeof(float)) return set_error(ICAF_ERR_BAD_ARG, "layernorm_bwd: workspace too small (icaf_train_workspace_bytes + 2 rows floats)");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* rmean = workspace + size_t(kRedChunks) * 2 * C;
+  float* rrstd = rmean + rows;
+  launch_k(ln_bwd_kernel, dim3(nblk(rows, 4)), dim3(128), 0, st, (const __half*)x, (const __half*)dy, gamma, (__half*)dx, rmean, rrstd, (long long)rows, C, eps);
+  if (int rc = check_launch("layernorm_bwd(dx)")) return rc;
+  if (dgamma || dbeta) {
+    launch_k(chan_partial_kernel<2>, dim3(nblk(C / 8, 32), kRedChunks), dim3(32, 8), 0, st, (const __half*)x, (const __half*)dy, (const float*)nullptr, (const float*)nullptr,
+             (const float*)rmean, (const float*)rrstd, workspace, (long long)rows, C, 0);
+    if (int rc = check_launch("layernorm_bwd(partial)")) return rc;
+    launch_k(chan_final_kernel, dim3(nblk(C, 128)), dim3(128), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate);
+    if (int rc = check_launch("layernorm_bwd(param grads)")) return rc;
+  }
+  return ICAF_OK;
+}
+
+// out[0] = (accumulate ? out[0] : 0) + scale * <x, y> over (rows, C) fp16 matrices (gradients of the scalar gains)
+extern "C" int icaf_dot(const void* x, const void* y, int64_t rows, int C, float* out, float scale, int accumulate, float* workspace, size_t workspace_bytes,
+                        void* stream) {
+  if (!x || !y || !out || !workspace || rows < 1 || C < 8 || C % 8) return set_error(ICAF_ERR_BAD_ARG, "dot: bad argument");
+  if (workspace_bytes < icaf_train_workspace_bytes(C)) return set_error(ICAF_ERR_BAD_ARG, "dot: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_k(chan_partial_kernel<3>, dim3(nblk(C / 8, 32), kRedChunks), dim3(32, 8), 0, st, (const __half*)x, (const __half*)y, (const float*)nullptr, (const float*)nullptr,
+           (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0);
+  if (int rc = check_launch("dot(partial)")) return rc;
+  launch_k(scalar_final_kernel, dim3(1), dim3(256), 0, st, (const float*)workspace, out, C, scale, accumulate);
+  return check_launch("dot");
+}
+
+extern "C" int icaf_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, void* stream) {
+  if (!dy || !dx || C % 8) return set_error(ICAF_ERR_BAD_ARG, "upsample2x_bwd: bad argument");
+  launch_k(upsample2x_bwd_kernel, dim3(nblk((long long)B * H * W * (C / 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)dy, (__half*)dx, B, H, W, C / 8);
+  return check_launch("upsample2x_bwd");
+}
+
+extern "C" int icaf_maxpool5_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream) {
+  if (!x || !dy || !dx) return set_error(ICAF_ERR_BAD_ARG, "maxpool5_bwd: null pointer");
+  launch_k(maxpool5_bwd_kernel, dim3(nblk((long long)B * H * W * C, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, (const __half*)dy, (__half*)dx, B, H, W, C);
+  return check_launch("maxpool5_bwd");
+}

@@ -599,3 +599,85 @@ def colsum(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = No
     _call("icaf_colsum", _lib.lib().icaf_colsum, (_ptr(x), rows, Cc, _ptr(out), float(scale), int(acc), _ptr(ws), C.c_size_t(ws.numel() * 4)),
           {"bytes": 2.0 * x.numel()})
     return out
+
+
+def _train_ws(Cc: int, extra_floats: int, device) -> torch.Tensor:
+    need = int(_lib.lib().icaf_train_workspace_bytes(Cc)) // 4 + extra_floats
+    return torch.empty(need, dtype=torch.float32, device=device)
+
+
+def bn_act_fwd(x: torch.Tensor, gamma, beta, run_mean, run_var, eps: float, momentum: float, act: int):
+    """Training-mode BatchNorm2d + activation on a dense fp16 NHWC map: -> (y, save_mean, save_invstd)."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    assert x.is_contiguous() and x.dtype == torch.float16
+    y = torch.empty_like(x)
+    sm = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    si = torch.empty_like(sm)
+    ws = _train_ws(Cc, 0, x.device)
+    _call("icaf_bn_act_fwd", _lib.lib().icaf_bn_act_fwd,
+          (_ptr(x), _ptr(gamma), _ptr(beta), _ptr(run_mean), _ptr(run_var), _ptr(y), _ptr(sm), _ptr(si), rows, Cc, float(eps), float(momentum), int(act),
+           _ptr(ws), C.c_size_t(ws.numel() * 4)), {"bytes": 6.0 * x.numel()})
+    return y, sm, si
+
+
+def bn_act_bwd(x, dy, gamma, beta, sm, si, act: int, dgamma=None, dbeta=None, grad_scale: float = 1.0, accumulate: bool = False):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    ws = _train_ws(Cc, 2 * Cc, x.device)
+    _call("icaf_bn_act_bwd", _lib.lib().icaf_bn_act_bwd,
+          (_ptr(x), _ptr(dy), _ptr(gamma), _ptr(beta), _ptr(sm), _ptr(si), _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, Cc, int(act), float(grad_scale),
+           int(accumulate), _ptr(ws), C.c_size_t(ws.numel() * 4)), {"bytes": 10.0 * x.numel()})
+    return dx
+
+
+def eltwise(mode: int, x, dy=None, p: float = 0.0, seed: int = 0):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _call("icaf_eltwise", _lib.lib().icaf_eltwise, (int(mode), _ptr(x), _ptr(None if dy is None else dy.contiguous()), _ptr(y), x.numel(), float(p), C.c_uint32(seed & 0xFFFFFFFF)),
+          {"bytes": 4.0 * x.numel()})
+    return y
+
+
+def layernorm_bwd(x, dy, gamma, eps: float, dgamma=None, dbeta=None, grad_scale: float = 1.0, accumulate: bool = False):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    ws = _train_ws(Cc, 2 * rows, x.device)
+    _call("icaf_layernorm_bwd", _lib.lib().icaf_layernorm_bwd,
+          (_ptr(x), _ptr(dy), _ptr(gamma), _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, Cc, float(eps), float(grad_scale), int(accumulate), _ptr(ws),
+           C.c_size_t(ws.numel() * 4)), {"bytes": 8.0 * x.numel()})
+    return dx
+
+
+def dot(x, y, out: Optional[torch.Tensor] = None, scale: float = 1.0):
+    """<x, y> (fp32, one element) of equally shaped fp16 tensors; accumulates into `out` when given."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    x, y = x.contiguous(), y.contiguous()
+    acc = out is not None
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = _train_ws(Cc, 0, x.device)
+    _call("icaf_dot", _lib.lib().icaf_dot, (_ptr(x), _ptr(y), rows, Cc, _ptr(out), float(scale), int(acc), _ptr(ws), C.c_size_t(ws.numel() * 4)),
+          {"bytes": 4.0 * x.numel()})
+    return out
+
+
+def upsample2x_bwd(dy):
+    B, H2, W2, Cc = dy.shape
+    dy = dy.contiguous()
+    dx = torch.empty(B, H2 // 2, W2 // 2, Cc, dtype=torch.float16, device=dy.device)
+    _call("icaf_upsample2x_bwd", _lib.lib().icaf_upsample2x_bwd, (_ptr(dy), _ptr(dx), B, H2 // 2, W2 // 2, Cc), {"bytes": 2.5 * dy.numel()})
+    return dx
+
+
+def maxpool5_bwd(x, dy):
+    B, H, W, Cc = x.shape
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    _call("icaf_maxpool5_bwd", _lib.lib().icaf_maxpool5_bwd, (_ptr(x), _ptr(dy), _ptr(dx), B, H, W, Cc), {"bytes": 6.0 * x.numel()})
+    return dx

@@ -263,6 +263,34 @@ int icaf_zero_stuff2(const void* x, void* y, int B, int H, int W, int C, int H2,
 int icaf_colsum(const void* x, int64_t rows, int C, float* out, float scale, int accumulate, float* workspace, size_t workspace_bytes,
                 void* stream);
 
+/* Reduction scratch of the kernels below: icaf_train_workspace_bytes(C) bytes (fp32, 16-byte aligned), plus what each states. */
+size_t icaf_train_workspace_bytes(int C);
+/* BatchNorm2d with BATCH statistics + activation (Conv.forward in training mode, models/common.py:56-57; act: 0 none, 1 SiLU):
+ * x, y: dense fp16 (rows, C) = NHWC maps; statistics in fp32 over the rows; run_mean / run_var (may be NULL) get the momentum
+ * update with the unbiased variance like nn.BatchNorm2d; save_mean / save_invstd (fp32 [C]) feed the backward. */
+int icaf_bn_act_fwd(const void* x, const float* gamma, const float* beta, float* run_mean, float* run_var, void* y, float* save_mean,
+                    float* save_invstd, int64_t rows, int C, float eps, float momentum, int act, float* workspace, size_t workspace_bytes,
+                    void* stream);
+/* Its backward: dx (fp16) and dgamma / dbeta (fp32, (accumulate ? += : =) grad_scale * value; may be NULL).
+ * workspace: icaf_train_workspace_bytes(C) + 2 C floats. */
+int icaf_bn_act_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                    void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int act, float grad_scale, int accumulate, float* workspace,
+                    size_t workspace_bytes, void* stream);
+/* Element-wise over n fp16 values (n % 8 == 0): mode 0 y = GELU_erf(x) (common.py:706); 1 y = dy * GELU'(x);
+ * 2 y = dropout(x, p) with a counter-based mask keyed by (element index, seed) -- calling it on dy with the same seed is the backward. */
+int icaf_eltwise(int mode, const void* x, const void* dy, void* y, int64_t n, float p, uint32_t seed, void* stream);
+/* nn.LayerNorm backward over dense fp16 (rows, C), C <= 2048: dx, dgamma, dbeta as above.
+ * workspace: icaf_train_workspace_bytes(C) + 2 rows floats. */
+int icaf_layernorm_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, float eps,
+                       float grad_scale, int accumulate, float* workspace, size_t workspace_bytes, void* stream);
+/* out[0] = (accumulate ? out[0] : 0) + scale * <x, y> over dense fp16 (rows, C): gradients of LearnableCoefficient / LearnableWeights. */
+int icaf_dot(const void* x, const void* y, int64_t rows, int C, float* out, float scale, int accumulate, float* workspace, size_t workspace_bytes,
+             void* stream);
+/* Backward of nn.Upsample(None, 2, 'nearest'): dx (B, H, W, C) = sums of the 2 x 2 blocks of dy (B, 2H, 2W, C). */
+int icaf_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+/* Backward of one MaxPool2d(5, 1, 2) of SPPF's chain (common.py:259-266): x is that pool's input, dy the gradient of its output. */
+int icaf_maxpool5_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+
 /* out = a[0] * x (+ b[0] * y when y != NULL) over n fp16 elements (n % 8 == 0, 16-byte aligned); a, b device fp32 scalars.
  * LearnableCoefficient.forward / LearnableWeights.forward called stand-alone (models/common.py:569-587). */
 int icaf_axpby(const void* x, const void* y, const float* a, const float* b, void* out, int64_t n, void* stream);
