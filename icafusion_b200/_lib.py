@@ -82,6 +82,9 @@ SIGNATURES = {
     "icaf_dot": [_vp, _vp, _i64, _i, _vp, _f, _i, _vp, C.c_size_t, _vp],
     "icaf_upsample2x_bwd": [_vp, _vp, _i, _i, _i, _i, _vp],
     "icaf_maxpool5_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "icaf_cross_attention_train": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, C.c_uint32, _vp],
+    "icaf_cross_attention_bwd_workspace_bytes": [_i, _i, _i],
+    "icaf_cross_attention_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, C.c_uint32, _vp, C.c_size_t, _vp],
     "icaf_axpby": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "icaf_detect_decode": [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, C.POINTER(C.c_float), _vp],
 }
@@ -106,7 +109,8 @@ def lib() -> C.CDLL:
             fn.argtypes = argtypes
             fn.restype = {"icaf_last_error": C.c_char_p, "icaf_kernel_launches": C.c_longlong,
                           "icaf_nms_workspace_bytes": C.c_size_t, "icaf_loss_workspace_bytes": C.c_size_t,
-                          "icaf_conv2d_wgrad_workspace_bytes": C.c_size_t, "icaf_train_workspace_bytes": C.c_size_t}.get(name, C.c_int)
+                          "icaf_conv2d_wgrad_workspace_bytes": C.c_size_t, "icaf_train_workspace_bytes": C.c_size_t,
+                          "icaf_cross_attention_bwd_workspace_bytes": C.c_size_t}.get(name, C.c_int)
         _lib = L
     return _lib
 

@@ -25,6 +25,8 @@ struct AttnParams {
   __half* out[2];
   int B, N, n_pad, C, heads;
   int ld;                // row pitch of qk: 2C, or 3C in the fused-qkv form ([q | k | v])
+  float p_drop;          // training forward only (TRAIN instantiation): dropout on the probabilities (common.py:677,680)
+  uint32_t seed;
   float scale_log2;      // log2(e) / sqrt(d)
 };
 
@@ -81,7 +83,9 @@ __device__ __forceinline__ float fast_exp2_t(float x) {
   return y;
 }
 
-template <int D, bool VF>
+// TRAIN: dropout on the attention probabilities (the row sum still runs over the un-dropped values, like
+// `att = softmax(..); att = attn_drop(att)`); its own instantiation, so the inference kernels keep their size.
+template <int D, bool VF, bool TRAIN = false>
 __global__ void __launch_bounds__(192, AttnCfg<D>::kCtas) cross_attn_tma_kernel(const AttnParams P, const __grid_constant__ AttnMaps M) {
   constexpr int kKV = AttnCfg<D>::kKV;
   using L = AttnSmemT<D, kKV>;
@@ -175,9 +179,14 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::kCtas) cross_attn_tma_kernel(
           for (int i = 0; i < 32; i += 2) {
             const float p0 = fast_exp2_t(fmaf(__uint_as_float(r[i]), sl2, -moff));
             const float p1 = fast_exp2_t(fmaf(__uint_as_float(r[i + 1]), sl2, -moff));
-            const __half2 h = __floats2half2_rn(p0, p1);
+            __half2 h = __floats2half2_rn(p0, p1);
             const float2 hf = __half22float2(h);            // sum what the PV MMA will actually see
             rs += hf.x + hf.y;
+            if (TRAIN) {
+              const float ks = 1.f / (1.f - P.p_drop);
+              const bool k0 = attn_keep(P.seed, dir, blockIdx.y, qn, kv0 + cb + i, P.p_drop), k1 = attn_keep(P.seed, dir, blockIdx.y, qn, kv0 + cb + i + 1, P.p_drop);
+              h = __floats2half2_rn(k0 ? hf.x * ks : 0.f, k1 ? hf.y * ks : 0.f);
+            }
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           }
         } else {
@@ -185,9 +194,14 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::kCtas) cross_attn_tma_kernel(
           for (int i = 0; i < 32; i += 2) {
             const float p0 = (kv0 + cb + i < N) ? fast_exp2_t(fmaf(__uint_as_float(r[i]), sl2, -moff)) : 0.f;
             const float p1 = (kv0 + cb + i + 1 < N) ? fast_exp2_t(fmaf(__uint_as_float(r[i + 1]), sl2, -moff)) : 0.f;
-            const __half2 h = __floats2half2_rn(p0, p1);
+            __half2 h = __floats2half2_rn(p0, p1);
             const float2 hf = __half22float2(h);
             rs += hf.x + hf.y;
+            if (TRAIN) {
+              const float ks = 1.f / (1.f - P.p_drop);
+              const bool k0 = attn_keep(P.seed, dir, blockIdx.y, qn, kv0 + cb + i, P.p_drop), k1 = attn_keep(P.seed, dir, blockIdx.y, qn, kv0 + cb + i + 1, P.p_drop);
+              h = __floats2half2_rn(k0 ? hf.x * ks : 0.f, k1 ? hf.y * ks : 0.f);
+            }
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           }
         }
@@ -370,16 +384,17 @@ static int fill_attn(const void* qk_vis, const void* qk_ir, const void* vt_vis, 
   P.out[0] = (__half*)out_vis; P.out[1] = (__half*)out_ir;
   P.B = B; P.N = N; P.n_pad = n_pad; P.C = C; P.heads = heads;
   P.ld = vt_vis ? 2 * C : 3 * C;
+  P.p_drop = 0.f; P.seed = 0u;
   P.scale_log2 = 1.4426950408889634f / sqrtf(float(d));   // 1/sqrt(d_k), common.py:670
   return ICAF_OK;
 }
 
-template <int D, bool VF>
+template <int D, bool VF, bool TRAIN = false>
 static int launch_attn_tma(const AttnParams& P, cudaStream_t st) {
   constexpr int kKV = AttnCfg<D>::kKV;
   using L = AttnSmemT<D, kKV>;
   static bool configured[kMaxDevices] = {false};
-  if (int rc = configure_smem(cross_attn_tma_kernel<D, VF>, L::kTotal, configured, "cross_attention: cudaFuncSetAttribute")) return rc;
+  if (int rc = configure_smem(cross_attn_tma_kernel<D, VF, TRAIN>, L::kTotal, configured, "cross_attention: cudaFuncSetAttribute")) return rc;
   AttnMaps maps;
   memset(&maps, 0, sizeof(maps));
   const uint64_t rows = uint64_t(P.B) * P.n_pad;
@@ -394,7 +409,7 @@ static int launch_attn_tma(const AttnParams& P, cudaStream_t st) {
     }
   }
   dim3 grid((P.n_pad + kQT - 1) / kQT, P.B * P.heads, 2);
-  launch_k(cross_attn_tma_kernel<D, VF>, dim3(grid), dim3(192), L::kTotal, st, P, maps);
+  launch_k(cross_attn_tma_kernel<D, VF, TRAIN>, dim3(grid), dim3(192), L::kTotal, st, P, maps);
   return check_launch("cross_attention");
 }
 
@@ -422,6 +437,25 @@ extern "C" int icaf_cross_attention(const void* qk_vis, const void* qk_ir, const
       (reinterpret_cast<uintptr_t>(vt_ir) & 15) || (reinterpret_cast<uintptr_t>(qk_ir) & 15))
     return set_error(ICAF_ERR_BAD_ARG, "cross_attention: TMA needs 16-byte aligned tensors and row pitches");
   return vt_vis ? dispatch_attn<false>(P, st) : dispatch_attn<true>(P, st);
+}
+
+extern "C" int icaf_cross_attention_train(const void* qkv_vis, const void* qkv_ir, void* out_vis, void* out_ir, int B, int N, int n_pad, int C, int heads,
+                                          float p_drop, uint32_t seed, void* stream) {
+  AttnParams P;
+  int rc = fill_attn(qkv_vis, qkv_ir, nullptr, nullptr, out_vis, out_ir, B, N, n_pad, C, heads, P);
+  if (rc) return rc;
+  if (!(p_drop >= 0.f && p_drop < 1.f)) return set_error(ICAF_ERR_BAD_ARG, "cross_attention_train: dropout probability must be in [0, 1)");
+  if ((uint64_t(B) * n_pad * 2) % 16 || (reinterpret_cast<uintptr_t>(qkv_vis) & 15) || (reinterpret_cast<uintptr_t>(qkv_ir) & 15))
+    return set_error(ICAF_ERR_BAD_ARG, "cross_attention_train: TMA needs 16-byte aligned tensors and row pitches");
+  P.p_drop = p_drop; P.seed = seed;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p_drop == 0.f) return dispatch_attn<true>(P, st);
+  switch (C / heads) {
+    case 16: return launch_attn_tma<16, true, true>(P, st);
+    case 32: return launch_attn_tma<32, true, true>(P, st);
+    case 64: return launch_attn_tma<64, true, true>(P, st);
+    default: return launch_attn_tma<128, true, true>(P, st);
+  }
 }
 
 extern "C" int icaf_cross_attention_simt(const void* qk_vis, const void* qk_ir, const void* vt_vis, const void* vt_ir,

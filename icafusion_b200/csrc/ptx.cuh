@@ -251,6 +251,18 @@ __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t (&o)[8])
                "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "l"(p));
 }
 
+// ------------------------------------------------------------------ counter-based dropout mask of the attention probabilities
+// keep(dir, batch*head, query, key): the training forward (attn.cu) and the backward (attn_bwd.cu) regenerate the same mask.
+__device__ __forceinline__ uint32_t attn_hash(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+__device__ __forceinline__ bool attn_keep(uint32_t seed, int dir, int bh, int q, int k, float p) {
+  const uint32_t h = attn_hash(uint32_t(q) * 65536u + uint32_t(k & 0xffff), uint32_t(bh) * 2u + uint32_t(dir) + (uint32_t(k) >> 16) * 0x10001u, seed);
+  return float(h >> 8) * (1.f / 16777216.f) >= p;
+}
+
 // ------------------------------------------------------------------ small math helpers
 // x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (rel. error ~1e-6, far below the fp16 output rounding)
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }

@@ -446,6 +446,45 @@ def cross_attention(qk_vis, qk_ir, vt_vis, vt_ir, B: int, N: int, n_pad: int, Cc
     return out_v, out_i
 
 
+def cross_attention_train(qkv_vis, qkv_ir, B: int, N: int, n_pad: int, Cc: int, heads: int, p_drop: float = 0.0, seed: int = 0):
+    """Training-mode forward of the fused cross-attention: dropout p_drop on the probabilities (common.py:677,680), mask keyed
+    by `seed` so that cross_attention_bwd regenerates it."""
+    want = (B, n_pad, 3 * Cc)
+    for t in (qkv_vis, qkv_ir):
+        assert t.is_contiguous() and t.dtype == torch.float16
+        if tuple(t.shape) != want:
+            raise ValueError(f"cross_attention_train: projection tensors must be {want}, got {tuple(t.shape)}")
+    out_v = torch.empty(B, n_pad, Cc, dtype=torch.float16, device=qkv_vis.device)
+    out_i = torch.empty_like(out_v)
+    _call("icaf_cross_attention_train", _lib.lib().icaf_cross_attention_train,
+          (_ptr(qkv_vis), _ptr(qkv_ir), _ptr(out_v), _ptr(out_i), B, N, n_pad, Cc, heads, float(p_drop), int(seed) & 0xffffffff),
+          {"flops": 8.0 * B * N * N * Cc, "bytes": 2.0 * 2 * 4 * B * n_pad * Cc})
+    return out_v, out_i
+
+
+def cross_attention_bwd(qkv_vis, qkv_ir, out_vis, out_ir, dout_vis, dout_ir, B: int, N: int, n_pad: int, Cc: int, heads: int,
+                        p_drop: float = 0.0, seed: int = 0):
+    """Gradients of the fused cross-attention w.r.t. the two [q|k|v] projection tensors (probabilities recomputed)."""
+    want = (B, n_pad, 3 * Cc)
+    for t in (qkv_vis, qkv_ir):
+        assert t.is_contiguous() and t.dtype == torch.float16
+        if tuple(t.shape) != want:
+            raise ValueError(f"cross_attention_bwd: projection tensors must be {want}, got {tuple(t.shape)}")
+    for t in (out_vis, out_ir, dout_vis, dout_ir):
+        assert t.is_contiguous() and t.dtype == torch.float16
+        if tuple(t.shape) != (B, n_pad, Cc):
+            raise ValueError(f"cross_attention_bwd: outputs / output gradients must be {(B, n_pad, Cc)}, got {tuple(t.shape)}")
+    dq_v = torch.empty_like(qkv_vis)
+    dq_i = torch.empty_like(qkv_ir)
+    nb = _lib.lib().icaf_cross_attention_bwd_workspace_bytes(B, n_pad, heads)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=qkv_vis.device)
+    _call("icaf_cross_attention_bwd", _lib.lib().icaf_cross_attention_bwd,
+          (_ptr(qkv_vis), _ptr(qkv_ir), _ptr(out_vis), _ptr(out_ir), _ptr(dout_vis), _ptr(dout_ir), _ptr(dq_v), _ptr(dq_i),
+           B, N, n_pad, Cc, heads, float(p_drop), int(seed) & 0xffffffff, _ptr(ws), nb),
+          {"flops": 20.0 * B * N * N * Cc, "bytes": 2.0 * 2 * 9 * B * n_pad * Cc})
+    return dq_v, dq_i
+
+
 def dmff_upsample_cat(tok_vis, tok_ir, x_vis, x_ir, nh: int, nw: int, mode: int = 0) -> torch.Tensor:
     B, H, W, Cc = x_vis.shape
     out = torch.empty(B, H, W, 2 * Cc, dtype=torch.float16, device=x_vis.device)

@@ -291,6 +291,21 @@ int icaf_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, vo
 /* Backward of one MaxPool2d(5, 1, 2) of SPPF's chain (common.py:259-266): x is that pool's input, dy the gradient of its output. */
 int icaf_maxpool5_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
 
+/* Training-mode forward of the fused form: like icaf_cross_attention(qkv_vis, qkv_ir, NULL, NULL, ...) plus dropout with
+ * probability p_drop on the attention probabilities (common.py:677,680; counter-based mask keyed by `seed`, reproduced by the
+ * backward below). */
+int icaf_cross_attention_train(const void* qkv_vis, const void* qkv_ir, void* out_vis, void* out_ir, int B, int N, int n_pad, int C, int heads,
+                               float p_drop, uint32_t seed, void* stream);
+
+/* Backward of icaf_cross_attention in its fused form (qkv_* fp16 (B, Npad, 3C) rows [q | k | v]; out_* the forward outputs,
+ * dout_* their gradients, fp16 (B, Npad, C)): dqkv_* (same layout as qkv_*; pad rows zeroed).  Probabilities are recomputed;
+ * p_drop / seed reproduce the dropout mask of a training forward (0 = none).  CUDA-core kernels for the pooled-token regime.
+ * workspace: icaf_cross_attention_bwd_workspace_bytes(B, n_pad, heads). */
+size_t icaf_cross_attention_bwd_workspace_bytes(int B, int n_pad, int heads);
+int icaf_cross_attention_bwd(const void* qkv_vis, const void* qkv_ir, const void* out_vis, const void* out_ir, const void* dout_vis,
+                             const void* dout_ir, void* dqkv_vis, void* dqkv_ir, int B, int N, int n_pad, int C, int heads, float p_drop,
+                             uint32_t seed, void* workspace, size_t workspace_bytes, void* stream);
+
 /* out = a[0] * x (+ b[0] * y when y != NULL) over n fp16 elements (n % 8 == 0, 16-byte aligned); a, b device fp32 scalars.
  * LearnableCoefficient.forward / LearnableWeights.forward called stand-alone (models/common.py:569-587). */
 int icaf_axpby(const void* x, const void* y, const float* a, const float* b, void* out, int64_t n, void* stream);

@@ -122,3 +122,75 @@ def test_small_training_kernels(cuda_device):
     a, b2, c2 = ops.eltwise(2, ones, p=0.1, seed=7), ops.eltwise(2, ones, p=0.1, seed=7), ops.eltwise(2, ones, p=0.1, seed=8)
     keep = float((a > 0).float().mean())
     assert torch.equal(a, b2) and not torch.equal(a, c2) and abs(keep - 0.9) < 0.01 and abs(float(a.max()) - 1 / 0.9) < 1e-3
+
+
+def _attn_ref(qkv_q, qkv_kv, N, C, h, mask=None, p=0.0):
+    """One direction of the cross-attention (common.py:670-684) with autograd; mask (B, h, N, N) = kept probabilities."""
+    B = qkv_q.shape[0]
+    d = C // h
+    q = qkv_q[:, :N, :C].reshape(B, N, h, d).permute(0, 2, 1, 3)
+    k = qkv_kv[:, :N, C:2 * C].reshape(B, N, h, d).permute(0, 2, 1, 3)
+    v = qkv_kv[:, :N, 2 * C:].reshape(B, N, h, d).permute(0, 2, 1, 3)
+    att = torch.softmax(q @ k.transpose(-1, -2) / d ** 0.5, -1)
+    if mask is not None:
+        att = att * mask / (1 - p)
+    return (att @ v).permute(0, 2, 1, 3).reshape(B, N, C)
+
+
+@pytest.mark.parametrize("B,N,C,h", [(2, 100, 128, 8), (1, 333, 256, 8), (1, 200, 512, 8), (1, 150, 1024, 8), (2, 77, 64, 4)])
+def test_cross_attention_backward(cuda_device, B, N, C, h):
+    """dq, dk, dv of both directions against torch autograd (fp32 on the same fp16 operands), eval (no dropout)."""
+    from icafusion_b200 import ops
+    n_pad = ops.round_up(N, 8)
+    g = torch.Generator().manual_seed(N + C)
+    qv, qi = torch.randn(B, n_pad, 3 * C, generator=g).half(), torch.randn(B, n_pad, 3 * C, generator=g).half()
+    dov, doi = (torch.randn(B, n_pad, C, generator=g) * 0.1).half(), (torch.randn(B, n_pad, C, generator=g) * 0.1).half()
+    rv, ri = qv.float().requires_grad_(True), qi.float().requires_grad_(True)
+    o_v, o_i = _attn_ref(ri, rv, N, C, h), _attn_ref(rv, ri, N, C, h)     # RGB output: IR queries on RGB keys/values
+    (o_v * dov[:, :N].float()).sum().backward(retain_graph=True)
+    (o_i * doi[:, :N].float()).sum().backward()
+    dev = [t.to(cuda_device) for t in (qv, qi)]
+    out_v, out_i = ops.cross_attention_train(*dev, B, N, n_pad, C, h)
+    dq_v, dq_i = ops.cross_attention_bwd(*dev, out_v, out_i, dov.to(cuda_device), doi.to(cuda_device), B, N, n_pad, C, h)
+    torch.cuda.synchronize()
+    e_o = max(err(out_v[:, :N], o_v.detach()), err(out_i[:, :N], o_i.detach()))
+    e_g = max(err(dq_v[:, :N], rv.grad[:, :N]), err(dq_i[:, :N], ri.grad[:, :N]))
+    print(f"\n[attention bwd B{B} N{N} C{C} d{C // h}] out {e_o:.2e}  dqkv {e_g:.2e}")
+    assert e_o < 1e-3 and e_g < 2e-3
+    if n_pad > N:
+        assert float(dq_v[:, N:].abs().max()) == 0 and float(dq_i[:, N:].abs().max()) == 0
+
+
+def test_cross_attention_dropout(cuda_device):
+    """Attention dropout: the mask is read back through identity values, then the dropped forward and its backward are checked
+    against autograd with that mask; the keep rate and seed behaviour are checked too."""
+    from icafusion_b200 import ops
+    B, N, C, h, p, seed = 2, 64, 256, 4, 0.25, 1234
+    d, n_pad = C // h, 64
+    g = torch.Generator().manual_seed(3)
+    qv, qi = torch.randn(B, n_pad, 3 * C, generator=g).half(), torch.randn(B, n_pad, 3 * C, generator=g).half()
+    qv[:, :, :2 * C] *= 0.3
+    qi[:, :, :2 * C] *= 0.3                                   # flat-ish rows: every probability stays well above fp16 zero
+    eye = torch.eye(N).reshape(1, N, 1, d).expand(B, N, h, d).reshape(B, N, C).half()     # v[key, head, c] = (key == c)
+    pv, pi = qv.clone(), qi.clone()
+    pv[:, :, 2 * C:], pi[:, :, 2 * C:] = eye, eye
+    m_v, m_i = ops.cross_attention_train(pv.to(cuda_device), pi.to(cuda_device), B, N, n_pad, C, h, p, seed)
+    mask_v = (m_v.cpu().reshape(B, N, h, d).permute(0, 2, 1, 3) > 0).float()              # (B, h, q, key)
+    mask_i = (m_i.cpu().reshape(B, N, h, d).permute(0, 2, 1, 3) > 0).float()
+    keep = float(torch.cat([mask_v, mask_i]).mean())
+    assert abs(keep - (1 - p)) < 0.02 and not torch.equal(mask_v, mask_i)
+    m2, _ = ops.cross_attention_train(pv.to(cuda_device), pi.to(cuda_device), B, N, n_pad, C, h, p, seed + 1)
+    assert not torch.equal(m2, m_v)
+    dov, doi = (torch.randn(B, n_pad, C, generator=g) * 0.1).half(), (torch.randn(B, n_pad, C, generator=g) * 0.1).half()
+    rv, ri = qv.float().requires_grad_(True), qi.float().requires_grad_(True)
+    o_v, o_i = _attn_ref(ri, rv, N, C, h, mask_v, p), _attn_ref(rv, ri, N, C, h, mask_i, p)
+    (o_v * dov.float()).sum().backward(retain_graph=True)
+    (o_i * doi.float()).sum().backward()
+    dev = [t.to(cuda_device) for t in (qv, qi)]
+    out_v, out_i = ops.cross_attention_train(*dev, B, N, n_pad, C, h, p, seed)
+    dq_v, dq_i = ops.cross_attention_bwd(*dev, out_v, out_i, dov.to(cuda_device), doi.to(cuda_device), B, N, n_pad, C, h, p, seed)
+    torch.cuda.synchronize()
+    e_o = max(err(out_v, o_v.detach()), err(out_i, o_i.detach()))
+    e_g = max(err(dq_v, rv.grad), err(dq_i, ri.grad))
+    print(f"\n[attention dropout p{p}] keep {keep:.3f}  out {e_o:.2e}  dqkv {e_g:.2e}")
+    assert e_o < 1.5e-3 and e_g < 2e-3
