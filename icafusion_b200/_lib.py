@@ -67,9 +67,11 @@ SIGNATURES = {
     "icaf_dmff_upsample_cat": [_vp, _vp, _i, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp],
     "icaf_nms_workspace_bytes": [_i, _i],
     "icaf_nms": [_vp, _i, _i, _i, _f, _f, _i, C.c_uint64, _i, _vp, _vp, _vp, C.c_size_t, _vp],
-    "icaf_loss_workspace_bytes": [_i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i],
-    "icaf_compute_loss_fwd": [C.POINTER(C.c_void_p), _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _i, _i, _i, _vp, _i,
+    "icaf_loss_workspace_bytes": [_i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _i],
+    "icaf_compute_loss_fwd": [C.POINTER(C.c_void_p), _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _i, _i, _i, _vp, _i,
                               C.POINTER(C.c_float), C.POINTER(LossHyp), _vp, _vp, C.c_size_t, _vp],
+    "icaf_compute_loss_bwd": [C.POINTER(C.c_void_p), _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), _i, _i, _i, _i, _vp, _i,
+                              C.POINTER(C.c_float), C.POINTER(LossHyp), _vp, C.POINTER(C.c_void_p), _vp, C.c_size_t, _vp],
     "icaf_conv2d_wgrad_workspace_bytes": [C.POINTER(ConvGeom)],
     "icaf_conv2d_wgrad": [C.POINTER(ConvGeom), _vp, _i64, _vp, _i64, _vp, _f, _i, _vp, C.c_size_t, _vp],
     "icaf_zero_stuff2": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

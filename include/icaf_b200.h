@@ -238,10 +238,22 @@ typedef struct {
   float cp, cn;          /* smoothed positive / negative class targets (smooth_BCE, loss.py:15-17)                 */
   float balance[5];      /* per-level objectness weights: {4, 1, 0.4} for three levels (loss.py:346)               */
 } icaf_loss_hyp;
-size_t icaf_loss_workspace_bytes(int B, int na, int nt, const int* ny, const int* nx, int nl);
-int icaf_compute_loss_fwd(const void* const* p, int p_fp32, const int* ny, const int* nx, int nl, int B, int na, int no,
+/* p_ld: 0 when p[i] is the reference's (B, na, ny, nx, no) contiguous tensor; otherwise the pixel pitch (elements) of the
+ * head's own (B, ny, nx, na*no) NHWC map (the training path hands the 1x1 head convolution's output over without a permute).
+ * no_bwd: 0 for a forward-only workspace, `no` when icaf_compute_loss_bwd will follow. */
+size_t icaf_loss_workspace_bytes(int B, int na, int nt, const int* ny, const int* nx, int nl, int no_bwd);
+int icaf_compute_loss_fwd(const void* const* p, int p_fp32, int p_ld, const int* ny, const int* nx, int nl, int B, int na, int no,
                           const float* targets, int nt, const float* anchors_host, const icaf_loss_hyp* hyp, float* out,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of the loss (train.py:344 starts here): dp[i] = grad_out[0] * d out[0] / d p[i], in the dtype and memory layout of
+ * p[i] (every element of the (cells x no) slab is written; pad channels of an NHWC map with p_ld > na*no are left alone).
+ * Same arguments as the forward call that filled `workspace` (sized with no_bwd = no); grad_out: device fp32 scalar (the
+ * GradScaler factor arrives here).  The CIoU derivative is the forward expression evaluated on forward-mode duals; the
+ * objectness target and CIoU's alpha are constants, as in the reference (loss.py:372, general.py:444).  Candidate gradients
+ * meeting in one cell are summed with fp32 atomics (sum order not fixed), then rounded once. */
+int icaf_compute_loss_bwd(const void* const* p, int p_fp32, int p_ld, const int* ny, const int* nx, int nl, int B, int na, int no,
+                          const float* targets, int nt, const float* anchors_host, const icaf_loss_hyp* hyp, const float* grad_out,
+                          void* const* dp, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Training-step building blocks (train.py:344 backward of the hot path's nn.Conv2d / nn.Linear layers).  Operator level

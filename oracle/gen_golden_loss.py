@@ -4,7 +4,8 @@
 
 Predictions are seeded random Detect training outputs (rebuilt in the tests from the same numpy PCG64 streams, not stored);
 targets are seeded random boxes (stored).  Cases: KAIST shape nc=1 (three levels of a 512x640 frame, batch 4), a 3-class
-variant with label smoothing and non-unit BCE weights, gr = 0.5, and an empty target list.
+variant with label smoothing and non-unit BCE weights, gr = 0.5, and an empty target list.  Each case also stores the
+reference's own backward (loss.backward()): the coarsest level's gradient in full and a 3-number fingerprint per level.
 """
 from __future__ import annotations
 
@@ -48,6 +49,13 @@ def synth_case(name, nc, B, nt, seed=3):
     return p, t
 
 
+def grad_fingerprint(g: np.ndarray, lvl: int) -> np.ndarray:
+    """[sum |g|, <g, w1>, <g, w2>] in float64 with seeded Gaussian w: compact stand-in for the full gradient of a level."""
+    r = np.random.Generator(np.random.PCG64([17, lvl]))
+    g64 = g.astype(np.float64).reshape(-1)
+    return np.array([np.abs(g64).sum(), g64 @ r.standard_normal(g64.size), g64 @ r.standard_normal(g64.size)], dtype=np.float64)
+
+
 def main():
     _, yolo = load_reference()
     from utils.loss import ComputeLoss
@@ -59,7 +67,12 @@ def main():
         model.hyp, model.gr = hyp, gr
         loss_fn = ComputeLoss(model)
         p, t = synth_case(name, nc, B, nt)
-        loss, items = loss_fn([torch.from_numpy(x) for x in p], torch.from_numpy(t))
+        pt = [torch.from_numpy(x).requires_grad_(True) for x in p]
+        loss, items = loss_fn(pt, torch.from_numpy(t))
+        loss.sum().backward()                                                   # train.py:344 on the reference's own graph
+        for lvl, x in enumerate(pt):
+            arrays[f"{name}_gproj{lvl}"] = grad_fingerprint(x.grad.numpy(), lvl)
+        arrays[f"{name}_grad2"] = pt[2].grad.numpy().astype(np.float32)         # coarsest level in full
         arrays[f"{name}_targets"] = t
         arrays[f"{name}_out"] = np.concatenate([loss.detach().numpy().reshape(1), items.numpy()]).astype(np.float32)
         arrays[f"{name}_anchors"] = model.model[-1].anchors.numpy().astype(np.float32)

@@ -314,7 +314,7 @@ def ciou_xywh(box1, box2, eps=1e-7):
     c2 = cw ** 2 + ch ** 2 + eps
     rho2 = ((x2a + x2b - x1a - x1b) ** 2 + (y2a + y2b - y1a - y1b) ** 2) / 4
     v = (4 / math.pi ** 2) * torch.pow(torch.atan(w2 / h2) - torch.atan(w1 / h1), 2)
-    alpha = v / (v - iou + (1 + eps))
+    alpha = (v / (v - iou + (1 + eps))).detach()          # torch.no_grad() in the reference (general.py:444-445)
     return iou - (rho2 / c2 + v * alpha)
 
 

@@ -89,7 +89,16 @@ def test_loss_oracle_matches_reference_golden():
     for cs in m["cases"]:
         p, t = synth_case(cs["name"], cs["nc"], cs["B"], cs["nt"])
         assert np.array_equal(t, d[f"{cs['name']}_targets"])
-        loss, items = O.compute_loss([torch.from_numpy(x) for x in p], torch.from_numpy(t), torch.from_numpy(d[f"{cs['name']}_anchors"]),
-                                     cs["hyp"], cs["gr"])
-        got = np.concatenate([loss.numpy().reshape(1), items.numpy()])
+        pt = [torch.from_numpy(x).requires_grad_(True) for x in p]
+        loss, items = O.compute_loss(pt, torch.from_numpy(t), torch.from_numpy(d[f"{cs['name']}_anchors"]), cs["hyp"], cs["gr"])
+        got = np.concatenate([loss.detach().numpy().reshape(1), items.detach().numpy()])
         assert np.allclose(got, d[f"{cs['name']}_out"], rtol=2e-5, atol=1e-6), (cs["name"], got, d[f"{cs['name']}_out"])
+        # the oracle's autograd graph equals the reference's (tobj and CIoU's alpha detached): its backward reproduces the
+        # reference's loss.backward() -- coarsest level in full, every level through the stored fingerprint
+        from oracle.gen_golden_loss import grad_fingerprint
+        loss.sum().backward()
+        g2 = d[f"{cs['name']}_grad2"]
+        assert np.abs(pt[2].grad.numpy() - g2).max() <= 2e-5 * np.abs(g2).max(), cs["name"]
+        for lvl, x in enumerate(pt):
+            want = d[f"{cs['name']}_gproj{lvl}"]
+            assert np.allclose(grad_fingerprint(x.grad.numpy(), lvl), want, rtol=1e-4, atol=1e-6 * want[0]), (cs["name"], lvl)
