@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libicaf_b200.so")
-SOURCES = ["api.cu", "conv_gemm.cu", "conv_persist.cu", "conv_pair.cu", "attn.cu", "aux.cu", "loss.cu", "conv_stem.cu", "wgrad.cu", "train.cu", "attn_bwd.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "conv_persist.cu", "conv_pair.cu", "attn.cu", "aux.cu", "loss.cu", "conv_stem.cu", "wgrad.cu", "train.cu", "attn_bwd.cu", "dmff_bwd.cu"]
 HEADERS = ["ptx.cuh", "icaf_internal.cuh", "conv_common.cuh", os.path.join("..", "..", "include", "icaf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

@@ -485,6 +485,35 @@ def cross_attention_bwd(qkv_vis, qkv_ir, out_vis, out_ir, dout_vis, dout_ir, B: 
     return dq_v, dq_i
 
 
+def dmff_pool_tokens_bwd(x_vis, x_ir, dtok_vis, dtok_ir, mix, nh: int, nw: int):
+    """Gradients of dmff_pool_tokens w.r.t. the two NHWC feature maps (dense fp16)."""
+    B, H, W, Cc = x_vis.shape
+    ld = _check_view(x_vis, "dmff x_vis")
+    if tuple(x_ir.shape) != tuple(x_vis.shape) or _check_view(x_ir, "dmff x_ir") != ld:
+        raise ValueError("dmff_pool_tokens_bwd: the two feature maps must share shape and pitch")
+    n_pad = dtok_vis.shape[1]
+    for t in (dtok_vis, dtok_ir):
+        assert t.is_contiguous() and t.dtype == torch.float16 and tuple(t.shape) == (B, n_pad, Cc)
+    dx_v = torch.empty(B, H, W, Cc, dtype=torch.float16, device=x_vis.device)
+    dx_i = torch.empty_like(dx_v)
+    _call("icaf_dmff_pool_tokens_bwd", _lib.lib().icaf_dmff_pool_tokens_bwd,
+          (_ptr(x_vis), _ptr(x_ir), ld, _ptr(dtok_vis), _ptr(dtok_ir), _ptr(mix), _ptr(dx_v), _ptr(dx_i), B, H, W, Cc, nh, nw, n_pad),
+          {"bytes": 2.0 * 2 * (2 * x_vis.numel() + dtok_vis.numel())})
+    return dx_v, dx_i
+
+
+def dmff_upsample_cat_bwd(dcat: torch.Tensor, nh: int, nw: int, n_pad: int, mode: int = 1):
+    """Token-stream gradients of dmff_upsample_cat in its training mode (nearest); dcat: (B,H,W,2C) NHWC view."""
+    B, H, W, C2 = dcat.shape
+    Cc = C2 // 2
+    ld = _check_view(dcat, "dmff dcat")
+    dt_v = torch.empty(B, n_pad, Cc, dtype=torch.float16, device=dcat.device)
+    dt_i = torch.empty_like(dt_v)
+    _call("icaf_dmff_upsample_cat_bwd", _lib.lib().icaf_dmff_upsample_cat_bwd,
+          (_ptr(dcat), ld, _ptr(dt_v), _ptr(dt_i), B, H, W, Cc, nh, nw, n_pad, mode), {"bytes": 2.0 * (dcat.numel() + 2 * dt_v.numel())})
+    return dt_v, dt_i
+
+
 def dmff_upsample_cat(tok_vis, tok_ir, x_vis, x_ir, nh: int, nw: int, mode: int = 0) -> torch.Tensor:
     B, H, W, Cc = x_vis.shape
     out = torch.empty(B, H, W, 2 * Cc, dtype=torch.float16, device=x_vis.device)
@@ -596,11 +625,35 @@ def linear_wgrad(x: torch.Tensor, dy: torch.Tensor, scale: float = 1.0, out: Opt
     return conv2d_wgrad(x.unflatten(0, (1, 1, x.shape[0])), dy.unflatten(0, (1, 1, dy.shape[0])), 1, 1, 1, 0, scale, o4).view(dy.shape[1], x.shape[1])
 
 
+def pack_weight(weight: torch.Tensor, stride: int, pad: int, act: int = ACT_NONE, bias: Optional[torch.Tensor] = None,
+                dgrad: bool = False) -> PackedConv:
+    """fp32 master filter (Cout,Cin,kh,kw) on the device -> PackedConv through icaf_pack_weight (one launch; the training step
+    re-packs every filter after each optimiser update).  dgrad: the flipped / transposed filter of the data-gradient
+    convolution, W'[c][n][ky][kx] = W[n][c][kh-1-ky][kw-1-kx], its channel count (Cout) padded to a multiple of 8."""
+    cout, cin, kh, kw = weight.shape
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous() or not on_device(w):
+        raise ValueError("pack_weight: contiguous fp32 CUDA filter expected")
+    if dgrad:
+        chan, rows, pcin, pcout = round_up(cout, 8), round_up(cin, 32), round_up(cout, 8), cin
+    else:
+        if cin % 8:
+            raise ValueError(f"pack_weight: input channels must be a multiple of 8, got {cin}")
+        chan, rows, pcin, pcout = cin, round_up(cout, 32), cin, cout
+    k_pad = round_up(kh * kw * chan, 64)
+    out = torch.empty(rows, k_pad, dtype=torch.float16, device=w.device)
+    _call("icaf_pack_weight", _lib.lib().icaf_pack_weight, (_ptr(w), cout, cin, kh, kw, chan, rows, k_pad, int(dgrad), _ptr(out)),
+          {"bytes": 4.0 * w.numel() + 2.0 * out.numel()})
+    b = None if bias is None else bias.detach().float().contiguous()
+    return PackedConv(out, b, pcin, pcout, kh, kw, stride, pad, act)
+
+
 def pack_dgrad_weight(weight: torch.Tensor, device=None) -> PackedConv:
-    """Filter of the data-gradient convolution: W'[c][n][ky][kx] = W[n][c][kh-1-ky][kw-1-kx], stride 1, pad k-1-p is set by
-    the caller through conv2d_dgrad (no bias, no activation)."""
-    w = weight.detach().float().flip(2, 3).permute(1, 0, 2, 3).contiguous()
-    return pack_conv_weight(w, None, 1, 0, ACT_NONE, device)
+    """Filter of the data-gradient convolution (stride 1; pad k-1-p is set by conv2d_dgrad; no bias, no activation)."""
+    w = weight.detach().float().contiguous()
+    if device is not None:
+        w = w.to(device)
+    return pack_weight(w, 1, 0, ACT_NONE, None, dgrad=True)
 
 
 def zero_stuff2(dy: torch.Tensor, H2: int, W2: int) -> torch.Tensor:

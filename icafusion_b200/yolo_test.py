@@ -264,6 +264,9 @@ class Model(nn.Module):
         return self.forward_once(x, x2, profile)
 
     def forward_once(self, x, x2, profile=False):
+        if self.training:                           # train.py:336: the list of raw Detect maps, with an autograd graph
+            from . import autograd
+            return autograd.model_forward(self, x, x2)
         z, logits, xs = self._forward_nhwc(x, x2)
         return z, logits, xs
 

@@ -303,6 +303,22 @@ int icaf_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, vo
 /* Backward of one MaxPool2d(5, 1, 2) of SPPF's chain (common.py:259-266): x is that pool's input, dy the gradient of its output. */
 int icaf_maxpool5_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
 
+/* Backward of icaf_dmff_pool_tokens w.r.t. the two feature maps (dense fp16 (B,H,W,C) gradients): every pixel gathers, from
+ * each pooling window that contains it, dtok * (w_avg / window + w_max * [pixel is the window's first maximum]).  The
+ * gradients of the mixing weights and positional embeddings are plain reductions of dtok (icaf_dot / icaf_colsum). */
+int icaf_dmff_pool_tokens_bwd(const void* x_vis, const void* x_ir, int64_t x_ld, const void* dtok_vis, const void* dtok_ir, const float* mix,
+                              void* dx_vis, void* dx_ir, int B, int H, int W, int C, int nh, int nw, int n_pad, void* stream);
+/* Backward of icaf_dmff_upsample_cat (mode 1, nearest: the training-mode tail, common.py:828-829) w.r.t. the token streams:
+ * dtok[b][n] = sum of dcat over the pixels token n was copied to (pad rows get 0).  dcat: (B,H,W,2C) with pixel pitch d_ld;
+ * the gradients of the two residual inputs are its channel halves. */
+int icaf_dmff_upsample_cat_bwd(const void* dcat, int64_t d_ld, void* dtok_vis, void* dtok_ir, int B, int H, int W, int C, int nh, int nw,
+                               int n_pad, int mode, void* stream);
+/* fp32 master filter (Cout,Cin,kh,kw) -> fp16 bank [rows][k_pad] of icaf_conv2d_fwd, K order (ky,kx,channel), channel count
+ * padded to chan_pad, padding written as zero.  transpose_flip = 0: the forward filter (rows >= Cout, channels = Cin);
+ * 1: the data-gradient filter W'[c][n][ky][kx] = W[n][c][kh-1-ky][kw-1-kx] (rows >= Cin, channels = Cout). */
+int icaf_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, int chan_pad, int rows, int k_pad, int transpose_flip, void* out,
+                     void* stream);
+
 /* Training-mode forward of the fused form: like icaf_cross_attention(qkv_vis, qkv_ir, NULL, NULL, ...) plus dropout with
  * probability p_drop on the attention probabilities (common.py:677,680; counter-based mask keyed by `seed`, reproduced by the
  * backward below). */

@@ -27,6 +27,8 @@ import torch.nn.functional as F
 SD = Dict[str, torch.Tensor]
 
 BN_EPS_MODEL = 1e-3      # utils/torch_utils.py:151  (initialize_weights sets eps on every BN of a built Model)
+BN_MOMENTUM_MODEL = 0.03  # utils/torch_utils.py:152
+_BN_TRAIN = [False]       # set by model_forward(training=True): Conv.forward with the module in train() (common.py:56-57)
 BN_EPS_STANDALONE = 1e-5  # nn.BatchNorm2d default, stand-alone TransformerFusionBlock
 LN_EPS = 1e-5            # nn.LayerNorm default, models/common.py:631-632,723-724
 
@@ -46,8 +48,12 @@ def conv_bn_silu(x, sd: SD, pre: str, k: int, s: int, p=None, act=True, bn_eps=B
     pad = autopad(k, p)
     if pre + ".bn.weight" in sd:
         y = F.conv2d(x, w, None, stride=s, padding=pad)
-        y = F.batch_norm(y, sd[pre + ".bn.running_mean"], sd[pre + ".bn.running_var"],
-                         sd[pre + ".bn.weight"], sd[pre + ".bn.bias"], False, 0.0, bn_eps)
+        if _BN_TRAIN[0]:      # module in train(): batch statistics, running stats updated in place (momentum 0.03, torch_utils.py:152)
+            y = F.batch_norm(y, sd[pre + ".bn.running_mean"], sd[pre + ".bn.running_var"],
+                             sd[pre + ".bn.weight"], sd[pre + ".bn.bias"], True, BN_MOMENTUM_MODEL, bn_eps)
+        else:
+            y = F.batch_norm(y, sd[pre + ".bn.running_mean"], sd[pre + ".bn.running_var"],
+                             sd[pre + ".bn.weight"], sd[pre + ".bn.bias"], False, 0.0, bn_eps)
     else:
         y = F.conv2d(x, w, sd[pre + ".conv.bias"], stride=s, padding=pad)
     return F.silu(y) if act else y
@@ -236,13 +242,25 @@ def parse_layers(cfg: dict) -> List[dict]:
     return layers
 
 
-def model_forward(sd: SD, cfg: dict, rgb, ir, training=False, dmff_loops: int = 1):
+def model_forward(sd: SD, cfg: dict, rgb, ir, training=False, dmff_loops: int = 1, taps: list = None):
     """Model.forward_once, yolo_test.py:136-163: sequential walk; `f == -4` feeds the IR image."""
     layers = parse_layers(cfg)
     save = set()
     for L in layers:
         fs = [L["f"]] if isinstance(L["f"], int) else L["f"]
         save.update(x % L["i"] for x in fs if x != -1)
+    y: List = []
+    x = rgb
+    _BN_TRAIN[0] = bool(training)
+    try:
+        return _walk(layers, save, sd, rgb, ir, training, dmff_loops, taps)
+    finally:
+        _BN_TRAIN[0] = False
+
+
+def _walk(layers, save, sd: SD, rgb, ir, training: bool, dmff_loops: int, taps: list = None):
+    """Training mode restates the dropout-free graph (every nn.Dropout with p = 0): the reference's masks come from torch's
+    generator and cannot be reproduced by another implementation."""
     y: List = []
     x = rgb
     for L in layers:
@@ -272,6 +290,8 @@ def model_forward(sd: SD, cfg: dict, rgb, ir, training=False, dmff_loops: int = 
         elif t == "Detect":
             x = detect(list(x), sd, pre, L["nc"], L["anchors"], [8.0, 16.0, 32.0], training)
         y.append(x if i in save else None)
+        if taps is not None:
+            taps.append(x)
     return x
 
 
@@ -504,3 +524,36 @@ def model_conv_flops(cfg: dict, H: int, W: int) -> float:
                 total += conv(cj, na * (L["nc"] + 5), 1, hj, wj)
             shapes.append(None)
     return total
+
+
+# ----------------------------------------------------------------------------------------
+# one training step (train.py:334-344): forward in train mode, loss, backward
+# ----------------------------------------------------------------------------------------
+def train_step(sd: SD, cfg: dict, rgb, ir, targets, hyp: dict, gr: float = 1.0, dmff_loops: int = 1, autocast_device=None,
+               loss_scale: float = 1.0):
+    """-> (loss (1,), loss_items (4,), {name: gradient}, [raw Detect maps], updated state).  `sd` is left untouched: parameters
+    are cloned into autograd leaves, BatchNorm buffers are cloned and updated like nn.BatchNorm2d does in train().
+    autocast_device: run the same graph on that CUDA device under fp16 autocast with a static loss scale -- the reference's own
+    training regime (train.py:334-344); the GPU tests use it to measure how far that regime sits from fp32."""
+    if autocast_device is not None:
+        sd = {k: v.to(autocast_device) for k, v in sd.items()}
+        rgb, ir, targets = rgb.to(autocast_device), ir.to(autocast_device), targets.to(autocast_device)
+        with torch.autocast("cuda", dtype=torch.float16):
+            return _train_step(sd, cfg, rgb, ir, targets, hyp, gr, dmff_loops, loss_scale)
+    return _train_step(sd, cfg, rgb, ir, targets, hyp, gr, dmff_loops, loss_scale)
+
+
+def _train_step(sd: SD, cfg: dict, rgb, ir, targets, hyp: dict, gr: float, dmff_loops: int, loss_scale: float):
+    state = {k: v.clone() for k, v in sd.items()}
+    params = {}
+    for k, v in state.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var", "anchors", "anchor_grid")):
+            params[k] = v.requires_grad_(True)
+    pred = model_forward(state, cfg, rgb, ir, training=True, dmff_loops=dmff_loops)
+    det = [L for L in parse_layers(cfg) if L["type"] == "Detect"][0]
+    anchors = torch.tensor(det["anchors"], dtype=torch.float32).view(len(det["anchors"]), -1, 2) / torch.tensor([8.0, 16.0, 32.0]).view(-1, 1, 1)
+    # (the loss itself always runs in fp32 on the CPU; under autocast the fp16 maps are cast up, their gradient cast back down)
+    loss, items = compute_loss([p.float().cpu() for p in pred], targets.cpu(), anchors, hyp, gr)
+    (loss.sum() * loss_scale).backward()
+    grads = {k: p.grad / loss_scale for k, p in params.items() if p.grad is not None}
+    return loss.detach(), items.detach(), grads, [p.detach() for p in pred], {k: v.detach() for k, v in state.items()}

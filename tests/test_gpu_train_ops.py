@@ -194,3 +194,109 @@ def test_cross_attention_dropout(cuda_device):
     e_g = max(err(dq_v, rv.grad), err(dq_i, ri.grad))
     print(f"\n[attention dropout p{p}] keep {keep:.3f}  out {e_o:.2e}  dqkv {e_g:.2e}")
     assert e_o < 1.5e-3 and e_g < 2e-3
+
+
+def _ref_pool_tokens(x, pos, w1, w2, nh, nw):
+    """AdaptivePool2d avg / max (common.py:868-891) mixed by LearnableWeights + positional embedding (common.py:817-819)."""
+    B, C, H, W = x.shape
+    if H > nh or W > nw:
+        sh, sw = H // nh, W // nw
+        k = (H - (nh - 1) * sh, W - (nw - 1) * sw)
+        a, m = F.avg_pool2d(x, k, (sh, sw)), F.max_pool2d(x, k, (sh, sw))
+    else:
+        a = m = x
+    return (w1 * a + w2 * m).flatten(2).permute(0, 2, 1) + pos
+
+
+@pytest.mark.parametrize("B,C,H,W,va,ha", [(2, 64, 40, 40, 20, 20), (2, 128, 20, 20, 16, 16), (1, 64, 64, 80, 20, 20), (2, 64, 10, 10, 10, 10)])
+def test_dmff_pool_and_tail_nodes(cuda_device, B, C, H, W, va, ha):
+    """PoolTokensFn / UpsampleCatFn (token pooling with overlapping windows, nearest tail) forward + backward vs torch autograd."""
+    from icafusion_b200 import autograd as A
+    g = torch.Generator().manual_seed(H * W + va)
+    nh, nw = (va, ha) if (H > va or W > ha) else (H, W)
+    N = nh * nw
+    rgb, ir = torch.randn(B, C, H, W, generator=g).half(), torch.randn(B, C, H, W, generator=g).half()
+    rgb[0, :, 0:3, 0:3] = rgb[0, :, 0:1, 0:1]                     # ties inside a window: the first maximum takes the gradient
+    pos = [(0.1 * torch.randn(1, N, C, generator=g)).half().float() for _ in range(2)]
+    wts = [torch.tensor([v]) for v in (0.6, 0.4, 0.3, 0.7)]
+    dtok = [(0.1 * torch.randn(B, N, C, generator=g)).half() for _ in range(2)]
+    dcat = (0.1 * torch.randn(B, 2 * C, H, W, generator=g)).half()
+    # reference (fp32 autograd on the same fp16-rounded operands)
+    R = [t.float().requires_grad_(True) for t in (rgb, ir)]
+    P = [t.clone().requires_grad_(True) for t in pos]
+    Wt = [t.clone().requires_grad_(True) for t in wts]
+    tr = [_ref_pool_tokens(R[0], P[0], Wt[0], Wt[1], nh, nw), _ref_pool_tokens(R[1], P[1], Wt[2], Wt[3], nh, nw)]
+    (tr[0] * dtok[0].float()).sum().backward(retain_graph=True)
+    (tr[1] * dtok[1].float()).sum().backward()
+    # device
+    dev = cuda_device
+    Rd = [nhwc(t).to(dev).requires_grad_(True) for t in (rgb, ir)]
+    Pd = [t.clone().to(dev).requires_grad_(True) for t in pos]
+    Wd = [t.clone().to(dev).requires_grad_(True) for t in wts]
+    tv, ti = A.PoolTokensFn.apply(Rd[0], Rd[1], Pd[0], Pd[1], Wd[0], Wd[1], Wd[2], Wd[3], nh, nw)
+    n_pad = tv.shape[1]
+    pad = lambda t: torch.cat([t, t.new_zeros(B, n_pad - N, C)], 1).to(dev)      # noqa: E731
+    ((tv.float() * pad(dtok[0]).float()).sum() + (ti.float() * pad(dtok[1]).float()).sum()).backward()
+    e_f = max(err(tv[:, :N], tr[0]), err(ti[:, :N], tr[1]))
+    e_x = max(err(Rd[0].grad.permute(0, 3, 1, 2), R[0].grad), err(Rd[1].grad.permute(0, 3, 1, 2), R[1].grad))
+    e_p = max(err(Pd[0].grad, P[0].grad), err(Pd[1].grad, P[1].grad))
+    e_w = max(err(Wd[k].grad, Wt[k].grad) for k in range(4))
+    print(f"\n[pool tokens {H}x{W}->{nh}x{nw} C{C}] fwd {e_f:.2e}  dx {e_x:.2e}  dpos {e_p:.2e}  dmix {e_w:.2e}")
+    assert e_f < 1e-3 and e_x < 2e-3 and e_p < 1e-3 and e_w < 5e-3     # dmix: a cancelling sum of fp16-rounded token products
+    # tail: nearest resample + residual + concat
+    tok = [(torch.randn(B, N, C, generator=g)).half() for _ in range(2)]
+    T = [t.float().requires_grad_(True) for t in tok]
+    R = [t.float().requires_grad_(True) for t in (rgb, ir)]
+    up = lambda t: F.interpolate(t.reshape(B, nh, nw, C).permute(0, 3, 1, 2), size=(H, W), mode="nearest")   # noqa: E731
+    cat = torch.cat([up(T[0]) + R[0], up(T[1]) + R[1]], 1)
+    (cat * dcat.float()).sum().backward()
+    Td = [pad(t).requires_grad_(True) for t in tok]
+    Rd = [nhwc(t).to(dev).requires_grad_(True) for t in (rgb, ir)]
+    cd = A.UpsampleCatFn.apply(Td[0], Td[1], Rd[0], Rd[1], nh, nw)
+    (cd.float() * nhwc(dcat).to(dev).float()).sum().backward()
+    e_f = err(cd.permute(0, 3, 1, 2), cat)
+    e_t = max(err(Td[0].grad[:, :N], T[0].grad), err(Td[1].grad[:, :N], T[1].grad))
+    e_x = max(err(Rd[0].grad.permute(0, 3, 1, 2), R[0].grad), err(Rd[1].grad.permute(0, 3, 1, 2), R[1].grad))
+    print(f"[tail {nh}x{nw}->{H}x{W}] fwd {e_f:.2e}  dtok {e_t:.2e}  dx {e_x:.2e}")
+    assert e_f < 1e-3 and e_t < 2e-3 and e_x < 1e-3
+    assert float(Td[0].grad[:, N:].abs().max() if n_pad > N else 0.0) == 0.0
+
+
+def test_conv_bn_act_node(cuda_device):
+    """ConvBnActFn (common.Conv in train()): forward, running statistics, and all four gradients vs torch autograd; also the
+    6x6 / stride-2 image stem through its space-to-depth form."""
+    import torch.nn as nn
+    from icafusion_b200 import autograd as A
+    from icafusion_b200 import common
+    g = torch.Generator().manual_seed(21)
+    for (cin, cout, k, s, H, W, stem) in [(64, 128, 3, 2, 32, 40, False), (128, 64, 1, 1, 16, 20, False), (3, 32, 6, 2, 64, 96, True)]:
+        m = common.Conv(cin, cout, k, s, 2 if stem else None)
+        with torch.no_grad():
+            m.conv.weight.copy_((torch.randn(m.conv.weight.shape, generator=g) / (cin * k * k) ** 0.5).half().float())
+            m.bn.weight.copy_(1 + 0.2 * torch.randn(cout, generator=g))
+            m.bn.bias.copy_(0.2 * torch.randn(cout, generator=g))
+        m.bn.eps, m.bn.momentum = 1e-3, 0.03
+        ref = nn.Sequential(nn.Conv2d(cin, cout, k, s, m.conv.padding, bias=False), nn.BatchNorm2d(cout, eps=1e-3, momentum=0.03), nn.SiLU())
+        ref[0].weight.data.copy_(m.conv.weight.data)
+        ref[1].load_state_dict(m.bn.state_dict())
+        ref.train()
+        x = torch.rand(2, cin, H, W, generator=g).half() if stem else torch.randn(2, cin, H, W, generator=g).half()
+        xr = x.float().requires_grad_(True)
+        y = ref(xr)
+        dy = (0.1 * torch.randn(y.shape, generator=g)).half()
+        y.backward(dy.float())
+        m = m.to(cuda_device).train()
+        if stem:
+            xd = m.stage_image(x.to(cuda_device))
+        else:
+            xd = nhwc(x).to(cuda_device).requires_grad_(True)
+        yd = A.conv_bn_act(m, xd, stem)
+        yd.backward(nhwc(dy).to(cuda_device))
+        torch.cuda.synchronize()
+        e = dict(y=err(yd.permute(0, 3, 1, 2), y), dw=err(m.conv.weight.grad, ref[0].weight.grad), dg=err(m.bn.weight.grad, ref[1].weight.grad),
+                 db=err(m.bn.bias.grad, ref[1].bias.grad), rm=err(m.bn.running_mean, ref[1].running_mean), rv=err(m.bn.running_var, ref[1].running_var))
+        if not stem:
+            e["dx"] = err(xd.grad.permute(0, 3, 1, 2), xr.grad)
+        print(f"\n[conv node {cin}->{cout} k{k}s{s}{' stem' if stem else ''}] " + "  ".join(f"{k2} {v:.2e}" for k2, v in e.items()))
+        assert max(e.values()) < 2.5e-3, e
+        assert int(m.bn.num_batches_tracked) == 1

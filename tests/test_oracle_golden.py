@@ -102,3 +102,34 @@ def test_loss_oracle_matches_reference_golden():
         for lvl, x in enumerate(pt):
             want = d[f"{cs['name']}_gproj{lvl}"]
             assert np.allclose(grad_fingerprint(x.grad.numpy(), lvl), want, rtol=1e-4, atol=1e-6 * want[0]), (cs["name"], lvl)
+
+
+def test_training_step_oracle_matches_reference_golden():
+    """oracle.train_step (train-mode forward with BatchNorm batch statistics and the nearest DMFF tail, loss, autograd backward)
+    reproduces the REAL reference's training step (tests/golden/train_yolov5s_320.npz, oracle/gen_golden_train.py): loss, a
+    fingerprint of every parameter gradient, the set of parameters that receive no gradient, updated BN running statistics."""
+    from oracle.gen_golden_train import fingerprint, synth_targets
+    m, d = load_golden("train_yolov5s_320")
+    cfg = load_cfg(f"yolov5{m['size']}_Transfusion_kaist")
+    sd = synth.synth_state_dict(synth.model_param_shapes(cfg), m["seed"])
+    rgb, ir = synth.synth_images(m["B"], m["H"], m["W"], m["seed"])
+    t = synth_targets(m["nt"], m["B"], m["seed"])
+    assert np.array_equal(t, d["targets"])
+    loss, items, grads, pred, state = O.train_step(sd, cfg, rgb, ir, torch.from_numpy(t), m["hyp"], m["gr"])
+    got = np.concatenate([loss.numpy().reshape(1), items.numpy()])
+    assert np.allclose(got, d["out"], rtol=1e-4, atol=1e-6), (got, d["out"])
+    assert sorted(grads) == sorted(m["params"])                     # the same 30 parameters stay without a gradient
+    worst = 0.0
+    for k in m["params"]:
+        want = d["g:" + k]
+        fp = fingerprint(grads[k].numpy(), k)
+        # floor: key-projection biases (softmax is shift invariant) and the last MLP biases (a per-channel constant in front of
+        # a batch-statistics BatchNorm) have mathematically zero gradients -- 1e-8 rounding noise on both sides
+        worst = max(worst, float(np.abs(fp - want).max() / max(want[0], 1e-3)))
+    assert worst < 2e-4, worst                                      # fp32 CPU both sides (observed 4e-5)
+    for i in range(3):
+        want = d[f"pred{i}"]
+        assert np.abs(fingerprint(pred[i].numpy(), f"pred{i}") - want).max() < 1e-4 * want[0]
+    for k in m["bn_probes"]:
+        assert np.allclose(state[k + ".running_mean"].numpy(), d["rm:" + k], rtol=1e-4, atol=1e-6)
+        assert np.allclose(state[k + ".running_var"].numpy(), d["rv:" + k], rtol=1e-4, atol=1e-6)
