@@ -83,8 +83,8 @@ SIGNATURES = {
     "icaf_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp, C.c_size_t, _vp],
     "icaf_dot": [_vp, _vp, _i64, _i, _vp, _f, _i, _vp, C.c_size_t, _vp],
     "icaf_upsample2x_bwd": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "icaf_maxpool5_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "icaf_dmff_pool_tokens_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "icaf_maxpool5_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, C.c_size_t, _vp],
+    "icaf_dmff_pool_tokens_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp],
     "icaf_dmff_upsample_cat_bwd": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "icaf_pack_weight": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "icaf_cross_attention_train": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, C.c_uint32, _vp],

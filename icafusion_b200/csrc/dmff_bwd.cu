@@ -24,10 +24,42 @@ __device__ __forceinline__ uint4 ld16(const __half* p) { return __ldg(reinterpre
 
 struct PoolBwdParams {
   const __half* x[2]; const __half* dtok[2]; __half* dx[2];
+  uint2* code[2];          // [B][N][C8]: per window and channel, the position code (ky*kw + kx) of its first maximum
   const float* mix;
   long long x_ld;
   int B, H, W, C8, nh, nw, n_pad, kh, kw, sh, sw;
 };
+// 1 of 2: arg-max position of every pooling window (windows are few: nh*nw per image)
+__global__ void __launch_bounds__(128) dmff_pool_argmax_kernel(const PoolBwdParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int mod = blockIdx.y;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int N = P.nh * P.nw;
+  if (i >= (long long)P.B * N * P.C8) return;
+  const int c = int(i % P.C8);
+  const long long t = i / P.C8;
+  const int n = int(t % N), b = int(t / N);
+  const int ty = n / P.nw, tx = n % P.nw;
+  const __half* x0 = (mod ? P.x[1] : P.x[0]) + ((long long)(b * P.H + ty * P.sh) * P.W + tx * P.sw) * P.x_ld + c * 8;
+  float best[8];
+  uint32_t arg[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0u; }
+  for (int k = 0; k < P.kh * P.kw; ++k) {
+    const int ky = k / P.kw, kx = k - ky * P.kw;
+    float f[8];
+    unpack8b(ld16(x0 + ((long long)ky * P.W + kx) * P.x_ld), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (f[e] > best[e]) { best[e] = f[e]; arg[e] = uint32_t(k); }       // strict: the first maximum in row-major order wins
+  }
+  uint2 o;
+  o.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+  o.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+  (mod ? P.code[1] : P.code[0])[i] = o;
+}
+// 2 of 2: every pixel gathers from the windows that contain it
 __global__ void __launch_bounds__(128) dmff_pool_tokens_bwd_kernel(const PoolBwdParams P) {
   pdl_launch_dependents();
   pdl_wait();
@@ -40,12 +72,11 @@ __global__ void __launch_bounds__(128) dmff_pool_tokens_bwd_kernel(const PoolBwd
   const int w = int(p % P.W);
   long long t = p / P.W;
   const int h = int(t % P.H), b = int(t / P.H);
-  const int C = P.C8 * 8;
-  const __half* x = (mod ? P.x[1] : P.x[0]) + c * 8;
+  const int C = P.C8 * 8, N = P.nh * P.nw;
   const __half* dtok = (mod ? P.dtok[1] : P.dtok[0]) + (long long)b * P.n_pad * C + c * 8;
+  const uint2* code = (mod ? P.code[1] : P.code[0]) + (long long)b * N * P.C8 + c;
   const float w1 = P.mix[mod * 2] / float(P.kh * P.kw), w2 = P.mix[mod * 2 + 1];
-  float mine[8], acc[8];
-  unpack8b(ld16(x + p * P.x_ld), mine);
+  float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   // windows [ty*sh, ty*sh + kh) that contain row h (likewise columns); kh >= sh, so there is at least one
@@ -55,24 +86,16 @@ __global__ void __launch_bounds__(128) dmff_pool_tokens_bwd_kernel(const PoolBwd
     if (h < ty * P.sh || h >= ty * P.sh + P.kh) continue;
     for (int tx = tx0; tx <= tx1; ++tx) {
       if (w < tx * P.sw || w >= tx * P.sw + P.kw) continue;
+      const int n = ty * P.nw + tx;
       float g[8];
-      unpack8b(ld16(dtok + (long long)(ty * P.nw + tx) * C), g);
-      // am I the arg-max of this window?  (first maximum in row-major order, like max_pool2d's backward)
-      bool first[8];
+      unpack8b(ld16(dtok + (long long)n * C), g);
+      const uint2 cd = __ldg(code + (long long)n * P.C8);
+      const uint32_t mine = uint32_t((h - ty * P.sh) * P.kw + (w - tx * P.sw));
 #pragma unroll
-      for (int e = 0; e < 8; ++e) first[e] = true;
-      const int my = (h - ty * P.sh) * P.kw + (w - tx * P.sw);
-      const __half* x0 = x + ((long long)(b * P.H + ty * P.sh) * P.W + tx * P.sw) * P.x_ld;
-      for (int k = 0; k < P.kh * P.kw; ++k) {
-        if (k == my) continue;
-        const int ky = k / P.kw, kx = k - ky * P.kw;
-        float f[8];
-        unpack8b(ld16(x0 + ((long long)ky * P.W + kx) * P.x_ld), f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) first[e] = first[e] && (k < my ? f[e] < mine[e] : f[e] <= mine[e]);
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t a = ((e < 4 ? cd.x : cd.y) >> (8 * (e & 3))) & 0xffu;
+        acc[e] += g[e] * (w1 + (a == mine ? w2 : 0.f));
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += g[e] * (w1 + (first[e] ? w2 : 0.f));
     }
   }
   *reinterpret_cast<uint4*>((mod ? P.dx[1] : P.dx[0]) + p * C + c * 8) = pack8b(acc);
@@ -146,8 +169,11 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 using namespace icaf;
 
 extern "C" int icaf_dmff_pool_tokens_bwd(const void* x_vis, const void* x_ir, int64_t x_ld, const void* dtok_vis, const void* dtok_ir, const float* mix,
-                                         void* dx_vis, void* dx_ir, int B, int H, int W, int C, int nh, int nw, int n_pad, void* stream) {
-  if (!x_vis || !x_ir || !dtok_vis || !dtok_ir || !mix || !dx_vis || !dx_ir) return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens_bwd: null pointer");
+                                         void* dx_vis, void* dx_ir, int B, int H, int W, int C, int nh, int nw, int n_pad, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  if (!x_vis || !x_ir || !dtok_vis || !dtok_ir || !mix || !dx_vis || !dx_ir || !workspace) return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens_bwd: null pointer");
+  if (workspace_bytes < 2 * size_t(B) * nh * nw * C || (reinterpret_cast<uintptr_t>(workspace) & 7))
+    return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens_bwd: workspace needs 2*B*nh*nw*C bytes, 8-byte aligned");
   if (C % 8 || x_ld % 8 || B < 1 || nh < 1 || nw < 1 || H < nh || W < nw || n_pad < nh * nw)
     return set_error(ICAF_ERR_BAD_ARG, "dmff_pool_tokens_bwd: bad shape");
   PoolBwdParams P;
@@ -156,6 +182,11 @@ extern "C" int icaf_dmff_pool_tokens_bwd(const void* x_vis, const void* x_ir, in
   P.B = B; P.H = H; P.W = W; P.C8 = C / 8; P.nh = nh; P.nw = nw; P.n_pad = n_pad;
   P.sh = H / nh; P.sw = W / nw;                                   // AdaptivePool2d geometry, models/common.py:878-882
   P.kh = H - (nh - 1) * P.sh; P.kw = W - (nw - 1) * P.sw;
+  if (P.kh * P.kw > 255) return set_error(ICAF_ERR_UNSUPPORTED, "dmff_pool_tokens_bwd: pooling windows of more than 255 pixels");
+  P.code[0] = (uint2*)workspace; P.code[1] = P.code[0] + size_t(B) * nh * nw * P.C8;
+  const long long nwin = (long long)B * nh * nw * P.C8;
+  launch_k(dmff_pool_argmax_kernel, dim3((unsigned)((nwin + 127) / 128), 2), dim3(128), 0, (cudaStream_t)stream, P);
+  if (int rc = check_launch("dmff_pool_tokens_bwd(argmax)")) return rc;
   const long long total = (long long)B * H * W * P.C8;
   launch_k(dmff_pool_tokens_bwd_kernel, dim3((unsigned)((total + 127) / 128), 2), dim3(128), 0, (cudaStream_t)stream, P);
   return check_launch("dmff_pool_tokens_bwd");

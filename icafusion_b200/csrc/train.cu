@@ -7,7 +7,7 @@
 
 namespace icaf {
 
-constexpr int kRedChunks = 64;
+constexpr int kRedChunks = 1024;      // upper bound of the row chunks of a two-stage reduction (sizes the workspace); the launch picks <= this many
 
 __device__ __forceinline__ void unpack8h(const uint4& v, float (&f)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&v);
@@ -28,18 +28,24 @@ __device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf
 template <int MODE>
 __global__ void __launch_bounds__(256) chan_partial_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const float* __restrict__ a,
                                                            const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                           float* __restrict__ out, long long rows, int C, int act) {
+                                                           float* __restrict__ out, long long rows, int C, int act, int chunks) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float red[8][32][17];
-  const int cg = blockIdx.x * 32 + threadIdx.x;            // 8-channel group
+  __shared__ float red[256][17];
+  // the 256 threads cover (g channel groups) x (rpp rows) per pass: all of them stay busy for narrow maps too (C = 64 -> 8 x 32)
   const int C8 = C >> 3;
-  const long long per = (rows + kRedChunks - 1) / kRedChunks;
+  const int g = min(C8 - int(blockIdx.x) * 32, 32);
+  const int rpp = 256 / g;
+  const int tid = threadIdx.x;
+  const bool active = tid < g * rpp;
+  const int cgl = tid % g, rl = tid / g;
+  const int cg = blockIdx.x * 32 + cgl;
+  const long long per = (rows + chunks - 1) / chunks;
   const long long r0 = blockIdx.y * per, r1 = min(r0 + per, rows);
   float s0[8], s1[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s0[e] = s1[e] = 0.f;
-  if (cg < C8) {
+  if (active) {
     float av[8], bv[8], mv[8], iv[8];
     if (MODE == 1) {                                        // a = gamma, b = beta on entry -> per-channel affine of the BN apply
 #pragma unroll
@@ -48,7 +54,7 @@ __global__ void __launch_bounds__(256) chan_partial_kernel(const __half* __restr
         av[e] = a[cg * 8 + e] * iv[e]; bv[e] = b[cg * 8 + e] - mv[e] * av[e];
       }
     }
-    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+    for (long long r = r0 + rl; r < r1; r += rpp) {
       float xv[8], dv[8];
       unpack8h(__ldg(reinterpret_cast<const uint4*>(x + r * C + cg * 8)), xv);
       if (MODE != 0) unpack8h(__ldg(reinterpret_cast<const uint4*>(dy + r * C + cg * 8)), dv);
@@ -69,27 +75,39 @@ __global__ void __launch_bounds__(256) chan_partial_kernel(const __half* __restr
     }
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { red[threadIdx.y][threadIdx.x][e] = s0[e]; red[threadIdx.y][threadIdx.x][8 + e] = s1[e]; }
+  for (int e = 0; e < 8; ++e) { red[tid][e] = s0[e]; red[tid][8 + e] = s1[e]; }
   __syncthreads();
-  if (threadIdx.y == 0 && cg < C8) {
+  if (tid < g) {                                            // fixed order over the rpp row lanes: deterministic
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       float s = 0.f;
-      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][e];
+      for (int y = 0; y < rpp; ++y) s += red[y * g + tid][e];
       out[(size_t(blockIdx.y) * 2 + (e >> 3)) * C + cg * 8 + (e & 7)] = s;
     }
   }
 }
 
+// second stages: block (32 channels, 8 chunk lanes); lane y sums chunks y, y + 8, ...; the 8 lane sums are added in lane order
+__device__ __forceinline__ void chunk_sums(const float* __restrict__ part, int C, int chunks, int c, float& s, float& q, float (*sm)[8][32]) {
+  float a = 0.f, b2 = 0.f;
+  if (c < C)
+    for (int k = threadIdx.y; k < chunks; k += 8) { a += part[(size_t(k) * 2) * C + c]; b2 += part[(size_t(k) * 2 + 1) * C + c]; }
+  sm[0][threadIdx.y][threadIdx.x] = a; sm[1][threadIdx.y][threadIdx.x] = b2;
+  __syncthreads();
+  s = q = 0.f;
+  for (int y = 0; y < 8; ++y) { s += sm[0][y][threadIdx.x]; q += sm[1][y][threadIdx.x]; }
+}
+
 // BatchNorm statistics, second stage: mean, invstd, and the running statistics update (momentum, unbiased variance)
-__global__ void bn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ invstd, float* run_mean,
-                                   float* run_var, int C, long long rows, float eps, float momentum) {
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ invstd, float* run_mean,
+                                                          float* run_var, int C, long long rows, float eps, float momentum, int chunks) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f, q = 0.f;
-  for (int k = 0; k < kRedChunks; ++k) { s += part[(size_t(k) * 2) * C + c]; q += part[(size_t(k) * 2 + 1) * C + c]; }
+  __shared__ float sm[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s, q;
+  chunk_sums(part, C, chunks, c, s, q, sm);
+  if (c >= C || threadIdx.y) return;
   const float m = s / float(rows);
   const float var = fmaxf(q / float(rows) - m * m, 0.f);
   mean[c] = m;
@@ -100,24 +118,25 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, float* __rest
   }
 }
 // generic second stage: out[which][c] = (accumulate ? out : 0) + scale * sum_chunks part
-__global__ void chan_final_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1, int C, float scale, int accumulate) {
+__global__ void __launch_bounds__(256) chan_final_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1, int C, float scale,
+                                                         int accumulate, int chunks) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f, q = 0.f;
-  for (int k = 0; k < kRedChunks; ++k) { s += part[(size_t(k) * 2) * C + c]; q += part[(size_t(k) * 2 + 1) * C + c]; }
+  __shared__ float sm[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s, q;
+  chunk_sums(part, C, chunks, c, s, q, sm);
+  if (c >= C || threadIdx.y) return;
   if (out0) out0[c] = (accumulate ? out0[c] : 0.f) + scale * s;
   if (out1) out1[c] = (accumulate ? out1[c] : 0.f) + scale * q;
 }
 // scalar second stage of MODE 3 partials: out[0] = (accumulate ? out[0] : 0) + scale * sum of everything
-__global__ void scalar_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C, float scale, int accumulate) {
+__global__ void scalar_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C, float scale, int accumulate, int chunks) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[256];
   float s = 0.f;
-  for (int k = 0; k < kRedChunks; ++k)
-    for (int c = threadIdx.x; c < C; c += 256) s += part[(size_t(k) * 2) * C + c];
+  for (long long i = threadIdx.x; i < (long long)chunks * C; i += 256) s += part[(i / C) * 2 * C + (i % C)];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -288,37 +307,81 @@ __global__ void upsample2x_bwd_kernel(const __half* __restrict__ dy, __half* __r
 }
 
 // MaxPool2d(5, 1, 2) backward (one stage of SPPF's chain): dx[q] = sum over the windows w containing q of dy[w] * [argmax_w == q],
-// argmax = first maximum in row-major window order (torch's max_pool2d_with_indices).  Gather form: deterministic.
-__global__ void maxpool5_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ dx, int B, int H, int W, int C) {
+// argmax = first maximum in row-major window order (torch's max_pool2d_with_indices).  Two gather kernels, deterministic:
+//   1. per window (= per output pixel) and channel: the position code (ky*5 + kx) of its first maximum -> one byte;
+//   2. per input pixel q: the <= 25 windows that contain q; those whose code points at q contribute their dy.
+__global__ void __launch_bounds__(256) maxpool5_argmax_kernel(const __half* __restrict__ x, uint2* __restrict__ code, int B, int H, int W, int C8) {
   pdl_launch_dependents();
   pdl_wait();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= (long long)B * H * W * C) return;
-  const int c = int(i % C);
-  long long p = i / C;
+  if (i >= (long long)B * H * W * C8) return;
+  const int c = int(i % C8);
+  long long p = i / C8;
+  const int wx = int(p % W);
+  p /= W;
+  const int wy = int(p % H), b = int(p / H);
+  const __half* xb = x + (size_t(b) * H * W) * (C8 * 8) + c * 8;
+  float best[8];
+  uint32_t arg[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0u; }
+  for (int ky = 0; ky < 5; ++ky) {
+    const int yy = wy + ky - 2;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < 5; ++kx) {
+      const int xx = wx + kx - 2;
+      if (xx < 0 || xx >= W) continue;
+      float v[8];
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(xb + (size_t(yy) * W + xx) * (C8 * 8))), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (v[e] > best[e]) { best[e] = v[e]; arg[e] = uint32_t(ky * 5 + kx); }
+    }
+  }
+  uint2 o;
+  o.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+  o.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+  code[i] = o;
+}
+__global__ void __launch_bounds__(256) maxpool5_bwd_kernel(const uint2* __restrict__ code, const __half* __restrict__ dy, __half* __restrict__ dx, int B, int H, int W,
+                                                           int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * H * W * C8) return;
+  const int c = int(i % C8);
+  long long p = i / C8;
   const int qx = int(p % W);
   p /= W;
   const int qy = int(p % H), b = int(p / H);
-  const __half* xb = x + size_t(b) * H * W * C + c;
-  const __half* db = dy + size_t(b) * H * W * C + c;
-  const float xq = __half2float(xb[(size_t(qy) * W + qx) * C]);
-  float acc = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   for (int wy = max(qy - 2, 0); wy <= min(qy + 2, H - 1); ++wy)
     for (int wx = max(qx - 2, 0); wx <= min(qx + 2, W - 1); ++wx) {
-      // is q the first maximum of the window centred at (wy, wx)?
-      bool win = true;
-      for (int yy = max(wy - 2, 0); yy <= min(wy + 2, H - 1) && win; ++yy)
-        for (int xx = max(wx - 2, 0); xx <= min(wx + 2, W - 1); ++xx) {
-          const float v = __half2float(xb[(size_t(yy) * W + xx) * C]);
-          const bool before = yy < qy || (yy == qy && xx < qx);
-          if (v > xq || (before && v == xq)) { win = false; break; }
-        }
-      if (win) acc += __half2float(db[(size_t(wy) * W + wx) * C]);
+      const size_t w = ((size_t(b) * H + wy) * W + wx) * C8 + c;
+      const uint2 cd = __ldg(code + w);
+      const uint32_t mine = uint32_t((qy - wy + 2) * 5 + (qx - wx + 2));      // q's position code inside window w
+      float g[8];
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(dy) + w), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t a = ((e < 4 ? cd.x : cd.y) >> (8 * (e & 3))) & 0xffu;
+        if (a == mine) acc[e] += g[e];
+      }
     }
-  dx[i] = __float2half_rn(acc);
+  reinterpret_cast<uint4*>(dx)[i] = pack8h(acc);
 }
 
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+// row chunks of a two-stage channel reduction: about 8 blocks per SM over the whole grid, at least four passes of work per block
+static inline int pick_chunks(long long rows, int C) {
+  const int C8 = C / 8, bx = (C8 + 31) / 32, g = C8 < 32 ? C8 : 32, rpp = 256 / g;
+  long long want = 1184 / bx, cap = (rows + 4ll * rpp - 1) / (4ll * rpp);
+  long long c = want < cap ? want : cap;
+  if (c > kRedChunks) c = kRedChunks;
+  return c < 1 ? 1 : int(c);
+}
 
 }  // namespace icaf
 
@@ -332,10 +395,11 @@ extern "C" int icaf_bn_act_fwd(const void* x, const float* gamma, const float* b
   if (!x || !gamma || !beta || !y || !save_mean || !save_invstd || !workspace || rows < 1 || C < 8 || C % 8) return set_error(ICAF_ERR_BAD_ARG, "bn_act_fwd: bad argument");
   if (workspace_bytes < icaf_train_workspace_bytes(C)) return set_error(ICAF_ERR_BAD_ARG, "bn_act_fwd: workspace too small (icaf_train_workspace_bytes)");
   cudaStream_t st = (cudaStream_t)stream;
-  launch_k(chan_partial_kernel<0>, dim3(nblk(C / 8, 32), kRedChunks), dim3(32, 8), 0, st, (const __half*)x, (const __half*)nullptr, (const float*)nullptr,
-           (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0);
+  const int chunks = pick_chunks(rows, C);
+  launch_k(chan_partial_kernel<0>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)nullptr, (const float*)nullptr,
+           (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0, chunks);
   if (int rc = check_launch("bn_act_fwd(stats)")) return rc;
-  launch_k(bn_finalize_kernel, dim3(nblk(C, 128)), dim3(128), 0, st, (const float*)workspace, save_mean, save_invstd, run_mean, run_var, C, (long long)rows, eps, momentum);
+  launch_k(bn_finalize_kernel, dim3(nblk(C, 32)), dim3(32, 8), 0, st, (const float*)workspace, save_mean, save_invstd, run_mean, run_var, C, (long long)rows, eps, momentum, chunks);
   if (int rc = check_launch("bn_act_fwd(finalize)")) return rc;
   const long long n8 = rows * (C / 8);
   launch_k(affine_act_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, gamma, beta, (const float*)save_mean, (const float*)save_invstd, (__half*)y, n8, C / 8, act);
@@ -349,13 +413,14 @@ extern "C" int icaf_bn_act_bwd(const void* x, const void* dy, const float* gamma
   if (workspace_bytes < icaf_train_workspace_bytes(C) + 2 * size_t(C) * sizeof(float)) return set_error(ICAF_ERR_BAD_ARG, "bn_act_bwd: workspace too small (icaf_train_workspace_bytes + 2 C floats)");
   cudaStream_t st = (cudaStream_t)stream;
   float* sums = workspace + size_t(kRedChunks) * 2 * C;     // [2][C]: S1 = sum dz, S2 = sum dz xhat
-  launch_k(chan_partial_kernel<1>, dim3(nblk(C / 8, 32), kRedChunks), dim3(32, 8), 0, st, (const __half*)x, (const __half*)dy, gamma, beta, save_mean, save_invstd,
-           workspace, (long long)rows, C, act);
+  const int chunks = pick_chunks(rows, C);
+  launch_k(chan_partial_kernel<1>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)dy, gamma, beta, save_mean, save_invstd,
+           workspace, (long long)rows, C, act, chunks);
   if (int rc = check_launch("bn_act_bwd(partial)")) return rc;
-  launch_k(chan_final_kernel, dim3(nblk(C, 128)), dim3(128), 0, st, (const float*)workspace, sums, sums + C, C, 1.0f, 0);
+  launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, 8), 0, st, (const float*)workspace, sums, sums + C, C, 1.0f, 0, chunks);
   if (int rc = check_launch("bn_act_bwd(sums)")) return rc;
   if (dgamma || dbeta) {                                    // parameter gradients: dbeta = S1, dgamma = S2 (unscaled by the loss scale)
-    launch_k(chan_final_kernel, dim3(nblk(C, 128)), dim3(128), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate);
+    launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, 8), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks);
     if (int rc = check_launch("bn_act_bwd(param grads)")) return rc;
   }
   const long long n8 = rows * (C / 8);
@@ -386,10 +451,11 @@ extern "C" int icaf_layernorm_bwd(const void* x, const void* dy, const float* ga
   launch_k(ln_bwd_kernel, dim3(nblk(rows, 4)), dim3(128), 0, st, (const __half*)x, (const __half*)dy, gamma, (__half*)dx, rmean, rrstd, (long long)rows, C, eps);
   if (int rc = check_launch("layernorm_bwd(dx)")) return rc;
   if (dgamma || dbeta) {
-    launch_k(chan_partial_kernel<2>, dim3(nblk(C / 8, 32), kRedChunks), dim3(32, 8), 0, st, (const __half*)x, (const __half*)dy, (const float*)nullptr, (const float*)nullptr,
-             (const float*)rmean, (const float*)rrstd, workspace, (long long)rows, C, 0);
+    const int chunks = pick_chunks(rows, C);
+    launch_k(chan_partial_kernel<2>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (const float*)nullptr, (const float*)nullptr,
+             (const float*)rmean, (const float*)rrstd, workspace, (long long)rows, C, 0, chunks);
     if (int rc = check_launch("layernorm_bwd(partial)")) return rc;
-    launch_k(chan_final_kernel, dim3(nblk(C, 128)), dim3(128), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate);
+    launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, 8), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks);
     if (int rc = check_launch("layernorm_bwd(param grads)")) return rc;
   }
   return ICAF_OK;
@@ -401,10 +467,11 @@ extern "C" int icaf_dot(const void* x, const void* y, int64_t rows, int C, float
   if (!x || !y || !out || !workspace || rows < 1 || C < 8 || C % 8) return set_error(ICAF_ERR_BAD_ARG, "dot: bad argument");
   if (workspace_bytes < icaf_train_workspace_bytes(C)) return set_error(ICAF_ERR_BAD_ARG, "dot: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  launch_k(chan_partial_kernel<3>, dim3(nblk(C / 8, 32), kRedChunks), dim3(32, 8), 0, st, (const __half*)x, (const __half*)y, (const float*)nullptr, (const float*)nullptr,
-           (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0);
+  const int chunks = pick_chunks(rows, C);
+  launch_k(chan_partial_kernel<3>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)y, (const float*)nullptr, (const float*)nullptr,
+           (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0, chunks);
   if (int rc = check_launch("dot(partial)")) return rc;
-  launch_k(scalar_final_kernel, dim3(1), dim3(256), 0, st, (const float*)workspace, out, C, scale, accumulate);
+  launch_k(scalar_final_kernel, dim3(1), dim3(256), 0, st, (const float*)workspace, out, C, scale, accumulate, chunks);
   return check_launch("dot");
 }
 
@@ -414,8 +481,13 @@ extern "C" int icaf_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W
   return check_launch("upsample2x_bwd");
 }
 
-extern "C" int icaf_maxpool5_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream) {
-  if (!x || !dy || !dx) return set_error(ICAF_ERR_BAD_ARG, "maxpool5_bwd: null pointer");
-  launch_k(maxpool5_bwd_kernel, dim3(nblk((long long)B * H * W * C, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, (const __half*)dy, (__half*)dx, B, H, W, C);
+extern "C" int icaf_maxpool5_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !dy || !dx || !workspace || C % 8 || B < 1 || H < 1 || W < 1) return set_error(ICAF_ERR_BAD_ARG, "maxpool5_bwd: null pointer or C % 8");
+  if (workspace_bytes < size_t(B) * H * W * C || (reinterpret_cast<uintptr_t>(workspace) & 7)) return set_error(ICAF_ERR_BAD_ARG, "maxpool5_bwd: workspace needs B*H*W*C bytes, 8-byte aligned");
+  const long long n8 = (long long)B * H * W * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_k(maxpool5_argmax_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (uint2*)workspace, B, H, W, C / 8);
+  if (int rc = check_launch("maxpool5_bwd(argmax)")) return rc;
+  launch_k(maxpool5_bwd_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const uint2*)workspace, (const __half*)dy, (__half*)dx, B, H, W, C / 8);
   return check_launch("maxpool5_bwd");
 }

@@ -496,8 +496,10 @@ def dmff_pool_tokens_bwd(x_vis, x_ir, dtok_vis, dtok_ir, mix, nh: int, nw: int):
         assert t.is_contiguous() and t.dtype == torch.float16 and tuple(t.shape) == (B, n_pad, Cc)
     dx_v = torch.empty(B, H, W, Cc, dtype=torch.float16, device=x_vis.device)
     dx_i = torch.empty_like(dx_v)
+    ws = torch.empty((2 * B * nh * nw * Cc + 7) // 8, dtype=torch.int64, device=x_vis.device)
     _call("icaf_dmff_pool_tokens_bwd", _lib.lib().icaf_dmff_pool_tokens_bwd,
-          (_ptr(x_vis), _ptr(x_ir), ld, _ptr(dtok_vis), _ptr(dtok_ir), _ptr(mix), _ptr(dx_v), _ptr(dx_i), B, H, W, Cc, nh, nw, n_pad),
+          (_ptr(x_vis), _ptr(x_ir), ld, _ptr(dtok_vis), _ptr(dtok_ir), _ptr(mix), _ptr(dx_v), _ptr(dx_i), B, H, W, Cc, nh, nw, n_pad, _ptr(ws),
+           C.c_size_t(ws.numel() * 8)),
           {"bytes": 2.0 * 2 * (2 * x_vis.numel() + dtok_vis.numel())})
     return dx_v, dx_i
 
@@ -771,5 +773,7 @@ def maxpool5_bwd(x, dy):
     B, H, W, Cc = x.shape
     x, dy = x.contiguous(), dy.contiguous()
     dx = torch.empty_like(x)
-    _call("icaf_maxpool5_bwd", _lib.lib().icaf_maxpool5_bwd, (_ptr(x), _ptr(dy), _ptr(dx), B, H, W, Cc), {"bytes": 6.0 * x.numel()})
+    ws = torch.empty((x.numel() + 7) // 8, dtype=torch.int64, device=x.device)
+    _call("icaf_maxpool5_bwd", _lib.lib().icaf_maxpool5_bwd, (_ptr(x), _ptr(dy), _ptr(dx), B, H, W, Cc, _ptr(ws), C.c_size_t(ws.numel() * 8)),
+          {"bytes": 7.0 * x.numel()})
     return dx

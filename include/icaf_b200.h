@@ -300,14 +300,16 @@ int icaf_dot(const void* x, const void* y, int64_t rows, int C, float* out, floa
              void* stream);
 /* Backward of nn.Upsample(None, 2, 'nearest'): dx (B, H, W, C) = sums of the 2 x 2 blocks of dy (B, 2H, 2W, C). */
 int icaf_upsample2x_bwd(const void* dy, void* dx, int B, int H, int W, int C, void* stream);
-/* Backward of one MaxPool2d(5, 1, 2) of SPPF's chain (common.py:259-266): x is that pool's input, dy the gradient of its output. */
-int icaf_maxpool5_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+/* Backward of one MaxPool2d(5, 1, 2) of SPPF's chain (common.py:259-266): x is that pool's input, dy the gradient of its output
+ * (dense fp16 NHWC, C % 8 == 0).  workspace: B*H*W*C bytes (one arg-max code per window and channel), 8-byte aligned. */
+int icaf_maxpool5_bwd(const void* x, const void* dy, void* dx, int B, int H, int W, int C, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of icaf_dmff_pool_tokens w.r.t. the two feature maps (dense fp16 (B,H,W,C) gradients): every pixel gathers, from
  * each pooling window that contains it, dtok * (w_avg / window + w_max * [pixel is the window's first maximum]).  The
  * gradients of the mixing weights and positional embeddings are plain reductions of dtok (icaf_dot / icaf_colsum). */
 int icaf_dmff_pool_tokens_bwd(const void* x_vis, const void* x_ir, int64_t x_ld, const void* dtok_vis, const void* dtok_ir, const float* mix,
-                              void* dx_vis, void* dx_ir, int B, int H, int W, int C, int nh, int nw, int n_pad, void* stream);
+                              void* dx_vis, void* dx_ir, int B, int H, int W, int C, int nh, int nw, int n_pad, void* workspace,
+                              size_t workspace_bytes, void* stream);   /* workspace: 2*B*nh*nw*C bytes (arg-max codes), 8-byte aligned */
 /* Backward of icaf_dmff_upsample_cat (mode 1, nearest: the training-mode tail, common.py:828-829) w.r.t. the token streams:
  * dtok[b][n] = sum of dcat over the pixels token n was copied to (pad rows get 0).  dcat: (B,H,W,2C) with pixel pitch d_ld;
  * the gradients of the two residual inputs are its channel halves. */
