@@ -24,7 +24,7 @@ from torch.autograd import Function
 from . import ops
 from .ops import ACT_NONE, ACT_SILU
 
-_STATE = {"seed": 0x1234567, "count": 0}
+_STATE = {"seed": 0x1234567, "count": 0, "defer_bn": False, "bn": []}
 
 
 def manual_seed(seed: int) -> None:
@@ -55,8 +55,10 @@ class ConvBnActFn(Function):
         z = ops.conv2d([x], [pk])[0]
         mom = 0.1 if bn.momentum is None else bn.momentum
         y, sm, si = ops.bn_act_fwd(z, _f32(gamma), _f32(beta), bn.running_mean, bn.running_var, bn.eps, mom, act)
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+        if bn.num_batches_tracked is not None:     # nn.BatchNorm2d's step counter: one fused increment per model forward
+            _STATE["bn"].append(bn.num_batches_tracked)
+            if not _STATE["defer_bn"]:
+                _flush_bn_counters()
         ctx.save_for_backward(x, z, weight, gamma, beta, sm, si)
         ctx.cfg = (stride, pad, act, stem)
         return y
@@ -77,6 +79,12 @@ class ConvBnActFn(Function):
             dw = ops.conv2d_wgrad(x, dz, kh, kw, stride, pad)
             dx = ops.conv2d_dgrad(dz, _f32(weight), stride, pad, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[0] else None
         return dx, dw.to(weight.dtype), dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, None, None, None, None
+
+
+def _flush_bn_counters() -> None:
+    if _STATE["bn"]:
+        torch._foreach_add_(_STATE["bn"], 1)
+        _STATE["bn"] = []
 
 
 def conv_bn_act(m, x: torch.Tensor, stem: bool = False) -> torch.Tensor:
@@ -272,8 +280,9 @@ class PoolTokensFn(Function):
         dpos = [ops.colsum(t.view(B, n_pad * C))[:N * C].view(1, N, C).to(pdt) for t in (dtv, dti)]
         zero = torch.zeros(N, C, dtype=torch.float16, device=rgb.device)
         dev = rgb.device
-        avg = ops.dmff_pool_tokens(rgb, ir, zero, zero, torch.tensor([1.0, 0.0, 1.0, 0.0], device=dev), nh, nw)
-        mx = ops.dmff_pool_tokens(rgb, ir, zero, zero, torch.tensor([0.0, 1.0, 0.0, 1.0], device=dev), nh, nw)
+        even = (torch.arange(4, device=dev) % 2 == 0).float()          # (1, 0, 1, 0), built on the device (graph-capture safe)
+        avg = ops.dmff_pool_tokens(rgb, ir, zero, zero, even, nh, nw)
+        mx = ops.dmff_pool_tokens(rgb, ir, zero, zero, 1.0 - even, nh, nw)
         dw = [ops.dot(dtv, avg[0]), ops.dot(dtv, mx[0]), ops.dot(dti, avg[1]), ops.dot(dti, mx[1])]
         return (dx_v if ctx.needs_input_grad[0] else None, dx_i if ctx.needs_input_grad[1] else None, dpos[0], dpos[1],
                 dw[0].to(wdt), dw[1].to(wdt), dw[2].to(wdt), dw[3].to(wdt), None, None)
@@ -436,6 +445,15 @@ def detect(m, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
 def model_forward(model, rgb_img: torch.Tensor, ir_img: torch.Tensor, taps: list = None):
     """The layer walk of Model.forward_once (yolo_test.py:136-163) over the training-mode nodes.  `taps` (diagnostics): receives
     every layer's NHWC output."""
+    _STATE["defer_bn"], _STATE["bn"] = True, []
+    try:
+        return _walk(model, rgb_img, ir_img, taps)
+    finally:
+        _STATE["defer_bn"] = False
+        _flush_bn_counters()
+
+
+def _walk(model, rgb_img, ir_img, taps):
     from .common import C3, SPPF, Concat, Conv, TransformerFusionBlock
     from .yolo_test import Detect
     y: list = []

@@ -128,3 +128,13 @@ extern "C" int icaf_sm_count(void) {
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
   return sms;
 }
+
+// Device-side offset added to every dropout seed (read by the kernels at run time): a captured CUDA graph of the training step
+// keeps its host-side seeds, so the caller bumps this counter on the device between replays to draw fresh masks.
+static const uint32_t* g_seed_offset = nullptr;
+namespace icaf { const uint32_t* seed_offset_ptr() { return g_seed_offset; } }
+extern "C" int icaf_set_seed_offset(const void* device_u32) {
+  g_seed_offset = (const uint32_t*)device_u32;
+  return ICAF_OK;
+}
+

@@ -27,6 +27,7 @@ struct AttnParams {
   int ld;                // row pitch of qk: 2C, or 3C in the fused-qkv form ([q | k | v])
   float p_drop;          // training forward only (TRAIN instantiation): dropout on the probabilities (common.py:677,680)
   uint32_t seed;
+  const uint32_t* seed_off;   // optional device-side offset (icaf_set_seed_offset)
   float scale_log2;      // log2(e) / sqrt(d)
 };
 
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::kCtas) cross_attn_tma_kernel(
             rs += hf.x + hf.y;
             if (TRAIN) {
               const float ks = 1.f / (1.f - P.p_drop);
-              const bool k0 = attn_keep(P.seed, dir, blockIdx.y, qn, kv0 + cb + i, P.p_drop), k1 = attn_keep(P.seed, dir, blockIdx.y, qn, kv0 + cb + i + 1, P.p_drop);
+              const bool k0 = attn_keep(P.seed + (P.seed_off ? __ldg(P.seed_off) : 0u), dir, blockIdx.y, qn, kv0 + cb + i, P.p_drop), k1 = attn_keep(P.seed + (P.seed_off ? __ldg(P.seed_off) : 0u), dir, blockIdx.y, qn, kv0 + cb + i + 1, P.p_drop);
               h = __floats2half2_rn(k0 ? hf.x * ks : 0.f, k1 ? hf.y * ks : 0.f);
             }
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::kCtas) cross_attn_tma_kernel(
             rs += hf.x + hf.y;
             if (TRAIN) {
               const float ks = 1.f / (1.f - P.p_drop);
-              const bool k0 = attn_keep(P.seed, dir, blockIdx.y, qn, kv0 + cb + i, P.p_drop), k1 = attn_keep(P.seed, dir, blockIdx.y, qn, kv0 + cb + i + 1, P.p_drop);
+              const bool k0 = attn_keep(P.seed + (P.seed_off ? __ldg(P.seed_off) : 0u), dir, blockIdx.y, qn, kv0 + cb + i, P.p_drop), k1 = attn_keep(P.seed + (P.seed_off ? __ldg(P.seed_off) : 0u), dir, blockIdx.y, qn, kv0 + cb + i + 1, P.p_drop);
               h = __floats2half2_rn(k0 ? hf.x * ks : 0.f, k1 ? hf.y * ks : 0.f);
             }
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
@@ -384,7 +385,7 @@ static int fill_attn(const void* qk_vis, const void* qk_ir, const void* vt_vis, 
   P.out[0] = (__half*)out_vis; P.out[1] = (__half*)out_ir;
   P.B = B; P.N = N; P.n_pad = n_pad; P.C = C; P.heads = heads;
   P.ld = vt_vis ? 2 * C : 3 * C;
-  P.p_drop = 0.f; P.seed = 0u;
+  P.p_drop = 0.f; P.seed = 0u; P.seed_off = nullptr;
   P.scale_log2 = 1.4426950408889634f / sqrtf(float(d));   // 1/sqrt(d_k), common.py:670
   return ICAF_OK;
 }
@@ -447,7 +448,7 @@ extern "C" int icaf_cross_attention_train(const void* qkv_vis, const void* qkv_i
   if (!(p_drop >= 0.f && p_drop < 1.f)) return set_error(ICAF_ERR_BAD_ARG, "cross_attention_train: dropout probability must be in [0, 1)");
   if ((uint64_t(B) * n_pad * 2) % 16 || (reinterpret_cast<uintptr_t>(qkv_vis) & 15) || (reinterpret_cast<uintptr_t>(qkv_ir) & 15))
     return set_error(ICAF_ERR_BAD_ARG, "cross_attention_train: TMA needs 16-byte aligned tensors and row pitches");
-  P.p_drop = p_drop; P.seed = seed;
+  P.p_drop = p_drop; P.seed = seed; P.seed_off = seed_offset_ptr();
   cudaStream_t st = (cudaStream_t)stream;
   if (p_drop == 0.f) return dispatch_attn<true>(P, st);
   switch (C / heads) {

@@ -18,6 +18,7 @@ struct AttnBwdParams {
   int B, N, n_pad, C, heads;
   float scale_log2, scale, p_drop;
   uint32_t seed;
+  const uint32_t* seed_off;   // optional device-side offset (icaf_set_seed_offset)
 };
 
 constexpr int kBT = 128;   // rows (queries or keys) per block
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kBT) attn_bwd_q_kernel(const AttnBwdParams P) 
         dp += __half2float(dT[c * kBT + threadIdx.x]) * __half2float(vt[j * D + c]);
       }
       const float p = exp2f(s * P.scale_log2 - m) * inv_l;
-      if (P.p_drop > 0.f) dp = attn_keep(P.seed, dir, bh, i, j0 + j, P.p_drop) ? dp * keep_scale : 0.f;
+      if (P.p_drop > 0.f) dp = attn_keep(P.seed + (P.seed_off ? __ldg(P.seed_off) : 0u), dir, bh, i, j0 + j, P.p_drop) ? dp * keep_scale : 0.f;
       const float ds = p * (dp - delta) * P.scale;
 #pragma unroll
       for (int c = 0; c < D; ++c) dq[c] += ds * __half2float(kt[j * D + c]);
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kBT) attn_bwd_kv_kernel(const AttnBwdParams P)
         const float p = exp2f(s * P.scale_log2 - st[i * 3]) * st[i * 3 + 1];
         float pd = p;
         if (P.p_drop > 0.f) {
-          const bool keep = attn_keep(P.seed, dir, bh, i0 + i, j, P.p_drop);
+          const bool keep = attn_keep(P.seed + (P.seed_off ? __ldg(P.seed_off) : 0u), dir, bh, i0 + i, j, P.p_drop);
           pd = keep ? p * keep_scale : 0.f;
           dp = keep ? dp * keep_scale : 0.f;
         }
@@ -228,7 +229,7 @@ extern "C" int icaf_cross_attention_bwd(const void* qkv_vis, const void* qkv_ir,
   P.qkv[0] = (const __half*)qkv_vis; P.qkv[1] = (const __half*)qkv_ir; P.o[0] = (const __half*)out_vis; P.o[1] = (const __half*)out_ir;
   P.dout[0] = (const __half*)dout_vis; P.dout[1] = (const __half*)dout_ir; P.dqkv[0] = (__half*)dqkv_vis; P.dqkv[1] = (__half*)dqkv_ir;
   P.stats = (float*)workspace; P.B = B; P.N = N; P.n_pad = n_pad; P.C = C; P.heads = heads;
-  P.scale = 1.0f / sqrtf(float(d)); P.scale_log2 = 1.4426950408889634f * P.scale; P.p_drop = p_drop; P.seed = seed;
+  P.scale = 1.0f / sqrtf(float(d)); P.scale_log2 = 1.4426950408889634f * P.scale; P.p_drop = p_drop; P.seed = seed; P.seed_off = seed_offset_ptr();
   cudaStream_t st = (cudaStream_t)stream;
   switch (d) {
     case 16: return launch_attn_bwd<16>(P, st);

@@ -12,6 +12,7 @@ namespace icaf {
 
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* where);
+const uint32_t* seed_offset_ptr();    // see icaf_set_seed_offset
 int check_launch(const char* where);   // cudaGetLastError after a launch; never synchronises
 int sm_count_cached();   // SM count of the CURRENT device (cached per device ordinal)
 int current_device();    // cudaGetDevice; -1 on error

@@ -87,23 +87,27 @@ __global__ void __launch_bounds__(256) chan_partial_kernel(const __half* __restr
   }
 }
 
-// second stages: block (32 channels, 8 chunk lanes); lane y sums chunks y, y + 8, ...; the 8 lane sums are added in lane order
-__device__ __forceinline__ void chunk_sums(const float* __restrict__ part, int C, int chunks, int c, float& s, float& q, float (*sm)[8][32]) {
+// second stages: block (32 channels, 32 chunk lanes); lane y sums chunks y, y + 32, ...; the 32 lane sums are added in lane order
+constexpr int kFinLanes = 32;
+__device__ __forceinline__ void chunk_sums(const float* __restrict__ part, int C, int chunks, int c, float& s, float& q, float (*sm)[kFinLanes][33]) {
   float a = 0.f, b2 = 0.f;
-  if (c < C)
-    for (int k = threadIdx.y; k < chunks; k += 8) { a += part[(size_t(k) * 2) * C + c]; b2 += part[(size_t(k) * 2 + 1) * C + c]; }
+  if (c < C) {
+#pragma unroll 4
+    for (int k = threadIdx.y; k < chunks; k += kFinLanes) { a += __ldg(part + (size_t(k) * 2) * C + c); b2 += __ldg(part + (size_t(k) * 2 + 1) * C + c); }
+  }
   sm[0][threadIdx.y][threadIdx.x] = a; sm[1][threadIdx.y][threadIdx.x] = b2;
   __syncthreads();
   s = q = 0.f;
-  for (int y = 0; y < 8; ++y) { s += sm[0][y][threadIdx.x]; q += sm[1][y][threadIdx.x]; }
+  if (threadIdx.y == 0)
+    for (int y = 0; y < kFinLanes; ++y) { s += sm[0][y][threadIdx.x]; q += sm[1][y][threadIdx.x]; }
 }
 
 // BatchNorm statistics, second stage: mean, invstd, and the running statistics update (momentum, unbiased variance)
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ invstd, float* run_mean,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ invstd, float* run_mean,
                                                           float* run_var, int C, long long rows, float eps, float momentum, int chunks) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float sm[2][8][32];
+  __shared__ float sm[2][kFinLanes][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s, q;
   chunk_sums(part, C, chunks, c, s, q, sm);
@@ -118,15 +122,18 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   }
 }
 // generic second stage: out[which][c] = (accumulate ? out : 0) + scale * sum_chunks part
-__global__ void __launch_bounds__(256) chan_final_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1, int C, float scale,
-                                                         int accumulate, int chunks) {
+// out0/out1: sums (scale, accumulate); raw0/raw1 (optional): the unscaled sums as well (BatchNorm backward needs both in one pass)
+__global__ void __launch_bounds__(1024) chan_final_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1, int C, float scale,
+                                                          int accumulate, int chunks, float* __restrict__ raw0, float* __restrict__ raw1) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float sm[2][8][32];
+  __shared__ float sm[2][kFinLanes][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s, q;
   chunk_sums(part, C, chunks, c, s, q, sm);
   if (c >= C || threadIdx.y) return;
+  if (raw0) raw0[c] = s;
+  if (raw1) raw1[c] = q;
   if (out0) out0[c] = (accumulate ? out0[c] : 0.f) + scale * s;
   if (out1) out1[c] = (accumulate ? out1[c] : 0.f) + scale * q;
 }
@@ -134,12 +141,13 @@ __global__ void __launch_bounds__(256) chan_final_kernel(const float* __restrict
 __global__ void scalar_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C, float scale, int accumulate, int chunks) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float red[256];
+  __shared__ float red[1024];
   float s = 0.f;
-  for (long long i = threadIdx.x; i < (long long)chunks * C; i += 256) s += part[(i / C) * 2 * C + (i % C)];
+  for (int k = 0; k < chunks; ++k)
+    for (int c = threadIdx.x; c < C; c += 1024) s += __ldg(part + (size_t(k) * 2) * C + c);
   red[threadIdx.x] = s;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = 512; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
@@ -198,7 +206,8 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t a, uint32_t b, uint32_t c)
   return h;
 }
 template <int MODE>
-__global__ void eltwise_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ y, long long n8, float p, uint32_t seed) {
+__global__ void eltwise_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ y, long long n8, float p, uint32_t seed,
+                               const uint32_t* __restrict__ seed_off) {
   pdl_launch_dependents();
   pdl_wait();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -216,7 +225,7 @@ __global__ void eltwise_kernel(const __half* __restrict__ x, const __half* __res
     }
     if (MODE == 2) {
       const long long idx = i * 8 + e;
-      const uint32_t h = hash_u32(uint32_t(idx), uint32_t(idx >> 32), seed);
+      const uint32_t h = hash_u32(uint32_t(idx), uint32_t(idx >> 32), seed + (seed_off ? __ldg(seed_off) : 0u));
       xv[e] = (float(h >> 8) * (1.f / 16777216.f) >= p) ? xv[e] / (1.f - p) : 0.f;
     }
   }
@@ -375,11 +384,11 @@ __global__ void __launch_bounds__(256) maxpool5_bwd_kernel(const uint2* __restri
 
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 // row chunks of a two-stage channel reduction: about 8 blocks per SM over the whole grid, at least four passes of work per block
-static inline int pick_chunks(long long rows, int C) {
+static inline int pick_chunks(long long rows, int C, int cap_chunks = kRedChunks) {
   const int C8 = C / 8, bx = (C8 + 31) / 32, g = C8 < 32 ? C8 : 32, rpp = 256 / g;
   long long want = 1184 / bx, cap = (rows + 4ll * rpp - 1) / (4ll * rpp);
   long long c = want < cap ? want : cap;
-  if (c > kRedChunks) c = kRedChunks;
+  if (c > cap_chunks) c = cap_chunks;
   return c < 1 ? 1 : int(c);
 }
 
@@ -399,7 +408,7 @@ extern "C" int icaf_bn_act_fwd(const void* x, const float* gamma, const float* b
   launch_k(chan_partial_kernel<0>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)nullptr, (const float*)nullptr,
            (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0, chunks);
   if (int rc = check_launch("bn_act_fwd(stats)")) return rc;
-  launch_k(bn_finalize_kernel, dim3(nblk(C, 32)), dim3(32, 8), 0, st, (const float*)workspace, save_mean, save_invstd, run_mean, run_var, C, (long long)rows, eps, momentum, chunks);
+  launch_k(bn_finalize_kernel, dim3(nblk(C, 32)), dim3(32, kFinLanes), 0, st, (const float*)workspace, save_mean, save_invstd, run_mean, run_var, C, (long long)rows, eps, momentum, chunks);
   if (int rc = check_launch("bn_act_fwd(finalize)")) return rc;
   const long long n8 = rows * (C / 8);
   launch_k(affine_act_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, gamma, beta, (const float*)save_mean, (const float*)save_invstd, (__half*)y, n8, C / 8, act);
@@ -417,12 +426,10 @@ extern "C" int icaf_bn_act_bwd(const void* x, const void* dy, const float* gamma
   launch_k(chan_partial_kernel<1>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)dy, gamma, beta, save_mean, save_invstd,
            workspace, (long long)rows, C, act, chunks);
   if (int rc = check_launch("bn_act_bwd(partial)")) return rc;
-  launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, 8), 0, st, (const float*)workspace, sums, sums + C, C, 1.0f, 0, chunks);
+  // one second stage: the raw sums for the apply pass and the parameter gradients dbeta = S1, dgamma = S2 (scaled by grad_scale)
+  launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, kFinLanes), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks, sums,
+           sums + C);
   if (int rc = check_launch("bn_act_bwd(sums)")) return rc;
-  if (dgamma || dbeta) {                                    // parameter gradients: dbeta = S1, dgamma = S2 (unscaled by the loss scale)
-    launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, 8), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks);
-    if (int rc = check_launch("bn_act_bwd(param grads)")) return rc;
-  }
   const long long n8 = rows * (C / 8);
   launch_k(bn_bwd_apply_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, gamma, beta, save_mean, save_invstd, (const float*)sums,
            (__half*)dx, n8, C / 8, 1.0f / float(rows), act);
@@ -435,9 +442,9 @@ extern "C" int icaf_eltwise(int mode, const void* x, const void* dy, void* y, in
   if (n == 0) return ICAF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const long long n8 = n / 8;
-  if (mode == 0) launch_k(eltwise_kernel<0>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed);
-  else if (mode == 1) launch_k(eltwise_kernel<1>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed);
-  else launch_k(eltwise_kernel<2>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed);
+  if (mode == 0) launch_k(eltwise_kernel<0>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed, seed_offset_ptr());
+  else if (mode == 1) launch_k(eltwise_kernel<1>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed, seed_offset_ptr());
+  else launch_k(eltwise_kernel<2>, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (__half*)y, n8, p, seed, seed_offset_ptr());
   return check_launch("eltwise");
 }
 
@@ -455,7 +462,8 @@ extern "C" int icaf_layernorm_bwd(const void* x, const void* dy, const float* ga
     launch_k(chan_partial_kernel<2>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (const float*)nullptr, (const float*)nullptr,
              (const float*)rmean, (const float*)rrstd, workspace, (long long)rows, C, 0, chunks);
     if (int rc = check_launch("layernorm_bwd(partial)")) return rc;
-    launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, 8), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks);
+    launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, kFinLanes), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks,
+             (float*)nullptr, (float*)nullptr);
     if (int rc = check_launch("layernorm_bwd(param grads)")) return rc;
   }
   return ICAF_OK;
@@ -467,11 +475,11 @@ extern "C" int icaf_dot(const void* x, const void* y, int64_t rows, int C, float
   if (!x || !y || !out || !workspace || rows < 1 || C < 8 || C % 8) return set_error(ICAF_ERR_BAD_ARG, "dot: bad argument");
   if (workspace_bytes < icaf_train_workspace_bytes(C)) return set_error(ICAF_ERR_BAD_ARG, "dot: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int chunks = pick_chunks(rows, C);
+  const int chunks = pick_chunks(rows, C, 64);
   launch_k(chan_partial_kernel<3>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)y, (const float*)nullptr, (const float*)nullptr,
            (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0, chunks);
   if (int rc = check_launch("dot(partial)")) return rc;
-  launch_k(scalar_final_kernel, dim3(1), dim3(256), 0, st, (const float*)workspace, out, C, scale, accumulate, chunks);
+  launch_k(scalar_final_kernel, dim3(1), dim3(1024), 0, st, (const float*)workspace, out, C, scale, accumulate, chunks);
   return check_launch("dot");
 }
 

@@ -20,6 +20,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .common import CrossTransformerBlock
 from .loss import ComputeLoss
 
@@ -104,3 +105,63 @@ class TrainStep:
         self.scaler.update()
         self.optimizer.zero_grad(set_to_none=True)
         return loss.detach(), items
+
+
+class GraphedTrainStep:
+    """The same step with forward + loss + scaled backward (+ DDP's bucketed all-reduce) captured ONCE as a CUDA graph and
+    replayed per batch: the ~3000 kernel launches of a yolov5l step cost the host more time than the GPU needs to run them.
+    Static shapes: (B,3,H,W) uint8 batches and at most `max_targets` label rows (unused rows carry image index -1, which
+    build_targets rejects).  The optimiser step and GradScaler.update stay eager (train.py:348-350; GradScaler reads its
+    inf flag on the host).  Dropout masks: the kernels add a device-side step counter to their seeds (icaf_set_seed_offset),
+    incremented inside the graph, so every replay draws new masks.
+
+    DDP (world_size > 1): construct the TrainStep inside ``torch.cuda.stream(side)`` and set TORCH_NCCL_ASYNC_ERROR_HANDLING=0
+    before init_process_group, as torch's CUDA-graph notes require; 11 eager iterations run before the capture."""
+
+    def __init__(self, ts: TrainStep, B: int, H: int, W: int, max_targets: int, device, warmup: Optional[int] = None):
+        self.ts = ts
+        dev = torch.device(device)
+        self.rgb = torch.zeros(B, 3, H, W, dtype=torch.uint8, device=dev)
+        self.ir = torch.zeros_like(self.rgb)
+        self.tg = torch.zeros(max_targets, 6, dtype=torch.float32, device=dev)
+        self.tg[:, 0] = -1.0
+        self.seed_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().icaf_set_seed_offset(self.seed_ctr.data_ptr()), "icaf_set_seed_offset")
+        self.max_targets = max_targets
+        warmup = (11 if ts.world_size > 1 else 3) if warmup is None else warmup
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # real steps on the zero batch: allocator, cuBLAS-free lazy inits, DDP buckets
+                self.seed_ctr += 1
+                ts(self.rgb, self.ir, self.tg)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        ts.optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.seed_ctr += 1
+            pred = ts.model(self.rgb, self.ir)
+            loss, self.items = ts.compute_loss(pred, self.tg)
+            if ts.world_size > 1:
+                loss = loss * ts.world_size
+            self.loss = loss
+            ts.scaler.scale(loss).backward()
+
+    def __call__(self, rgb: torch.Tensor, ir: torch.Tensor, targets: torch.Tensor):
+        nt = int(targets.shape[0])
+        if nt > self.max_targets:
+            raise ValueError(f"GraphedTrainStep: {nt} label rows, captured for at most {self.max_targets}")
+        self.rgb.copy_(rgb, non_blocking=True)
+        self.ir.copy_(ir, non_blocking=True)
+        self.tg[:nt].copy_(targets, non_blocking=True)
+        if nt < self.max_targets:
+            self.tg[nt:, 0] = -1.0
+        self.graph.replay()
+        self.ts.scaler.step(self.ts.optimizer)            # gradients live in static buffers the next replay overwrites
+        self.ts.scaler.update()
+        return self.loss.detach(), self.items
+
+    def close(self) -> None:
+        _lib.lib().icaf_set_seed_offset(None)

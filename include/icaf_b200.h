@@ -321,6 +321,11 @@ int icaf_dmff_upsample_cat_bwd(const void* dcat, int64_t d_ld, void* dtok_vis, v
 int icaf_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, int chan_pad, int rows, int k_pad, int transpose_flip, void* out,
                      void* stream);
 
+/* Optional device-side counter (one uint32) added to every dropout seed by the kernels at run time (NULL switches it off).  A
+ * captured CUDA graph of the training step keeps its host-side seeds; bumping this counter on the device between replays gives
+ * every replay fresh dropout masks, and the forward / backward kernels of one step still regenerate identical masks. */
+int icaf_set_seed_offset(const void* device_u32);
+
 /* Training-mode forward of the fused form: like icaf_cross_attention(qkv_vis, qkv_ir, NULL, NULL, ...) plus dropout with
  * probability p_drop on the attention probabilities (common.py:677,680; counter-based mask keyed by `seed`, reproduced by the
  * backward below). */
