@@ -87,7 +87,8 @@ class TrainStep:
         self.world_size = world_size
         if world_size > 1:
             from torch.nn.parallel import DistributedDataParallel as DDP
-            model = DDP(model, device_ids=[local_rank], output_device=local_rank, find_unused_parameters=False)   # train.py:233
+            model = DDP(model, device_ids=[local_rank], output_device=local_rank, find_unused_parameters=False,       # train.py:233
+                        gradient_as_bucket_view=True)              # .grad aliases the all-reduce buckets: no copy in / out
         self.model = model
         self.scaler = torch.amp.GradScaler("cuda", enabled=amp_scale)                 # train.py:282
         self.compute_loss = ComputeLoss(self.raw_model)                               # train.py:284
@@ -129,6 +130,9 @@ class GraphedTrainStep:
         _lib.check(_lib.lib().icaf_set_seed_offset(self.seed_ctr.data_ptr()), "icaf_set_seed_offset")
         self.max_targets = max_targets
         warmup = (11 if ts.world_size > 1 else 3) if warmup is None else warmup
+        # the warm-up iterations are real steps on an all-zero batch: snapshot everything they touch and put it back afterwards
+        saved = {k: v.detach().clone() for k, v in ts.raw_model.state_dict().items()}
+        saved_scaler = ts.scaler.state_dict()
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(cur)
@@ -138,6 +142,15 @@ class GraphedTrainStep:
                 ts(self.rgb, self.ir, self.tg)
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for k, v in ts.raw_model.state_dict().items():
+                v.copy_(saved[k])                        # in place: the graph will be captured on these very tensors
+            for st in ts.optimizer.state.values():
+                if st.get("momentum_buffer") is not None:
+                    st["momentum_buffer"].zero_()        # == the state before the first step (SGD seeds the buffer with the gradient)
+        if saved_scaler:
+            ts.scaler.load_state_dict(saved_scaler)
+        self.seed_ctr.zero_()
         ts.optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

@@ -183,3 +183,42 @@ def test_c3_sppf_fusion_block_nodes(cuda_device):
     mod.crosstransformer[0].loops = 2
     _module_case(cuda_device, mod, "b", lambda sd, a, b: O.dmff_block(a, b, sd, "b", 16, 16, 2, training=True, bn_eps=1e-5),
                  lambda m, a, b: A.fusion_block(m, a, b), [rgb, ir], 6e-3)
+
+
+def test_graphed_train_step_equals_eager(cuda_device):
+    """GraphedTrainStep (forward + loss + backward replayed from a CUDA graph) takes the same optimiser steps as the eager
+    TrainStep: same losses and the same parameters / BatchNorm buffers after three steps on changing batches (dropout off:
+    its masks are keyed by a step counter that the two modes advance differently)."""
+    from icafusion_b200 import Model
+    from icafusion_b200.trainer import GraphedTrainStep, TrainStep, dead_parameters
+    m, d = load_golden("train_yolov5s_320")
+    B, H, W = 2, 320, 320
+    batches = []
+    for s in range(3):
+        rgb, ir = synth.synth_images(B, H, W, 100 + s)
+        t = torch.from_numpy(synth_targets(8 + s, B, 100 + s))
+        batches.append(((rgb * 255).to(torch.uint8).to(cuda_device), (ir * 255).to(torch.uint8).to(cuda_device), t.to(cuda_device)))
+    runs = []
+    for graphed in (False, True):
+        model = Model("yolov5s_Transfusion_kaist")
+        load_synth(model, m["seed"])
+        model = model.to(cuda_device).train()
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        ts = TrainStep(model, None, total_batch_size=B, imgsz=320)
+        assert sorted(ts.dead) == sorted(m["dead_params"]) == sorted(dead_parameters(model))
+        step = GraphedTrainStep(ts, B, H, W, 16, cuda_device) if graphed else ts
+        losses = [float(step(*b)[0]) for b in batches]
+        if graphed:
+            step.close()
+        torch.cuda.synchronize()
+        runs.append((losses, {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}, float(ts.scaler.get_scale())))
+    (l0, s0, sc0), (l1, s1, sc1) = runs
+    print(f"\n[graphed step] losses eager {l0}  graphed {l1}  scale {sc0} / {sc1}")
+    assert sc0 == sc1
+    assert np.allclose(l0, l1, rtol=1e-4)
+    worst = max(float((s1[k] - s0[k]).abs().max() / max(float(s0[k].abs().max()), 1e-6)) for k in s0 if s0[k].is_floating_point())
+    print(f"[graphed step] worst relative parameter / buffer difference after 3 steps: {worst:.2e}")
+    assert worst < 1e-3
+    assert all(torch.equal(s0[k], s1[k]) for k in s0 if not s0[k].is_floating_point())      # num_batches_tracked
