@@ -457,6 +457,12 @@ def _measure_train(args, wl, K, Wm, dev, world, rank, local):
     e2e_ms = timed(e2e, K)
     if gts is not None:
         gts.close()
+    in_sync = None
+    if world > 1:      # every rank must hold the same parameters after the synchronised steps (the all-reduce really ran, also inside the graph)
+        chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        in_sync = bool(all(float(c) == float(allc[0]) for c in allc))
     nosync_ms = 0.0
     if world > 1:                                                 # last: ranks drift apart without the all-reduce
         def local_only():
@@ -506,6 +512,7 @@ def _measure_train(args, wl, K, Wm, dev, world, rank, local):
     if graph_note:
         out["note"] = graph_note
     if world > 1:
+        out["parameters_identical_across_ranks"] = in_sync
         out["allreduce"] = {"eager_ms_per_step_with": round(eager_ms / K, 3), "eager_ms_per_step_without": round(nosync_ms / K, 3),
                             "exposed_share_of_eager_step": round(max(0.0, 1.0 - nosync_ms / eager_ms), 4),
                             "note": "eager step under DDP.no_sync() (no gradient all-reduce) vs the synchronised eager step; DDP overlaps its 25 MB "

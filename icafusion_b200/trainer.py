@@ -87,10 +87,11 @@ class TrainStep:
         self.world_size = world_size
         if world_size > 1:
             from torch.nn.parallel import DistributedDataParallel as DDP
-            model = DDP(model, device_ids=[local_rank], output_device=local_rank, find_unused_parameters=False,       # train.py:233
+            model = DDP(model, device_ids=None if local_rank is None else [local_rank], output_device=local_rank,   # train.py:233
+                        find_unused_parameters=False,
                         gradient_as_bucket_view=True)              # .grad aliases the all-reduce buckets: no copy in / out
         self.model = model
-        self.scaler = torch.amp.GradScaler("cuda", enabled=amp_scale)                 # train.py:282
+        self.scaler = torch.amp.GradScaler("cuda", enabled=amp_scale and torch.cuda.is_available())    # train.py:282
         self.compute_loss = ComputeLoss(self.raw_model)                               # train.py:284
         self.hyp = hyp
 
@@ -104,8 +105,13 @@ class TrainStep:
         self.scaler.scale(loss).backward()                                            # train.py:344
         self.scaler.step(self.optimizer)                                              # train.py:348-350
         self.scaler.update()
-        self.optimizer.zero_grad(set_to_none=True)
+        self.zero_grad()
         return loss.detach(), items
+
+    def zero_grad(self) -> None:
+        """optimizer.zero_grad() of train.py:350, extended to the 18 trainable parameters no optimiser group holds (pos_emb_*,
+        LearnableWeights.w1/w2): the reference never clears their .grad, which then grows by one gradient per step."""
+        self.raw_model.zero_grad(set_to_none=True)
 
 
 class GraphedTrainStep:
@@ -151,7 +157,7 @@ class GraphedTrainStep:
         if saved_scaler:
             ts.scaler.load_state_dict(saved_scaler)
         self.seed_ctr.zero_()
-        ts.optimizer.zero_grad(set_to_none=True)
+        ts.zero_grad()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.seed_ctr += 1
