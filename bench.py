@@ -433,6 +433,17 @@ def _measure_train(args, wl, K, Wm, dev, world, rank, local):
     n0 = ops.launch_count()
     eager_ms = timed(resident, K)
     launches = ops.launch_count() - n0
+    # per-kernel split of one step (event pass on one stream)
+    summ = {}
+    if rank == 0:
+        torch.cuda.synchronize()
+    with ops.profile() as prof:
+        torch.cuda._sleep(int(4e8))       # ~0.2 s spin: the step's launches queue up behind it and then run back to back
+        prof.mark()
+        ts(rgb_d, ir_d, tg_d)
+        torch.cuda.synchronize()
+    for name, v in prof.summary().items():
+        summ[name] = {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / max(v["ms"], 1e-6) / 1e9, 1)}
     # the same step with forward + loss + backward (+ DDP all-reduce) replayed from one CUDA graph
     gts, graph_note = None, None
     if os.environ.get("ICAF_TRAIN_GRAPH", "1") != "0":
@@ -470,21 +481,6 @@ def _measure_train(args, wl, K, Wm, dev, world, rank, local):
                 return ts(rgb_d, ir_d, tg_d)
         local_only()
         nosync_ms = timed(local_only, K)
-    # per-kernel split of one step (event pass on one stream)
-    summ = {}
-    if rank == 0:
-        torch.cuda.synchronize()
-    with ops.profile() as prof:
-        torch.cuda._sleep(int(4e8))       # ~0.2 s spin: the step's launches queue up behind it and then run back to back
-        prof.mark()
-        if world > 1:
-            with ts.model.no_sync():
-                ts(rgb_d, ir_d, tg_d)
-        else:
-            ts(rgb_d, ir_d, tg_d)
-        torch.cuda.synchronize()
-    for name, v in prof.summary().items():
-        summ[name] = {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / max(v["ms"], 1e-6) / 1e9, 1)}
     t = torch.tensor([res_ms, e2e_ms, nosync_ms, eager_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

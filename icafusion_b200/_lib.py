@@ -87,6 +87,7 @@ SIGNATURES = {
     "icaf_dmff_pool_tokens_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp],
     "icaf_dmff_upsample_cat_bwd": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "icaf_pack_weight": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "icaf_pack_weight_pair": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp],
     "icaf_set_seed_offset": [_vp],
     "icaf_cross_attention_train": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, C.c_uint32, _vp],
     "icaf_cross_attention_bwd_workspace_bytes": [_i, _i, _i],

@@ -48,8 +48,11 @@ class ConvBnActFn(Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, bn: nn.BatchNorm2d, stride: int, pad: int, act: int, stem: bool):
         w = _f32(weight)
+        ctx.pk_dgrad = None
         if stem:      # 6x6/s2/p2 over the image == 3x3/s1/p1 over its space-to-depth form (ops.pack_stem_weight)
             pk = ops.pack_stem_weight(w, None, ACT_NONE)
+        elif ctx.needs_input_grad[0]:
+            pk, ctx.pk_dgrad = ops.pack_weight_pair(w, stride, pad)      # the backward's flipped filter comes out of the same launch
         else:
             pk = ops.pack_weight(w, stride, pad)
         z = ops.conv2d([x], [pk])[0]
@@ -77,7 +80,7 @@ class ConvBnActFn(Function):
             dx = None
         else:
             dw = ops.conv2d_wgrad(x, dz, kh, kw, stride, pad)
-            dx = ops.conv2d_dgrad(dz, _f32(weight), stride, pad, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[0] else None
+            dx = ops.conv2d_dgrad(dz, _f32(weight), stride, pad, (x.shape[1], x.shape[2]), ctx.pk_dgrad) if ctx.needs_input_grad[0] else None
         return dx, dw.to(weight.dtype), dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, None, None, None, None
 
 
@@ -111,7 +114,7 @@ class HeadConvFn(Function):
         ld = ops.round_up(cout, 8)
         buf = torch.zeros(B, H, W, ld, dtype=torch.float16, device=x.device) if ld > cout else \
             torch.empty(B, H, W, ld, dtype=torch.float16, device=x.device)
-        pk = ops.pack_weight(_f32(weight), 1, 0, ACT_NONE, _f32(bias))
+        pk, ctx.pk_dgrad = ops.pack_weight_pair(_f32(weight), 1, 0, ACT_NONE, _f32(bias))
         ops.conv2d([x], [pk], [buf[..., :cout]])
         ctx.save_for_backward(x, weight)
         ctx.cfg = (na, no, ld)
@@ -134,8 +137,7 @@ class HeadConvFn(Function):
         db = ops.colsum(dbuf.view(B * H * W, ld))[:cout]
         dx = None
         if ctx.needs_input_grad[0]:
-            pk = ops.pack_weight(_f32(weight), 1, 0, dgrad=True)
-            dx = ops.conv2d([dbuf], [pk])[0]
+            dx = ops.conv2d([dbuf], [ctx.pk_dgrad])[0]
         return dx, dw.to(weight.dtype).contiguous(), db.contiguous(), None, None
 
 
@@ -144,7 +146,7 @@ class HeadConvFn(Function):
 class LinearFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
-        pk = ops.pack_weight(_f32(weight)[:, :, None, None], 1, 0, ACT_NONE, None if bias is None else _f32(bias))
+        pk, ctx.pk_dgrad = ops.pack_weight_pair(_f32(weight)[:, :, None, None], 1, 0, ACT_NONE, None if bias is None else _f32(bias))
         y = ops.linear([x], [pk])[0]
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
@@ -158,8 +160,7 @@ class LinearFn(Function):
         db = ops.colsum(dy) if ctx.has_bias else None
         dx = None
         if ctx.needs_input_grad[0]:
-            pk = ops.pack_weight(_f32(weight)[:, :, None, None], 1, 0, dgrad=True)
-            dx = ops.linear([dy], [pk])[0]
+            dx = ops.linear([dy], [ctx.pk_dgrad])[0]
         return dx, dw.to(weight.dtype), db
 
 

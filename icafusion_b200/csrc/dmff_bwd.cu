@@ -164,6 +164,31 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
   out[i] = __float2half(v);
 }
 
+// both banks of one filter in one launch (the training step packs every filter once per step, forward and data-gradient form)
+__global__ void __launch_bounds__(256) pack_weight_pair_kernel(const float* __restrict__ w, __half* __restrict__ out_f, __half* __restrict__ out_d, int Cout, int Cin,
+                                                               int kh, int kw, int rows_f, int kpad_f, int chan_d, int rows_d, int kpad_d) {
+  pdl_launch_dependents();
+  pdl_wait();
+  long long i = blockIdx.x * 256ll + threadIdx.x;
+  const long long nf = (long long)rows_f * kpad_f, nd = (long long)rows_d * kpad_d;
+  if (i >= nf + nd) return;
+  const bool dg = i >= nf;
+  if (dg) i -= nf;
+  const int k_pad = dg ? kpad_d : kpad_f, chan_p = dg ? chan_d : Cin;
+  const int r = int(i / k_pad), k = int(i - (long long)r * k_pad);
+  const int tap = k / chan_p, ch = k - tap * chan_p;
+  float v = 0.f;
+  if (tap < kh * kw) {
+    const int ky = tap / kw, kx = tap - ky * kw;
+    if (!dg) {
+      if (r < Cout && ch < Cin) v = w[(((long long)r * Cin + ch) * kh + ky) * kw + kx];
+    } else {
+      if (r < Cin && ch < Cout) v = w[(((long long)ch * Cin + r) * kh + (kh - 1 - ky)) * kw + (kw - 1 - kx)];
+    }
+  }
+  (dg ? out_d : out_f)[i] = __float2half(v);
+}
+
 }  // namespace icaf
 
 using namespace icaf;
@@ -216,4 +241,15 @@ extern "C" int icaf_pack_weight(const float* w, int Cout, int Cin, int kh, int k
   launch_k(pack_weight_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, w, (__half*)out, Cout, Cin, kh, kw, chan_pad,
            rows, k_pad, transpose_flip ? 1 : 0);
   return check_launch("pack_weight");
+}
+
+extern "C" int icaf_pack_weight_pair(const float* w, int Cout, int Cin, int kh, int kw, int rows_f, int kpad_f, void* out_fwd, int chan_pad_d, int rows_d,
+                                     int kpad_d, void* out_dgrad, void* stream) {
+  if (!w || !out_fwd || !out_dgrad || Cout < 1 || Cin < 1 || kh < 1 || kw < 1) return set_error(ICAF_ERR_BAD_ARG, "pack_weight_pair: bad argument");
+  if (rows_f < Cout || kpad_f < kh * kw * Cin || chan_pad_d < Cout || rows_d < Cin || kpad_d < kh * kw * chan_pad_d)
+    return set_error(ICAF_ERR_BAD_ARG, "pack_weight_pair: padded sizes smaller than the filter");
+  const long long total = (long long)rows_f * kpad_f + (long long)rows_d * kpad_d;
+  launch_k(pack_weight_pair_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, w, (__half*)out_fwd, (__half*)out_dgrad, Cout, Cin,
+           kh, kw, rows_f, kpad_f, chan_pad_d, rows_d, kpad_d);
+  return check_launch("pack_weight_pair");
 }

@@ -19,7 +19,11 @@ __device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
   v.x = pack_half2(f[0], f[1]); v.y = pack_half2(f[2], f[3]); v.z = pack_half2(f[4], f[5]); v.w = pack_half2(f[6], f[7]);
   return v;
 }
-__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
+__device__ __forceinline__ float sigmoidf_(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ void ld8f(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // per-channel partial sums over row chunks: out[chunk][which][c], which = 0 / 1.
@@ -104,7 +108,8 @@ __device__ __forceinline__ void chunk_sums(const float* __restrict__ part, int C
 
 // BatchNorm statistics, second stage: mean, invstd, and the running statistics update (momentum, unbiased variance)
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ invstd, float* run_mean,
-                                                          float* run_var, int C, long long rows, float eps, float momentum, int chunks) {
+                                                          float* run_var, int C, long long rows, float eps, float momentum, int chunks,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ab) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sm[2][kFinLanes][33];
@@ -115,7 +120,10 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   const float m = s / float(rows);
   const float var = fmaxf(q / float(rows) - m * m, 0.f);
   mean[c] = m;
-  invstd[c] = rsqrtf(var + eps);
+  const float is = rsqrtf(var + eps);
+  invstd[c] = is;
+  const float a = gamma[c] * is;
+  ab[c] = a; ab[C + c] = beta[c] - m * a;                   // the apply pass: y = act(x * a + b)
   if (run_mean) {
     run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
     run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (rows > 1 ? float(rows) / float(rows - 1) : 1.f);
@@ -124,7 +132,9 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 // generic second stage: out[which][c] = (accumulate ? out : 0) + scale * sum_chunks part
 // out0/out1: sums (scale, accumulate); raw0/raw1 (optional): the unscaled sums as well (BatchNorm backward needs both in one pass)
 __global__ void __launch_bounds__(1024) chan_final_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1, int C, float scale,
-                                                          int accumulate, int chunks, float* __restrict__ raw0, float* __restrict__ raw1) {
+                                                          int accumulate, int chunks, float* __restrict__ raw0, float* __restrict__ raw1,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd, float inv_m, float* __restrict__ coef) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sm[2][kFinLanes][33];
@@ -134,6 +144,10 @@ __global__ void __launch_bounds__(1024) chan_final_kernel(const float* __restric
   if (c >= C || threadIdx.y) return;
   if (raw0) raw0[c] = s;
   if (raw1) raw1[c] = q;
+  if (coef) {      // BatchNorm backward apply pass: dx = a * (dz - k1 - (x - mean) * k2), z = x * a + b
+    const float is = invstd[c], a = gamma[c] * is, m = mean[c];
+    coef[c] = a; coef[C + c] = beta[c] - m * a; coef[2 * C + c] = m; coef[3 * C + c] = s * inv_m; coef[4 * C + c] = q * inv_m * is;
+  }
   if (out0) out0[c] = (accumulate ? out0[c] : 0.f) + scale * s;
   if (out1) out1[c] = (accumulate ? out1[c] : 0.f) + scale * q;
 }
@@ -143,8 +157,9 @@ __global__ void scalar_final_kernel(const float* __restrict__ part, float* __res
   pdl_wait();
   __shared__ float red[1024];
   float s = 0.f;
-  for (int k = 0; k < chunks; ++k)
-    for (int c = threadIdx.x; c < C; c += 1024) s += __ldg(part + (size_t(k) * 2) * C + c);
+  const int total = chunks * C;                            // fixed thread -> element map: deterministic
+#pragma unroll 4
+  for (int i = threadIdx.x; i < total; i += 1024) s += __ldg(part + size_t(i / C) * 2 * C + (i % C));
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
@@ -154,46 +169,42 @@ __global__ void scalar_final_kernel(const float* __restrict__ part, float* __res
   if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + scale * red[0];
 }
 
-// y = act(x * a[c] + b[c])   (BatchNorm apply + SiLU; a = gamma * invstd, b = beta - mean * a)
-__global__ void affine_act_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  const float* __restrict__ mean, const float* __restrict__ invstd, __half* __restrict__ y, long long n8, int C8, int act) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  const int cg = int(i % C8);
-  float v[8];
-  unpack8h(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = cg * 8 + e;
-    const float a = gamma[c] * invstd[c];
-    const float z = v[e] * a + (beta[c] - mean[c] * a);
-    v[e] = act ? z * sigmoidf_(z) : z;
-  }
-  reinterpret_cast<uint4*>(y)[i] = pack8h(v);
-}
-// dx = gamma * invstd * (dz - S1 / M - xhat * S2 / M),  dz = dy * act'(z)   (S1 = sum dz, S2 = sum dz xhat: `sums` = [2][C])
-__global__ void bn_bwd_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ sums, __half* __restrict__ dx, long long n8, int C8, float inv_m, int act) {
+// y = act(x * a[c] + b[c])   (BatchNorm apply + SiLU; a = gamma * invstd, b = beta - mean * a: `ab` = [2][C] from the finalize pass)
+__global__ void __launch_bounds__(256) affine_act_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y, long long n8, int C8,
+                                                         int act) {
   pdl_launch_dependents();
   pdl_wait();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const int cg = int(i % C8), C = C8 * 8;
-  float xv[8], dv[8];
-  unpack8h(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
-  unpack8h(__ldg(reinterpret_cast<const uint4*>(dy) + i), dv);
+  float v[8], a[8], b[8];
+  unpack8h(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
+  ld8f(ab + cg * 8, a);
+  ld8f(ab + C + cg * 8, b);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int c = cg * 8 + e;
-    const float a = gamma[c] * invstd[c];
-    const float xh = (xv[e] - mean[c]) * invstd[c];
-    const float z = xv[e] * a + (beta[c] - mean[c] * a);
+    const float z = fmaf(v[e], a[e], b[e]);
+    v[e] = act ? z * sigmoidf_(z) : z;
+  }
+  reinterpret_cast<uint4*>(y)[i] = pack8h(v);
+}
+// dx = a * (dz - k1 - (x - mean) * k2),  dz = dy * act'(z), z = x * a + b   (`coef` = [5][C]: a, b, mean, k1 = S1 / M, k2 = invstd * S2 / M)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const float* __restrict__ coef,
+                                                           __half* __restrict__ dx, long long n8, int C8, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int cg = int(i % C8), C = C8 * 8;
+  float xv[8], dv[8], a[8], b[8], m[8], k1[8], k2[8];
+  unpack8h(__ldg(reinterpret_cast<const uint4*>(x) + i), xv);
+  unpack8h(__ldg(reinterpret_cast<const uint4*>(dy) + i), dv);
+  ld8f(coef + cg * 8, a); ld8f(coef + C + cg * 8, b); ld8f(coef + 2 * C + cg * 8, m); ld8f(coef + 3 * C + cg * 8, k1); ld8f(coef + 4 * C + cg * 8, k2);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
     float dz = dv[e];
-    if (act) { const float sg = sigmoidf_(z); dz *= sg * (1.f + z * (1.f - sg)); }
-    xv[e] = a * (dz - sums[c] * inv_m - xh * sums[C + c] * inv_m);
+    if (act) { const float z = fmaf(xv[e], a[e], b[e]); const float sg = sigmoidf_(z); dz *= sg * fmaf(z, 1.f - sg, 1.f); }
+    xv[e] = a[e] * (dz - k1[e] - (xv[e] - m[e]) * k2[e]);
   }
   reinterpret_cast<uint4*>(dx)[i] = pack8h(xv);
 }
@@ -396,7 +407,9 @@ static inline int pick_chunks(long long rows, int C, int cap_chunks = kRedChunks
 
 using namespace icaf;
 
-extern "C" size_t icaf_train_workspace_bytes(int C) { return size_t(kRedChunks) * 2 * (C > 0 ? C : 1) * sizeof(float); }
+// [kRedChunks][2][C] partial sums, then 8 C floats of per-channel coefficients for the apply passes
+static inline size_t ws_floats(int C) { return size_t(kRedChunks) * 2 * (C > 0 ? C : 1) + 8 * size_t(C > 0 ? C : 1); }
+extern "C" size_t icaf_train_workspace_bytes(int C) { return ws_floats(C) * sizeof(float); }
 
 extern "C" int icaf_bn_act_fwd(const void* x, const float* gamma, const float* beta, float* run_mean, float* run_var, void* y, float* save_mean,
                                float* save_invstd, int64_t rows, int C, float eps, float momentum, int act, float* workspace, size_t workspace_bytes,
@@ -408,10 +421,11 @@ extern "C" int icaf_bn_act_fwd(const void* x, const float* gamma, const float* b
   launch_k(chan_partial_kernel<0>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)nullptr, (const float*)nullptr,
            (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, workspace, (long long)rows, C, 0, chunks);
   if (int rc = check_launch("bn_act_fwd(stats)")) return rc;
-  launch_k(bn_finalize_kernel, dim3(nblk(C, 32)), dim3(32, kFinLanes), 0, st, (const float*)workspace, save_mean, save_invstd, run_mean, run_var, C, (long long)rows, eps, momentum, chunks);
+  launch_k(bn_finalize_kernel, dim3(nblk(C, 32)), dim3(32, kFinLanes), 0, st, (const float*)workspace, save_mean, save_invstd, run_mean, run_var, C, (long long)rows, eps, momentum, chunks,
+           gamma, beta, workspace + size_t(kRedChunks) * 2 * C);
   if (int rc = check_launch("bn_act_fwd(finalize)")) return rc;
   const long long n8 = rows * (C / 8);
-  launch_k(affine_act_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, gamma, beta, (const float*)save_mean, (const float*)save_invstd, (__half*)y, n8, C / 8, act);
+  launch_k(affine_act_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const float*)(workspace + size_t(kRedChunks) * 2 * C), (__half*)y, n8, C / 8, act);
   return check_launch("bn_act_fwd");
 }
 
@@ -419,20 +433,19 @@ extern "C" int icaf_bn_act_bwd(const void* x, const void* dy, const float* gamma
                                void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int act, float grad_scale, int accumulate, float* workspace,
                                size_t workspace_bytes, void* stream) {
   if (!x || !dy || !gamma || !beta || !save_mean || !save_invstd || !dx || !workspace || rows < 1 || C < 8 || C % 8) return set_error(ICAF_ERR_BAD_ARG, "bn_act_bwd: bad argument");
-  if (workspace_bytes < icaf_train_workspace_bytes(C) + 2 * size_t(C) * sizeof(float)) return set_error(ICAF_ERR_BAD_ARG, "bn_act_bwd: workspace too small (icaf_train_workspace_bytes + 2 C floats)");
+  if (workspace_bytes < icaf_train_workspace_bytes(C)) return set_error(ICAF_ERR_BAD_ARG, "bn_act_bwd: workspace too small (icaf_train_workspace_bytes)");
   cudaStream_t st = (cudaStream_t)stream;
-  float* sums = workspace + size_t(kRedChunks) * 2 * C;     // [2][C]: S1 = sum dz, S2 = sum dz xhat
+  float* coef = workspace + size_t(kRedChunks) * 2 * C;     // [5][C] coefficients of the apply pass
   const int chunks = pick_chunks(rows, C);
   launch_k(chan_partial_kernel<1>, dim3(nblk(C / 8, 32), chunks), dim3(256), 0, st, (const __half*)x, (const __half*)dy, gamma, beta, save_mean, save_invstd,
            workspace, (long long)rows, C, act, chunks);
   if (int rc = check_launch("bn_act_bwd(partial)")) return rc;
-  // one second stage: the raw sums for the apply pass and the parameter gradients dbeta = S1, dgamma = S2 (scaled by grad_scale)
-  launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, kFinLanes), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks, sums,
-           sums + C);
+  // one second stage: the apply pass's coefficients and the parameter gradients dbeta = S1, dgamma = S2 (scaled by grad_scale)
+  launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, kFinLanes), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks,
+           (float*)nullptr, (float*)nullptr, gamma, beta, save_mean, save_invstd, 1.0f / float(rows), coef);
   if (int rc = check_launch("bn_act_bwd(sums)")) return rc;
   const long long n8 = rows * (C / 8);
-  launch_k(bn_bwd_apply_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, gamma, beta, save_mean, save_invstd, (const float*)sums,
-           (__half*)dx, n8, C / 8, 1.0f / float(rows), act);
+  launch_k(bn_bwd_apply_kernel, dim3(nblk(n8, 256)), dim3(256), 0, st, (const __half*)x, (const __half*)dy, (const float*)coef, (__half*)dx, n8, C / 8, act);
   return check_launch("bn_act_bwd");
 }
 
@@ -453,7 +466,7 @@ extern "C" int icaf_layernorm_bwd(const void* x, const void* dy, const float* ga
   if (!x || !dy || !gamma || !dx || !workspace || rows < 1 || C % 8 || C > 2048) return set_error(ICAF_ERR_BAD_ARG, "layernorm_bwd: bad argument (C % 8, C <= 2048)");
   if (workspace_bytes < icaf_train_workspace_bytes(C) + 2 * size_t(rows) * sizeof(float)) return set_error(ICAF_ERR_BAD_ARG, "layernorm_bwd: workspace too small (icaf_train_workspace_bytes + 2 rows floats)");
   cudaStream_t st = (cudaStream_t)stream;
-  float* rmean = workspace + size_t(kRedChunks) * 2 * C;
+  float* rmean = workspace + ws_floats(C);
   float* rrstd = rmean + rows;
   launch_k(ln_bwd_kernel, dim3(nblk(rows, 4)), dim3(128), 0, st, (const __half*)x, (const __half*)dy, gamma, (__half*)dx, rmean, rrstd, (long long)rows, C, eps);
   if (int rc = check_launch("layernorm_bwd(dx)")) return rc;
@@ -463,7 +476,7 @@ extern "C" int icaf_layernorm_bwd(const void* x, const void* dy, const float* ga
              (const float*)rmean, (const float*)rrstd, workspace, (long long)rows, C, 0, chunks);
     if (int rc = check_launch("layernorm_bwd(partial)")) return rc;
     launch_k(chan_final_kernel, dim3(nblk(C, 32)), dim3(32, kFinLanes), 0, st, (const float*)workspace, dbeta, dgamma, C, grad_scale, accumulate, chunks,
-             (float*)nullptr, (float*)nullptr);
+             (float*)nullptr, (float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, 0.f, (float*)nullptr);
     if (int rc = check_launch("layernorm_bwd(param grads)")) return rc;
   }
   return ICAF_OK;

@@ -147,20 +147,55 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const WgradParams P, cons
 }
 
 // dW[n][c][ky][kx] (PyTorch layout, fp32) = (accumulate ? dW : 0) + scale * sum_split partial[split][n][tap][c]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int n_pad, int taps, int c_pad,
-                                    int Cout, int Cin, float scale, int accumulate) {
+// One block per (n, 128-channel tile): partials are read tap-major (coalesced over c), transposed through shared memory, and
+// written as the contiguous [c][tap] run of dW -- both sides of the layout change stay coalesced.
+constexpr int kRedC = 128;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int n_pad, int taps, int c_pad,
+                                                           int Cout, int Cin, float scale, int accumulate) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)Cout * taps * Cin;
-  if (i >= total) return;
-  const int c = int(i % Cin);
-  long long r = i / Cin;
-  const int tap = int(r % taps), n = int(r / taps);
-  float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += partial[((size_t(sp) * n_pad + n) * taps + tap) * c_pad + c];
-  float* d = dw + (size_t(n) * Cin + c) * taps + tap;
-  *d = (accumulate ? *d : 0.f) + scale * s;
+  extern __shared__ float tile[];                          // [taps][kRedC + 1]
+  const int c_tiles = (Cin + kRedC - 1) / kRedC;
+  const int n = blockIdx.x / c_tiles, c0 = (blockIdx.x % c_tiles) * kRedC;
+  const int cw = min(kRedC, Cin - c0);
+  for (int i = threadIdx.x; i < taps * cw; i += 256) {
+    const int tap = i / cw, c = i - tap * cw;
+    const float* src = partial + (size_t(n) * taps + tap) * c_pad + c0 + c;
+    const size_t step = size_t(n_pad) * taps * c_pad;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;            // four independent chains (loads in flight), combined in a fixed order
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {
+      s0 += __ldg(src + sp * step); s1 += __ldg(src + (sp + 1) * step); s2 += __ldg(src + (sp + 2) * step); s3 += __ldg(src + (sp + 3) * step);
+    }
+    for (; sp < splits; ++sp) s0 += __ldg(src + sp * step);
+    tile[tap * (kRedC + 1) + c] = (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+  float* d = dw + (size_t(n) * Cin + c0) * taps;
+  for (int o = threadIdx.x; o < taps * cw; o += 256) {
+    const int c = o / taps, tap = o - c * taps;
+    const float v = scale * tile[tap * (kRedC + 1) + c];
+    d[o] = accumulate ? d[o] + v : v;
+  }
+}
+
+// 1x1 filters: the two layouts coincide, one thread per element
+__global__ void __launch_bounds__(256) wgrad_reduce_flat_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int n_pad, int c_pad, int Cout,
+                                                                int Cin, float scale, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= (long long)Cout * Cin) return;
+  const int c = int(i % Cin), n = int(i / Cin);
+  const float* src = partial + size_t(n) * c_pad + c;
+  const size_t step = size_t(n_pad) * c_pad;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int sp = 0;
+  for (; sp + 4 <= splits; sp += 4) {
+    s0 += __ldg(src + sp * step); s1 += __ldg(src + (sp + 1) * step); s2 += __ldg(src + (sp + 2) * step); s3 += __ldg(src + (sp + 3) * step);
+  }
+  for (; sp < splits; ++sp) s0 += __ldg(src + sp * step);
+  dw[i] = (accumulate ? dw[i] : 0.f) + scale * ((s0 + s1) + (s2 + s3));
 }
 
 // zero-stuffed copy: y[b, 2*oy, 2*ox, :] = x[b, oy, ox, :], every other pixel 0 (dgrad of a stride-2 convolution = stride-1
@@ -274,9 +309,14 @@ extern "C" int icaf_conv2d_wgrad(const icaf_conv_geom* g, const void* x, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   launch_k(wgrad_kernel, dim3(pl.grid), dim3(192), (size_t)kWSmem, st, P, maps);
   if (int r3 = check_launch("conv2d_wgrad")) return r3;
-  const long long total = (long long)g->Cout * P.taps * g->Cin;
-  launch_k(wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)P.partial, dw, P.splits, P.n_pad, P.taps,
-           P.c_pad, g->Cout, g->Cin, scale, accumulate);
+  if (P.taps == 1) {
+    launch_k(wgrad_reduce_flat_kernel, dim3((unsigned)(((long long)g->Cout * g->Cin + 255) / 256)), dim3(256), 0, st, (const float*)P.partial, dw, P.splits, P.n_pad,
+             P.c_pad, g->Cout, g->Cin, scale, accumulate);
+    return check_launch("conv2d_wgrad(reduce)");
+  }
+  const unsigned red_blocks = (unsigned)g->Cout * (unsigned)((g->Cin + kRedC - 1) / kRedC);
+  launch_k(wgrad_reduce_kernel, dim3(red_blocks), dim3(256), size_t(P.taps) * (kRedC + 1) * sizeof(float), st, (const float*)P.partial, dw, P.splits, P.n_pad,
+           P.taps, P.c_pad, g->Cout, g->Cin, scale, accumulate);
   return check_launch("conv2d_wgrad(reduce)");
 }
 

@@ -650,6 +650,23 @@ def pack_weight(weight: torch.Tensor, stride: int, pad: int, act: int = ACT_NONE
     return PackedConv(out, b, pcin, pcout, kh, kw, stride, pad, act)
 
 
+def pack_weight_pair(weight: torch.Tensor, stride: int, pad: int, act: int = ACT_NONE, bias: Optional[torch.Tensor] = None):
+    """-> (forward PackedConv, data-gradient PackedConv) of one fp32 master filter in ONE launch (see pack_weight)."""
+    cout, cin, kh, kw = weight.shape
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous() or not on_device(w) or cin % 8:
+        raise ValueError("pack_weight_pair: contiguous fp32 CUDA filter with input channels % 8 == 0 expected")
+    rows_f, kpad_f = round_up(cout, 32), round_up(kh * kw * cin, 64)
+    chan_d = round_up(cout, 8)
+    rows_d, kpad_d = round_up(cin, 32), round_up(kh * kw * chan_d, 64)
+    buf = torch.empty(rows_f * kpad_f + rows_d * kpad_d, dtype=torch.float16, device=w.device)
+    of, od = buf[:rows_f * kpad_f].view(rows_f, kpad_f), buf[rows_f * kpad_f:].view(rows_d, kpad_d)
+    _call("icaf_pack_weight_pair", _lib.lib().icaf_pack_weight_pair,
+          (_ptr(w), cout, cin, kh, kw, rows_f, kpad_f, _ptr(of), chan_d, rows_d, kpad_d, _ptr(od)), {"bytes": 4.0 * w.numel() + 2.0 * buf.numel()})
+    b = None if bias is None else bias.detach().float().contiguous()
+    return PackedConv(of, b, cin, cout, kh, kw, stride, pad, act), PackedConv(od, None, chan_d, cin, kh, kw, 1, 0, ACT_NONE)
+
+
 def pack_dgrad_weight(weight: torch.Tensor, device=None) -> PackedConv:
     """Filter of the data-gradient convolution (stride 1; pad k-1-p is set by conv2d_dgrad; no bias, no activation)."""
     w = weight.detach().float().contiguous()
@@ -665,12 +682,13 @@ def zero_stuff2(dy: torch.Tensor, H2: int, W2: int) -> torch.Tensor:
     return out
 
 
-def conv2d_dgrad(dy: torch.Tensor, weight: torch.Tensor, stride: int, pad: int, in_hw) -> torch.Tensor:
+def conv2d_dgrad(dy: torch.Tensor, weight: torch.Tensor, stride: int, pad: int, in_hw, packed: Optional[PackedConv] = None) -> torch.Tensor:
     """dx (B,Hi,Wi,Cin) fp16 of y = conv2d(x, weight, stride, pad): the forward tensor-core kernel on the flipped / transposed
-    filter; a stride-2 layer first spreads dy over the input grid (icaf_zero_stuff2)."""
+    filter (`packed`: that filter if the caller packed it already); a stride-2 layer first spreads dy over the input grid
+    (icaf_zero_stuff2)."""
     k = weight.shape[2]
     Hi, Wi = in_hw
-    pk = pack_dgrad_weight(weight, dy.device)
+    pk = packed if packed is not None else pack_dgrad_weight(weight, dy.device)
     if stride == 2:
         dy = zero_stuff2(dy, Hi + 2 * pad - k + 1, Wi + 2 * pad - k + 1)
     elif stride != 1:

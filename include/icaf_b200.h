@@ -320,6 +320,10 @@ int icaf_dmff_upsample_cat_bwd(const void* dcat, int64_t d_ld, void* dtok_vis, v
  * 1: the data-gradient filter W'[c][n][ky][kx] = W[n][c][kh-1-ky][kw-1-kx] (rows >= Cin, channels = Cout). */
 int icaf_pack_weight(const float* w, int Cout, int Cin, int kh, int kw, int chan_pad, int rows, int k_pad, int transpose_flip, void* out,
                      void* stream);
+/* Both banks of one filter in one launch: out_fwd [rows_f][kpad_f] (channels = Cin) and out_dgrad [rows_d][kpad_d] (channels = Cout
+ * padded to chan_pad_d). */
+int icaf_pack_weight_pair(const float* w, int Cout, int Cin, int kh, int kw, int rows_f, int kpad_f, void* out_fwd, int chan_pad_d, int rows_d,
+                          int kpad_d, void* out_dgrad, void* stream);
 
 /* Optional device-side counter (one uint32) added to every dropout seed by the kernels at run time (NULL switches it off).  A
  * captured CUDA graph of the training step keeps its host-side seeds; bumping this counter on the device between replays gives
