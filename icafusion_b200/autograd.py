@@ -455,11 +455,42 @@ def model_forward(model, rgb_img: torch.Tensor, ir_img: torch.Tensor, taps: list
 
 
 def _walk(model, rgb_img, ir_img, taps):
+    """The IR backbone (layers s .. 2s-1, fed by `f == -4`) is independent of the RGB one until the first DMFF block: it is
+    issued on a side stream, so the two streams' kernels overlap -- and so do their backward nodes, which autograd runs on the
+    stream each forward ran on.  Inside a CUDA-graph capture the fork / join become parallel branches of the graph."""
+    import contextlib
+    import os
     from .common import C3, SPPF, Concat, Conv, TransformerFusionBlock
     from .yolo_test import Detect
     y: list = []
     x = None
+    if "_ir_start" not in model.__dict__:
+        model._plan_streams()
+    s_ir = model._ir_start if os.environ.get("ICAF_TRAIN_STREAMS", "1") != "0" else None
+    main = side = None
+    if s_ir is not None and rgb_img.is_cuda:
+        main = torch.cuda.current_stream(rgb_img.device)
+        side = model._side_streams(rgb_img.device, 1)[0]
+        side.wait_stream(main)                       # fork before any RGB work is queued: the IR branch only needs the input batch
+    joined = side is None
     for m in model.model:
+        on_side = side is not None and s_ir <= m.i < 2 * s_ir
+        if not joined and m.i >= 2 * s_ir:           # first consumer of both branches
+            main.wait_stream(side)
+            for t in y[s_ir:2 * s_ir]:
+                if t is not None:
+                    t.record_stream(main)            # produced in the side stream's pool, read (and saved for backward) on main
+            joined = True
+        with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
+            x = _layer(model, m, x, y, rgb_img, ir_img, Conv, C3, SPPF, Concat, TransformerFusionBlock, Detect)
+        y.append(x if m.i in model.save else None)
+        if taps is not None:
+            taps.append(x)
+    return x
+
+
+def _layer(model, m, x, y, rgb_img, ir_img, Conv, C3, SPPF, Concat, TransformerFusionBlock, Detect):
+    if True:
         stem = False
         if m.f == -4 or x is None:                                # image stems: RGB is the first layer, IR enters at f == -4
             img = ir_img if m.f == -4 else rgb_img
@@ -487,7 +518,4 @@ def _walk(model, rgb_img, ir_img, taps):
             x = detect(m, x)
         else:
             raise NotImplementedError(type(m).__name__)
-        y.append(x if m.i in model.save else None)
-        if taps is not None:
-            taps.append(x)
     return x

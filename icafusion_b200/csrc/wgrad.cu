@@ -262,7 +262,8 @@ static int plan_wgrad(const icaf_conv_geom* g, int sms, WgradPlan& pl) {
   P.n_tiles = (g->Cout + 127) / 128;
   P.n_pad = P.n_tiles * 128; P.c_pad = P.c_tiles * P.c_tile;
   const long long items = (long long)P.n_tiles * P.c_tiles * P.taps;
-  long long splits = (2LL * sms + items - 1) / items;
+  // one CTA per SM is resident (192 KB of staging): the grid must not spill a few CTAs into an extra wave -> floor, not ceil
+  long long splits = (2LL * sms) / items;
   if (splits > P.m_tiles) splits = P.m_tiles;
   if (splits < 1) splits = 1;
   if (splits > 64) splits = 64;
