@@ -473,6 +473,7 @@ def _walk(model, rgb_img, ir_img, taps):
         side = model._side_streams(rgb_img.device, 1)[0]
         side.wait_stream(main)                       # fork before any RGB work is queued: the IR branch only needs the input batch
     joined = side is None
+    forked = {}                                      # layer index -> side stream a DMFF block is running on
     for m in model.model:
         on_side = side is not None and s_ir <= m.i < 2 * s_ir
         if not joined and m.i >= 2 * s_ir:           # first consumer of both branches
@@ -481,7 +482,26 @@ def _walk(model, rgb_img, ir_img, taps):
                 if t is not None:
                     t.record_stream(main)            # produced in the side stream's pool, read (and saved for backward) on main
             joined = True
-        with (torch.cuda.stream(side) if on_side else contextlib.nullcontext()):
+        st = side if on_side else None
+        if side is not None and joined and isinstance(m, TransformerFusionBlock):
+            # the DMFF blocks only read backbone maps and are independent of each other: one side stream each (they are chains
+            # of small token-level kernels that leave most of the GPU idle when run one after the other)
+            st = model._side_streams(rgb_img.device, 2 + len(forked))[1 + len(forked)]
+            st.wait_stream(main)
+            srcs = m.f if isinstance(m.f, (list, tuple)) else [m.f]
+            for j in srcs:
+                if j != -1 and y[j] is not None:
+                    y[j].record_stream(st)
+            forked[m.i] = st
+        elif forked:                                 # any other layer: join the DMFF streams it may read from
+            for i, fs in forked.items():
+                main.wait_stream(fs)
+                if y[i] is not None:
+                    y[i].record_stream(main)
+            if torch.is_tensor(x):
+                x.record_stream(main)                # the previous layer's output arrives as `-1` even when it is not in `save`
+            forked = {}
+        with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
             x = _layer(model, m, x, y, rgb_img, ir_img, Conv, C3, SPPF, Concat, TransformerFusionBlock, Detect)
         y.append(x if m.i in model.save else None)
         if taps is not None:
