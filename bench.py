@@ -551,6 +551,22 @@ def run_ours(args, wl):
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     K, Wm = args.steps, max(3, args.warmup)
+    if args.mode == "train":
+        tr = _measure_train(args, wl, K, max(4, Wm // 2), dev, world, rank, local)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank != 0:
+            return
+        per = tr.pop("per_kernel_event_pass")
+        line = {"metric": "640x512 RGB+IR training pairs/sec (train.py step)", "value": tr["value"], "unit": "pairs/s", "n_gpus": world, "steps": tr["steps"],
+                "warmup": tr["warmup"], "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "data": "synthetic", "config": tr["config"], "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"],
+                **{k: v for k, v in tr.items() if k in ("execution", "eager_ms_per_step", "allreduce", "parameters_identical_across_ranks", "grad_scale_after",
+                                                        "peak_mem_gib", "note")},
+                "per_kernel_event_pass": per}
+        print(json.dumps(line))
+        return
     m = _measure(args, wl, K, Wm, dev, world, rank, local, primary=True)      # the same workload at every N
     tr, tr_err = None, None
     if args.train != "off":
@@ -618,6 +634,8 @@ def main():
     ap.add_argument("--train", default="on", choices=["on", "off"], help="also time the training step of the workload's model (reported "
                     "under 'train'; with N > 1 it runs under DDP and names the gradient all-reduce's share)")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: the JSON line's top-level metric is the training "
+                    "step (BASELINE configs[3]; under torchrun it is the DDP step with its gradient all-reduce) instead of inference")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
