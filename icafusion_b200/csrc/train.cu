@@ -58,23 +58,37 @@ __global__ void __launch_bounds__(256) chan_partial_kernel(const __half* __restr
         av[e] = a[cg * 8 + e] * iv[e]; bv[e] = b[cg * 8 + e] - mv[e] * av[e];
       }
     }
-    for (long long r = r0 + rl; r < r1; r += rpp) {
-      float xv[8], dv[8];
-      unpack8h(__ldg(reinterpret_cast<const uint4*>(x + r * C + cg * 8)), xv);
-      if (MODE != 0) unpack8h(__ldg(reinterpret_cast<const uint4*>(dy + r * C + cg * 8)), dv);
-      float rm = 0.f, ri = 0.f;
-      if (MODE == 2) { rm = mean[r]; ri = invstd[r]; }
+    // two rows per trip: both rows' loads are issued before either is consumed (twice the bytes in flight per thread)
+    for (long long r = r0 + rl; r < r1; r += 2 * rpp) {
+      const long long rb = r + rpp;
+      const bool two = rb < r1;
+      float xv[2][8], dv[2][8];
+      const uint4 xa = __ldg(reinterpret_cast<const uint4*>(x + r * C + cg * 8));
+      const uint4 xb = two ? __ldg(reinterpret_cast<const uint4*>(x + rb * C + cg * 8)) : make_uint4(0, 0, 0, 0);
+      uint4 da = make_uint4(0, 0, 0, 0), db = make_uint4(0, 0, 0, 0);
+      if (MODE != 0) {
+        da = __ldg(reinterpret_cast<const uint4*>(dy + r * C + cg * 8));
+        if (two) db = __ldg(reinterpret_cast<const uint4*>(dy + rb * C + cg * 8));
+      }
+      unpack8h(xa, xv[0]); unpack8h(xb, xv[1]); unpack8h(da, dv[0]); unpack8h(db, dv[1]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (MODE == 0) { s0[e] += xv[e]; s1[e] += xv[e] * xv[e]; }
-        if (MODE == 1) {
-          const float z = xv[e] * av[e] + bv[e];
-          float dz = dv[e];
-          if (act) { const float sg = sigmoidf_(z); dz *= sg * (1.f + z * (1.f - sg)); }
-          s0[e] += dz; s1[e] += dz * (xv[e] - mv[e]) * iv[e];
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        float rm = 0.f, ri = 0.f;
+        if (MODE == 2) { rm = mean[h ? rb : r]; ri = invstd[h ? rb : r]; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xe = xv[h][e], de = dv[h][e];
+          if (MODE == 0) { s0[e] += xe; s1[e] += xe * xe; }
+          if (MODE == 1) {
+            const float z = xe * av[e] + bv[e];
+            float dz = de;
+            if (act) { const float sg = sigmoidf_(z); dz *= sg * (1.f + z * (1.f - sg)); }
+            s0[e] += dz; s1[e] += dz * (xe - mv[e]) * iv[e];
+          }
+          if (MODE == 2) { s0[e] += de; s1[e] += de * (xe - rm) * ri; }
+          if (MODE == 3) { s0[e] += xe * de; }
         }
-        if (MODE == 2) { s0[e] += dv[e]; s1[e] += dv[e] * (xv[e] - rm) * ri; }
-        if (MODE == 3) { s0[e] += xv[e] * dv[e]; }
       }
     }
   }
