@@ -63,11 +63,45 @@ def param_groups(model: nn.Module):
     return pg0, pg1, pg2
 
 
+class ModelEMA:
+    """utils/torch_utils.py:278-330: exponential moving average of every floating state_dict entry, decay ramped by the update
+    count.  Same attributes (`ema`, `updates`, `decay`) and the same `update(model)`; the per-tensor Python loop of the
+    reference (two kernels per tensor, ~1 300 launches for yolov5l) is two multi-tensor launches here."""
+
+    def __init__(self, model: nn.Module, decay: float = 0.9999, updates: int = 0):
+        import math
+        from copy import deepcopy
+        src = model.module if hasattr(model, "module") else model
+        packs = {id(m): {k: m.__dict__.pop(k) for k in [k for k in m.__dict__ if k.startswith("_icaf_")]} for m in src.modules()}
+        try:
+            self.ema = deepcopy(src).eval()              # (packed-filter caches and stream pools are not part of the model)
+        finally:
+            for m in src.modules():
+                m.__dict__.update(packs[id(m)])
+        self.updates = updates
+        self.decay = lambda x: decay * (1 - math.exp(-x / 2000))
+        for p in self.ema.parameters():
+            p.requires_grad_(False)
+
+    def update(self, model: nn.Module) -> None:
+        with torch.no_grad():
+            self.updates += 1
+            d = self.decay(self.updates)
+            msd = (model.module if hasattr(model, "module") else model).state_dict()
+            dst, src = [], []
+            for k, v in self.ema.state_dict().items():
+                if v.dtype.is_floating_point:
+                    dst.append(v)
+                    src.append(msd[k].detach())
+            torch._foreach_mul_(dst, d)
+            torch._foreach_add_(dst, src, alpha=1.0 - d)
+
+
 class TrainStep:
     """model -> (optional DDP) -> loss -> scaled backward -> optimiser step, per call (train.py:334-349)."""
 
     def __init__(self, model: nn.Module, hyp: Optional[Dict[str, float]] = None, total_batch_size: int = 64, world_size: int = 1,
-                 local_rank: Optional[int] = None, imgsz: int = 640, amp_scale: bool = True):
+                 local_rank: Optional[int] = None, imgsz: int = 640, amp_scale: bool = True, ema: bool = False):
         hyp = dict(HYP_SCRATCH if hyp is None else hyp)
         det = model.model[-1]
         nl, nc = det.nl, det.nc
@@ -94,6 +128,7 @@ class TrainStep:
         self.scaler = torch.amp.GradScaler("cuda", enabled=amp_scale and torch.cuda.is_available())    # train.py:282
         self.compute_loss = ComputeLoss(self.raw_model)                               # train.py:284
         self.hyp = hyp
+        self.ema = ModelEMA(self.raw_model) if ema else None                          # train.py:154 (rank 0 / single GPU in the reference)
 
     def __call__(self, rgb: torch.Tensor, ir: torch.Tensor, targets: torch.Tensor):
         """rgb / ir: (B,3,H,W) uint8 (scaled by 1/255 inside the stem staging, train.py:297-298) or float images on the device;
@@ -106,6 +141,8 @@ class TrainStep:
         self.scaler.step(self.optimizer)                                              # train.py:348-350
         self.scaler.update()
         self.zero_grad()
+        if self.ema is not None:
+            self.ema.update(self.raw_model)                                           # train.py:351-352
         return loss.detach(), items
 
     def zero_grad(self) -> None:
@@ -180,6 +217,8 @@ class GraphedTrainStep:
         self.graph.replay()
         self.ts.scaler.step(self.ts.optimizer)            # gradients live in static buffers the next replay overwrites
         self.ts.scaler.update()
+        if self.ts.ema is not None:
+            self.ts.ema.update(self.ts.raw_model)
         return self.loss.detach(), self.items
 
     def close(self) -> None:

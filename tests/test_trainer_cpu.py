@@ -89,3 +89,32 @@ def test_ddp_world2_gradient_average_and_dead_parameter_repair(freeze):
         assert kind == "ok" and val[0] == 0 and val[1] == val[2], val
     else:       # without the repair DDP refuses the second iteration: parameters that never got a gradient
         assert kind == "error" and "Expected to have finished reduction" in val
+
+
+def test_model_ema_matches_the_reference_loop():
+    """ModelEMA.update == the reference's per-tensor loop (utils/torch_utils.py:305-315), on a small DMFF block."""
+    import math
+    from copy import deepcopy
+    from icafusion_b200.common import TransformerFusionBlock
+    from icafusion_b200.trainer import ModelEMA
+    torch.manual_seed(0)
+    m = TransformerFusionBlock(64, 4, 4)
+    ema = ModelEMA(m)
+    ref = {k: v.clone() for k, v in deepcopy(m).state_dict().items()}
+    for step in range(1, 4):
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(0.1 * torch.randn_like(p))
+            m.conv1x1_out.bn.running_mean.add_(0.05)
+            m.conv1x1_out.bn.num_batches_tracked += 1
+        ema.update(m)
+        d = 0.9999 * (1 - math.exp(-step / 2000))
+        for k, v in m.state_dict().items():
+            if v.dtype.is_floating_point:
+                ref[k] = ref[k] * d + (1.0 - d) * v
+    assert ema.updates == 3
+    for k, v in ema.ema.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert torch.allclose(v, ref[k], rtol=1e-6, atol=1e-7), k
+        else:
+            assert torch.equal(v, ref[k]), k              # integer buffers are left alone, like in the reference
