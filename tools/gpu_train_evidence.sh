@@ -3,4 +3,4 @@
 mkdir -p gpurun_out
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed
 timeout 900 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/train_step.csv python tools/train_one.py > gpurun_out/train_step.log 2>&1; tail -n 1 gpurun_out/train_step.log
-python tools/summarize_train_step.py r02 && head -n 30 profiles/r02_train_step_yolov5l_b16.md | cut -c1-200
+python tools/ncu_kernel_sum.py gpurun_out/train_step.csv 12
