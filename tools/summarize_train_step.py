@@ -42,6 +42,10 @@ out = [f"# Training step, yolov5l_Transfusion_kaist, 16 pairs of 640x512, one B2
        "--clock-control none --profile-from-start off python tools/train_one.py` (one eager step after two warm-up steps; per-launch times are "
        "serialised and cold-cache, so the SHARES are the evidence, not the sum: the graph-replayed step runs the two backbone streams "
        "concurrently).", "",
+       "NOTE: this capture was cut by its 900 s limit after the launches below (a full eager step is ~2 660 launches, see "
+       "`r02_train_launches_time_only.md`): the forward pass and roughly the first 70 % of the backward pass are in, the early-layer "
+       "(largest-map) BatchNorm-backward / wgrad launches at the end of the backward pass are missing, so the shares of `wgrad_kernel`, "
+       "`chan_partial_kernel<1>` and `bn_bwd_apply_kernel` are understated here.", "",
        f"{len(launch)} launches, {tot / 1e3:.2f} ms summed ({ours / 1e3:.2f} ms in libicaf_b200 kernels, {(tot - ours) / 1e3:.2f} ms in torch's: "
        "gradient accumulation at fan-outs, optimiser, GradScaler, copies).", "",
        "| kernel | launches | ms | share | avg us | DRAM GB (r+w) | DRAM TB/s | tensor pipe % (time-weighted) | SM throughput % |", "|---|---|---|---|---|---|---|---|---|"]
