@@ -55,8 +55,13 @@ def to_nchw(v: torch.Tensor) -> torch.Tensor:
 
 def _require_eval(m: nn.Module):
     if m.training:
-        raise NotImplementedError(f"{type(m).__name__}: training-mode forward is not built yet in icafusion_b200 "
-                                  "(call .eval()); there is no PyTorch fallback")
+        raise NotImplementedError(f"{type(m).__name__}: the NHWC `run` entry points are the inference path (folded BatchNorm, fused "
+                                  "epilogues); in train() call the module itself (forward) or icafusion_b200.autograd")
+
+
+def _train_nodes():
+    from . import autograd
+    return autograd
 
 
 def _dev_half(t: torch.Tensor) -> torch.Tensor:
@@ -141,6 +146,8 @@ class Conv(nn.Module):
             v = self.stage_image(x)
         else:
             v = to_nhwc(x)
+        if self.training and hasattr(self, "bn"):          # batch statistics + backward: the autograd node (common.py:56-57)
+            return to_nchw(_train_nodes().conv_bn_act(self, v, stem=v.shape[3] == 16 and self.is_s2d_stem()))
         return to_nchw(Conv.run([self], [v])[0])
 
     def fuseforward(self, x):
@@ -163,6 +170,8 @@ class Bottleneck(nn.Module):
         return Conv.run([m.cv2 for m in mods], h, outs, list(xs) if mods[0].add else None)   # residual fused in the epilogue
 
     def forward(self, x):
+        if self.training:
+            return to_nchw(_train_nodes().bottleneck(self, to_nhwc(x)))
         return to_nchw(Bottleneck.run([self], [to_nhwc(x)])[0])
 
 
@@ -211,6 +220,8 @@ class C3(nn.Module):
         return Conv.run([m.cv3 for m in mods], cats, outs)
 
     def forward(self, x):
+        if self.training:
+            return to_nchw(_train_nodes().c3(self, to_nhwc(x)))
         return to_nchw(C3.run([self], [to_nhwc(x)])[0])
 
 
@@ -237,6 +248,8 @@ class SPPF(nn.Module):
         return Conv.run([m.cv2 for m in mods], cats, outs)
 
     def forward(self, x):
+        if self.training:
+            return to_nchw(_train_nodes().sppf(self, to_nhwc(x)))
         return to_nchw(SPPF.run([self], [to_nhwc(x)])[0])
 
 
@@ -397,12 +410,14 @@ class CrossAttention(nn.Module):
     def forward(self, x, attention_mask=None, attention_weights=None):
         """Stand-alone call: x = [rgb_tokens, ir_tokens] (B, N, C) -> [out_vis, out_ir] (common.py:641-687).  Inside
         CrossTransformerBlock the output projection additionally carries the coefficient pair in its epilogue."""
-        _require_eval(self)
         if attention_mask is not None or attention_weights is not None:
             raise NotImplementedError("CrossAttention: attention_mask / attention_weights are unused by the reference forward")
         r, i = x
         B, N, C = r.shape
         r, i, n_pad = _pad_tokens(r, N), _pad_tokens(i, N), ops.round_up(N, 8)
+        if self.training:                                  # dropout on probabilities / outputs, autograd nodes
+            o_v, o_i = _train_nodes().cross_attention(self, r.view(B * n_pad, C), i.view(B * n_pad, C), B, N, n_pad)
+            return [o_v.view(B, n_pad, C)[:, :N], o_i.view(B, n_pad, C)[:, :N]]
         a_v, a_i, P = self.attend(r.view(B * n_pad, C), i.view(B * n_pad, C), B, N, n_pad)
         o_v, o_i = ops.linear([a_v, a_i], [P["out_vis"], P["out_ir"]])                     # common.py:683,685
         return [o_v.view(B, n_pad, C)[:, :N], o_i.view(B, n_pad, C)[:, :N]]
@@ -485,7 +500,11 @@ class CrossTransformerBlock(nn.Module):
     def forward(self, x):
         """x = [rgb_tokens, ir_tokens], each (B, N, C) like the reference (common.py:737-759)."""
         r, i = x
-        N = r.shape[1]
+        B, N, C = r.shape
+        if self.training:
+            n_pad = ops.round_up(N, 8)
+            r2, i2 = _train_nodes().cross_transformer_block(self, _pad_tokens(r, N).view(B * n_pad, C), _pad_tokens(i, N).view(B * n_pad, C), B, N, n_pad)
+            return [r2.view(B, n_pad, C)[:, :N], i2.view(B, n_pad, C)[:, :N]]
         r, i = self.run(_pad_tokens(r, N), _pad_tokens(i, N), N)
         return [r[:, :N], i[:, :N]]
 
@@ -546,4 +565,6 @@ class TransformerFusionBlock(nn.Module):
     def forward(self, x):
         rgb, ir = x
         assert rgb.shape[0] == ir.shape[0]
+        if self.training:                                  # dropout, nearest tail, batch-statistics BN: the autograd nodes
+            return to_nchw(_train_nodes().fusion_block(self, to_nhwc(rgb), to_nhwc(ir)))
         return to_nchw(self.run(to_nhwc(rgb), to_nhwc(ir)))

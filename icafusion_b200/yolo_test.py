@@ -71,7 +71,7 @@ class Detect(nn.Module):
     def run_level(self, i: int, v: torch.Tensor, z, logits, off: int):
         """One detection level: 1x1 conv (yolo_test.py:49) + decode (:50-63) into rows [off, off+na*ny*nx) of z/logits."""
         if self.training:
-            raise NotImplementedError("Detect: training-mode forward is not built yet in icafusion_b200")
+            raise NotImplementedError("Detect.run_level is the inference path (decode); in train() call Detect.forward / autograd.detect")
         ag = self.anchor_grid
         key = (ag.data_ptr(), ag._version, ag.device)
         cache = self.__dict__.get("_icaf_anchor_px")
@@ -89,6 +89,9 @@ class Detect(nn.Module):
         return z, logits, xs
 
     def forward(self, x):
+        if self.training:                                  # yolo_test.py:49-51: the raw maps only
+            from . import autograd
+            return autograd.detect(self, [to_nhwc(t) for t in x])
         z, logits, xs = self.run([to_nhwc(t) for t in x])
         for i in range(self.nl):
             x[i] = xs[i]                 # the reference overwrites its input list in place (yolo_test.py:49-51)

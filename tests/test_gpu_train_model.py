@@ -222,3 +222,42 @@ def test_graphed_train_step_equals_eager(cuda_device):
     print(f"[graphed step] worst relative parameter / buffer difference after 3 steps: {worst:.2e}")
     assert worst < 1e-3
     assert all(torch.equal(s0[k], s1[k]) for k in s0 if not s0[k].is_floating_point())      # num_batches_tracked
+
+
+def test_standalone_module_forwards_in_train_mode(cuda_device):
+    """The reference-shaped entry points (NCHW tensors / (B,N,C) token lists) of the operator classes in train(): same values as
+    the NHWC autograd nodes they wrap, and gradients reach the caller's tensors and the parameters."""
+    from icafusion_b200 import autograd as A
+    from icafusion_b200 import common
+    g = torch.Generator().manual_seed(4)
+    m = common.C3(64, 64, 1).to(cuda_device).train()
+    x = torch.randn(2, 64, 16, 24, generator=g).to(cuda_device).requires_grad_(True)
+    y = m(x)
+    assert tuple(y.shape) == (2, 64, 16, 24)
+    y.float().square().mean().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all() and float(x.grad.abs().max()) > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    m2 = common.C3(64, 64, 1).to(cuda_device).train()
+    m2.load_state_dict(m.state_dict())
+    y2 = A.c3(m2, x.detach().permute(0, 2, 3, 1).contiguous().half())
+    assert torch.equal(y2.permute(0, 3, 1, 2), y.detach())
+    # token-level classes, N not a multiple of 8 (padded internally), dropout active
+    blk = common.CrossTransformerBlock(128, 128, 128, 8, 4, 0.1, 0.1).to(cuda_device).train()
+    r = torch.randn(2, 100, 128, generator=g).to(cuda_device).requires_grad_(True)
+    i = torch.randn(2, 100, 128, generator=g).to(cuda_device).requires_grad_(True)
+    o_r, o_i = blk([r, i])
+    assert tuple(o_r.shape) == (2, 100, 128) and tuple(o_i.shape) == (2, 100, 128)
+    (o_r.float().sum() + o_i.float().square().sum()).backward()
+    assert torch.isfinite(r.grad).all() and torch.isfinite(i.grad).all() and float(i.grad.abs().max()) > 0
+    live = [k for k, p in blk.named_parameters() if p.grad is not None]
+    dead = [k for k, p in blk.named_parameters() if p.grad is None]
+    assert dead and all(k.split(".")[0] in ("ln_input", "ln_output", "mlp", "LN1") for k in dead), dead
+    assert all(torch.isfinite(dict(blk.named_parameters())[k].grad).all() for k in live)
+    att = common.CrossAttention(128, 128, 128, 8).to(cuda_device).train()
+    a_r, a_i = att([r.detach(), i.detach()])
+    assert tuple(a_r.shape) == (2, 100, 128) and torch.isfinite(a_r).all() and torch.isfinite(a_i).all()
+    det_in = [torch.randn(2, c, h, w, generator=g).to(cuda_device) for c, h, w in ((128, 8, 8), (256, 4, 4), (512, 2, 2))]
+    from icafusion_b200.yolo_test import Detect
+    det = Detect(1, ((10, 13, 16, 30, 33, 23), (30, 61, 62, 45, 59, 119), (116, 90, 156, 198, 373, 326)), (128, 256, 512)).to(cuda_device).train()
+    outs = det(det_in)
+    assert [tuple(o.shape) for o in outs] == [(2, 3, 8, 8, 6), (2, 3, 4, 4, 6), (2, 3, 2, 2, 6)]
