@@ -95,9 +95,13 @@ def test_cross_transformer_block_token_api(cuda_device):
     assert err(o_r, rr) < 2e-3 and err(o_i, ri) < 2e-3
 
 
-def test_training_mode_raises(cuda_device):
+def test_training_mode_takes_the_autograd_path(cuda_device):
+    """In train() the module's forward runs the training nodes (batch-statistics BN, dropout, nearest tail; parity in
+    tests/test_gpu_train_model.py); the fused inference entry point `run` refuses to run with training semantics pending."""
     from icafusion_b200 import TransformerFusionBlock
     blk = TransformerFusionBlock(128, 10, 10).to(cuda_device).train()
-    x = torch.randn(1, 128, 16, 20, device=cuda_device).half()
+    x = torch.randn(2, 128, 16, 20, device=cuda_device).half()
+    y = blk([x, x])
+    assert tuple(y.shape) == (2, 128, 16, 20) and y.requires_grad and torch.isfinite(y).all()
     with pytest.raises(NotImplementedError):
-        blk([x, x])
+        blk.run(x.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous())
