@@ -284,7 +284,7 @@ int icaf_bn_act_fwd(const void* x, const float* gamma, const float* beta, float*
                     float* save_invstd, int64_t rows, int C, float eps, float momentum, int act, float* workspace, size_t workspace_bytes,
                     void* stream);
 /* Its backward: dx (fp16) and dgamma / dbeta (fp32, (accumulate ? += : =) grad_scale * value; may be NULL).
- * workspace: icaf_train_workspace_bytes(C) + 2 C floats. */
+ * workspace: icaf_train_workspace_bytes(C) (it includes the per-channel coefficient block of the apply pass). */
 int icaf_bn_act_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
                     void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int act, float grad_scale, int accumulate, float* workspace,
                     size_t workspace_bytes, void* stream);

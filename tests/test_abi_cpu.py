@@ -174,3 +174,43 @@ def test_dispatcher_plan_matches_small_and_odd_geometries():
     bad = _lib.ConvGeom(1, 8, 8, 12, 8, 8, 16, 1, 1, 1, 0, 64, 32, 0, 0)
     assert L.icaf_conv2d_plan(ctypes.byref(bad), 1, 148, -1, ctypes.byref(_lib.ConvPlan())) == 2
     assert L.icaf_conv2d_plan(ctypes.byref(g), 1, 0, -1, ctypes.byref(_lib.ConvPlan())) == 1
+
+
+@pytest.mark.parametrize("size,B", [("s", 2), ("l", 16)])
+def test_training_step_dry_run_plans_every_geometry(size, B):
+    """The training step (train-mode forward + backward of the whole model) walked on `meta` tensors in the GPU-less container:
+    every convolution it issues -- forward filters and the flipped / transposed data-gradient filters over (zero-stuffed)
+    gradient maps -- plans cleanly in the dispatcher, every weight-gradient geometry is one icaf_conv2d_wgrad supports (the wrapper
+    raises when its host-side plan returns no workspace size), and exactly the reference's live parameters receive a gradient."""
+    from icafusion_b200 import Model, _lib, ops
+    L = _lib.lib()
+    m = Model(f"yolov5{size}_Transfusion_kaist").to("meta").train()
+    rgb = torch.empty(B, 3, 512, 640, dtype=torch.uint8, device="meta")
+    with ops.dry_run() as dr:
+        pred = m(rgb, rgb)
+        assert [tuple(p.shape) for p in pred] == [(B, 3, 64, 80, 6), (B, 3, 32, 40, 6), (B, 3, 16, 20, 6)]
+        torch.autograd.backward(pred, [torch.empty_like(p) for p in pred])
+    count = {}
+    seen = set()
+    for name, args, work in dr.records:
+        count[name] = count.get(name, 0) + 1
+        if name == "icaf_conv2d_fwd":
+            g, n = work["geom"], work["n_io"]
+            key = tuple(getattr(g, f) for f, _ in g._fields_) + (n,)
+            if key in seen:
+                continue
+            seen.add(key)
+            pl = _lib.ConvPlan()
+            rc = L.icaf_conv2d_plan(ctypes.byref(g), n, 148, -1, ctypes.byref(pl))
+            assert rc == 0, f"{work['tag']}: {L.icaf_last_error().decode()}"
+            _check_plan(g, n, pl, 148, work["tag"])
+    n_bn = sum(isinstance(x, torch.nn.BatchNorm2d) for x in m.modules())
+    assert count["icaf_bn_act_fwd"] == count["icaf_bn_act_bwd"] == n_bn
+    # one weight gradient per Conv / Detect conv / live Linear (the three q, k, v projections of a modality share one GEMM)
+    n_lin = sum(isinstance(x, torch.nn.Linear) for x in m.modules())
+    n_dmff = sum(type(x).__name__ == "CrossTransformerBlock" for x in m.modules())
+    assert count["icaf_conv2d_wgrad"] == n_bn + 3 + (n_lin - n_dmff * (2 + 6)) + 2 * n_dmff
+    assert count["icaf_cross_attention_train"] == count["icaf_cross_attention_bwd"] == 3
+    dead = sorted(k for k, p in m.named_parameters() if p.grad is None)
+    from icafusion_b200.trainer import dead_parameters
+    assert dead == sorted(dead_parameters(m)) and len(dead) == 30
