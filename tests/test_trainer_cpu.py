@@ -33,62 +33,65 @@ def test_dead_parameters_and_groups_match_the_reference():
     assert all(k.split(".")[-1] in ("pos_emb_vis", "pos_emb_ir", "w1", "w2") for k in left_out) and len(left_out) == 3 * 6
 
 
-def _worker(rank, world, port, freeze, q):
+def _scenario(rank, world, freeze):
+    from icafusion_b200 import Model
+    from icafusion_b200 import trainer
+    model = Model("yolov5s_Transfusion_kaist")
+    keep = trainer.freeze_dead_parameters
+    if not freeze:
+        trainer.freeze_dead_parameters = lambda m: []                      # the reference as written (train.py:233)
+    try:
+        ts = trainer.TrainStep(model, None, total_batch_size=4, world_size=world, local_rank=None, imgsz=320)
+    finally:
+        trainer.freeze_dead_parameters = keep
+    live = [p for p in model.parameters() if p.requires_grad]
+    dead = set(trainer.dead_parameters(model))
+    used = [p for k, p in model.named_parameters() if k not in dead]
+
+    def stand_in(rgb, ir):                                                 # touches exactly what the real forward touches
+        return sum(p.sum() for p in used) * float(rank + 1)
+    model.forward = stand_in
+    try:
+        for _ in range(2):                                                 # the reference's DDP failure shows up in iteration 2
+            loss = ts.model(None, None) * world                            # train.py:339
+            loss.backward()
+            g = [p.grad.clone() for p in live if p.grad is not None]
+            ts.zero_grad()
+    except RuntimeError as e:
+        return ("error", str(e)[:80])
+    # mean over ranks of world * (rank + 1) = world * (world + 1) / 2 for every element
+    want = world * (world + 1) / 2
+    bad = [(float(x.min()), float(x.max())) for x in g if not torch.allclose(x, torch.full_like(x, want))]
+    return ("ok", (len(bad), len(g), len(live), bad[:3]))
+
+
+def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from icafusion_b200 import Model
-        from icafusion_b200 import trainer
-        model = Model("yolov5s_Transfusion_kaist")
-        if not freeze:
-            trainer.freeze_dead_parameters = lambda m: []                  # the reference as written (train.py:233)
-        ts = trainer.TrainStep(model, None, total_batch_size=4, world_size=world, local_rank=None, imgsz=320)
-        live = [p for p in model.parameters() if p.requires_grad]
-        dead = set(trainer.dead_parameters(model))
-        used = [p for k, p in model.named_parameters() if k not in dead]
-
-        def stand_in(rgb, ir):                                             # touches exactly what the real forward touches
-            return sum(p.sum() for p in used) * float(rank + 1)
-        model.forward = stand_in
-        err = None
-        try:
-            for _ in range(2):                                             # the reference's DDP failure shows up in iteration 2
-                loss = ts.model(None, None) * world                        # train.py:339
-                loss.backward()
-                g = [p.grad.clone() for p in live if p.grad is not None]
-                ts.zero_grad()
-        except RuntimeError as e:
-            err = str(e)
+        res = [_scenario(rank, world, True), _scenario(rank, world, False)]
         if rank == 0:
-            if err is not None:
-                q.put(("error", err[:80]))
-            else:
-                # mean over ranks of world * (rank + 1) = world * (world + 1) / 2 for every element
-                want = world * (world + 1) / 2
-                bad = [(float(x.min()), float(x.max())) for x in g if not torch.allclose(x, torch.full_like(x, want))]
-                q.put(("ok", (len(bad), len(g), len(live), bad[:3])))
+            q.put(res)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("freeze", [True, False])
-def test_ddp_world2_gradient_average_and_dead_parameter_repair(freeze):
+def test_ddp_world2_gradient_average_and_dead_parameter_repair():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, freeze, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(300)
+        p.join(400)
         assert p.exitcode == 0
-    kind, val = q.get(timeout=5)
-    if freeze:
-        assert kind == "ok" and val[0] == 0 and val[1] == val[2], val
-    else:       # without the repair DDP refuses the second iteration: parameters that never got a gradient
-        assert kind == "error" and "Expected to have finished reduction" in val
+    (kind, val), (kind2, val2) = q.get(timeout=5)
+    assert kind == "ok" and val[0] == 0 and val[1] == val[2], val          # repaired: averaged gradients on every live parameter
+    # without the repair DDP refuses the second iteration: parameters that never got a gradient
+    assert kind2 == "error" and "Expected to have finished reduction" in val2, (kind2, val2)
 
 
 def test_model_ema_matches_the_reference_loop():
