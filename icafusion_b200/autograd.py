@@ -510,32 +510,31 @@ def _walk(model, rgb_img, ir_img, taps):
 
 
 def _layer(model, m, x, y, rgb_img, ir_img, Conv, C3, SPPF, Concat, TransformerFusionBlock, Detect):
-    if True:
-        stem = False
-        if m.f == -4 or x is None:                                # image stems: RGB is the first layer, IR enters at f == -4
-            img = ir_img if m.f == -4 else rgb_img
-            x = model._stage(img, m)
-            stem = isinstance(m, Conv) and m.is_s2d_stem()
-            if not stem:
-                raise NotImplementedError("training: the image stem must be the 6x6 / stride 2 Conv of the yolov5 YAMLs")
-        elif m.f != -1:
-            x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
-        if isinstance(m, Conv):
-            x = conv_bn_act(m, x, stem)
-        elif isinstance(m, C3):
-            x = c3(m, x)
-        elif isinstance(m, SPPF):
-            x = sppf(m, x)
-        elif isinstance(m, nn.Upsample):
-            if m.mode != "nearest" or m.scale_factor is None or float(m.scale_factor) != 2.0:
-                raise NotImplementedError("Upsample: only nearest x2 is supported")
-            x = Upsample2xFn.apply(x)
-        elif isinstance(m, Concat):
-            x = ConcatFn.apply(*x)
-        elif isinstance(m, TransformerFusionBlock):
-            x = fusion_block(m, x[0], x[1])
-        elif isinstance(m, Detect):
-            x = detect(m, x)
-        else:
-            raise NotImplementedError(type(m).__name__)
+    stem = False
+    if m.f == -4 or x is None:                                # image stems: RGB is the first layer, IR enters at f == -4
+        img = ir_img if m.f == -4 else rgb_img
+        x = model._stage(img, m)
+        stem = isinstance(m, Conv) and m.is_s2d_stem()
+        if not stem:
+            raise NotImplementedError("training: the image stem must be the 6x6 / stride 2 Conv of the yolov5 YAMLs")
+    elif m.f != -1:
+        x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+    if isinstance(m, Conv):
+        x = conv_bn_act(m, x, stem)
+    elif isinstance(m, C3):
+        x = c3(m, x)
+    elif isinstance(m, SPPF):
+        x = sppf(m, x)
+    elif isinstance(m, nn.Upsample):
+        if m.mode != "nearest" or m.scale_factor is None or float(m.scale_factor) != 2.0:
+            raise NotImplementedError("Upsample: only nearest x2 is supported")
+        x = Upsample2xFn.apply(x)
+    elif isinstance(m, Concat):
+        x = ConcatFn.apply(*x)
+    elif isinstance(m, TransformerFusionBlock):
+        x = fusion_block(m, x[0], x[1])
+    elif isinstance(m, Detect):
+        x = detect(m, x)
+    else:
+        raise NotImplementedError(type(m).__name__)
     return x

@@ -119,6 +119,5 @@ class _LossFn(torch.autograd.Function):
                 dps.append(buf.as_strided(t.shape, t.stride()))
         else:
             dps = [torch.empty_like(t) for t in ps]
-        crit.with_backward = True
         crit._launch(ps, p_ld, ctx.tg, ws=ctx.ws, grad_out=g, dps=dps)
         return (None, None) + tuple(dps)
