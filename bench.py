@@ -437,11 +437,19 @@ def _measure_train(args, wl, K, Wm, dev, world, rank, local):
     summ = {}
     if rank == 0:
         torch.cuda.synchronize()
-    with ops.profile() as prof:
-        torch.cuda._sleep(int(4e8))       # ~0.2 s spin: the step's launches queue up behind it and then run back to back
-        prof.mark()
-        ts(rgb_d, ir_d, tg_d)
-        torch.cuda.synchronize()
+    prev_streams = os.environ.get("ICAF_TRAIN_STREAMS")
+    os.environ["ICAF_TRAIN_STREAMS"] = "0"   # the event chain attributes a launch to the gap since the previous one: one stream only
+    try:
+        with ops.profile() as prof:
+            torch.cuda._sleep(int(4e8))   # ~0.2 s spin: the step's launches queue up behind it and then run back to back
+            prof.mark()
+            ts(rgb_d, ir_d, tg_d)
+            torch.cuda.synchronize()
+    finally:
+        if prev_streams is None:
+            os.environ.pop("ICAF_TRAIN_STREAMS", None)
+        else:
+            os.environ["ICAF_TRAIN_STREAMS"] = prev_streams
     for name, v in prof.summary().items():
         summ[name] = {"launches": v["launches"], "ms": round(v["ms"], 3), "tflops": round(v["flops"] / max(v["ms"], 1e-6) / 1e9, 1)}
     # the same step with forward + loss + backward (+ DDP all-reduce) replayed from one CUDA graph
