@@ -214,3 +214,48 @@ def test_training_step_dry_run_plans_every_geometry(size, B):
     dead = sorted(k for k, p in m.named_parameters() if p.grad is None)
     from icafusion_b200.trainer import dead_parameters
     assert dead == sorted(dead_parameters(m)) and len(dead) == 30
+
+
+def test_training_entry_points_validate_arguments_without_a_gpu():
+    """The backward / training entry points reject bad arguments on the host, before any CUDA call (return code + readable
+    icaf_last_error), and their workspace-size queries are pure functions."""
+    from icafusion_b200 import _lib
+    L = _lib.lib()
+    P = ctypes.c_void_p
+    one = P(16)                                   # a non-null pointer that is never dereferenced: validation fails first
+    assert L.icaf_train_workspace_bytes(64) > 0 and L.icaf_train_workspace_bytes(256) == 4 * L.icaf_train_workspace_bytes(64)
+    # BatchNorm: C not a multiple of 8 / workspace too small
+    assert L.icaf_bn_act_fwd(one, one, one, None, None, one, one, one, 100, 12, 1e-3, 0.03, 1, one, 1 << 30, None) == 1
+    assert L.icaf_bn_act_fwd(one, one, one, None, None, one, one, one, 100, 64, 1e-3, 0.03, 1, one, 16, None) == 1
+    assert b"workspace" in L.icaf_last_error()
+    assert L.icaf_bn_act_bwd(one, one, one, one, one, one, one, None, None, 100, 64, 1, 1.0, 0, one, 16, None) == 1
+    # attention backward: head dim 24 is not built; dropout probability must be < 1
+    ws = L.icaf_cross_attention_bwd_workspace_bytes(2, 104, 8)
+    assert ws == 2 * 2 * 8 * 104 * 2 * 4
+    assert L.icaf_cross_attention_bwd(one, one, one, one, one, one, one, one, 2, 100, 104, 192, 8, 0.0, 0, one, ws, None) == 2
+    assert L.icaf_cross_attention_bwd(one, one, one, one, one, one, one, one, 2, 100, 104, 256, 8, 1.0, 0, one, ws, None) == 1
+    assert L.icaf_cross_attention_train(one, one, one, one, 2, 100, 104, 256, 8, 1.5, 0, None) == 1
+    # weight gradient: unsupported channel count -> no workspace size, and the call itself refuses
+    bad = _lib.ConvGeom(1, 16, 16, 24, 16, 16, 64, 3, 3, 1, 1, 256, 64, 0, 0)          # Cin = 24
+    assert L.icaf_conv2d_wgrad_workspace_bytes(ctypes.byref(bad)) == 0
+    good = _lib.ConvGeom(2, 16, 16, 64, 16, 16, 64, 3, 3, 1, 1, 576, 64, 0, 0)
+    need = L.icaf_conv2d_wgrad_workspace_bytes(ctypes.byref(good))
+    assert need > 0
+    assert L.icaf_conv2d_wgrad(ctypes.byref(good), one, 64, one, 64, one, 1.0, 0, one, need - 1, None) != 0
+    # filter packing: padded sizes smaller than the filter
+    assert L.icaf_pack_weight(one, 64, 64, 3, 3, 64, 32, 576, 0, one, None) == 1
+    assert L.icaf_pack_weight_pair(one, 64, 64, 3, 3, 64, 576, one, 64, 64, 512, one, None) == 1
+    # DMFF tail backward exists for the training-mode (nearest) tail only
+    assert L.icaf_dmff_upsample_cat_bwd(one, 256, one, one, 1, 16, 16, 128, 8, 8, 64, 0, None) == 2
+    assert L.icaf_dmff_pool_tokens_bwd(one, one, 128, one, one, one, one, one, 1, 16, 16, 128, 8, 8, 64, one, 8, None) == 1
+    assert L.icaf_maxpool5_bwd(one, one, one, 1, 8, 8, 64, one, 8, None) == 1
+    # loss backward: needs the backward workspace (no_bwd = no) and a gradient pointer
+    ny, nx = (ctypes.c_int * 3)(8, 4, 2), (ctypes.c_int * 3)(8, 4, 2)
+    w_f, w_b = L.icaf_loss_workspace_bytes(2, 3, 4, ny, nx, 3, 0), L.icaf_loss_workspace_bytes(2, 3, 4, ny, nx, 3, 6)
+    assert 0 < w_f < w_b
+    ptrs = (ctypes.c_void_p * 3)(16, 16, 16)
+    anch = (ctypes.c_float * 18)(*([1.0] * 18))
+    hyp = _lib.LossHyp(0.05, 1.0, 0.5, 1.0, 1.0, 4.0, 0.0, 1.0, 1.0, 0.0, (ctypes.c_float * 5)(4.0, 1.0, 0.4, 0.0, 0.0))
+    assert L.icaf_compute_loss_bwd(ptrs, 0, 0, ny, nx, 3, 2, 3, 6, one, 4, anch, ctypes.byref(hyp), None, ptrs, one, w_b, None) == 1
+    assert L.icaf_compute_loss_bwd(ptrs, 0, 0, ny, nx, 3, 2, 3, 6, one, 4, anch, ctypes.byref(hyp), one, ptrs, P(256), w_f, None) == 1
+    assert L.icaf_set_seed_offset(None) == 0
